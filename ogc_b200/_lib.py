@@ -1,0 +1,67 @@
+"""ctypes binding of libogc_b200.so -- the C ABI declared in include/ogc_b200.h.
+
+The library is hand-written sm_100a CUDA; there is NO fallback.  If it is missing, or a call
+is made with non-CUDA tensors, we raise: a silent CPU/eager path would void every parity and
+performance claim of this repository.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libogc_b200.so")
+
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+_F = ctypes.c_float
+
+# name -> argtypes; every function returns int (0 ok, <0 ogc_status, >0 cudaError_t)
+SIGNATURES = {
+    "ogc_furthest_point_sampling": [_I, _I, _I, _P, _P, _P, _P],
+    "ogc_gather_points": [_I, _I, _I, _I, _P, _P, _P, _P],
+    "ogc_gather_points_grad": [_I, _I, _I, _I, _P, _P, _P, _P],
+    "ogc_knn": [_I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "ogc_knn_sqrt": [_I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "ogc_three_nn": [_I, _I, _I, _P, _P, _P, _P, _P],
+    "ogc_three_interpolate": [_I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "ogc_three_interpolate_grad": [_I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "ogc_group_points": [_I, _I, _I, _I, _I, _P, _P, _P, _P],
+    "ogc_group_points_grad": [_I, _I, _I, _I, _I, _P, _P, _P, _P],
+    "ogc_ball_query": [_I, _I, _I, _F, _I, _P, _P, _P, _P],
+}
+
+_lib = None
+
+
+class OgcLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libogc_b200.so once; raise loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OgcLibraryError(
+            f"{LIB_PATH} not found. Build it with `python -m ogc_b200.build` "
+            "(or __graft_entry__.build()). There is no CPU / eager fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError = header / library mismatch: fail loudly
+        fn.argtypes = argtypes
+        fn.restype = _I
+    lib.ogc_version.restype = ctypes.c_char_p
+    lib.ogc_version.argtypes = []
+    _lib = lib
+    return lib
+
+
+_STATUS = {-1: "OGC_ERR_INVALID_ARG", -2: "OGC_ERR_UNSUPPORTED", -3: "OGC_ERR_WORKSPACE"}
+
+
+def check(rc: int, what: str):
+    if rc == 0:
+        return
+    if rc < 0:
+        raise ValueError(f"{what}: {_STATUS.get(rc, rc)}")
+    raise RuntimeError(f"{what}: CUDA error {rc}")

@@ -1,0 +1,233 @@
+"""Operator back-ends behind `pointnet2.pointnet2`.
+
+`B200Backend` is the product: it allocates outputs with torch (caching allocator), passes raw
+device pointers + the CURRENT CUDA stream to the C ABI of libogc_b200.so (include/ogc_b200.h) and
+never synchronises.  Method set = the ten native entry points of the reference's
+`pointnet2_cuda` module (pointnet2/src/pointnet2_api.cpp:10-25), with allocation folded in.
+
+`set_backend()` is the seam tests use to run the same operator layer on the CPU oracle or on the
+reference extension; product code never imports `oracle/`.
+"""
+import ctypes
+from contextlib import contextmanager
+
+import torch
+
+from . import _lib
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk_f32(t, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise RuntimeError(f"ogc_b200: `{name}` must be a CUDA tensor (no CPU fallback exists); got "
+                           f"{t.device if isinstance(t, torch.Tensor) else type(t)}")
+    if t.dtype != torch.float32:
+        raise ValueError(f"ogc_b200: `{name}` must be float32, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"ogc_b200: `{name}` must be contiguous")
+
+
+def _chk_i32(t, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise RuntimeError(f"ogc_b200: `{name}` must be a CUDA tensor (no CPU fallback exists)")
+    if t.dtype != torch.int32:
+        raise ValueError(f"ogc_b200: `{name}` must be int32, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"ogc_b200: `{name}` must be contiguous")
+
+
+class OpTimer:
+    """Optional per-op CUDA-event timing on the launching stream (used by bench.py for the
+    roofline block).  Disabled by default: zero overhead beyond one attribute test."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []  # (name, start_event, end_event, algorithmic_bytes)
+
+    @contextmanager
+    def span(self, name, nbytes):
+        if not self.enabled:
+            yield
+            return
+        s = torch.cuda.Event(enable_timing=True)
+        e = torch.cuda.Event(enable_timing=True)
+        s.record()
+        yield
+        e.record()
+        self.records.append((name, s, e, nbytes))
+
+    def summary(self):
+        """{name: {"calls", "ms", "bytes"}} -- call after torch.cuda.synchronize()."""
+        out = {}
+        for name, s, e, nb in self.records:
+            d = out.setdefault(name, {"calls": 0, "ms": 0.0, "bytes": 0})
+            d["calls"] += 1
+            d["ms"] += s.elapsed_time(e)
+            d["bytes"] += nb
+        return out
+
+    def reset(self):
+        self.records = []
+
+
+TIMER = OpTimer()
+
+
+class B200Backend:
+    name = "b200"
+
+    def __init__(self):
+        self.lib = _lib.load()  # raises if the extension is missing
+        self.launches = 0       # number of libogc_b200 kernels launched (bench.py's gpu_launches)
+
+    # ---- K1 ------------------------------------------------------------------------------
+    def fps(self, xyz, npoint):
+        _chk_f32(xyz, "xyz")
+        B, N, _ = xyz.shape
+        out = torch.empty(B, npoint, dtype=torch.int32, device=xyz.device)
+        temp = torch.empty(B, N, dtype=torch.float32, device=xyz.device) if N > 16384 else None
+        with TIMER.span("fps", B * (12 * N + 4 * npoint)):
+            _lib.check(self.lib.ogc_furthest_point_sampling(B, N, npoint, _ptr(xyz), _ptr(temp), _ptr(out),
+                                                            _stream()), "ogc_furthest_point_sampling")
+        self.launches += 1
+        return out
+
+    # ---- K4 / K5 ---------------------------------------------------------------------------
+    def knn(self, k, unknown, known, sqrt=False):
+        _chk_f32(unknown, "unknown")
+        _chk_f32(known, "known")
+        B, n, _ = unknown.shape
+        m = known.shape[1]
+        d = torch.empty(B, n, k, dtype=torch.float32, device=unknown.device)
+        idx = torch.empty(B, n, k, dtype=torch.int32, device=unknown.device)
+        fn = self.lib.ogc_knn_sqrt if sqrt else self.lib.ogc_knn
+        with TIMER.span("knn", B * (12 * (n + m) + 8 * n * k)):
+            _lib.check(fn(B, n, m, k, _ptr(unknown), _ptr(known), _ptr(d), _ptr(idx), _stream()), "ogc_knn")
+        self.launches += 1
+        return d, idx
+
+    def three_nn(self, unknown, known):
+        _chk_f32(unknown, "unknown")
+        _chk_f32(known, "known")
+        B, n, _ = unknown.shape
+        m = known.shape[1]
+        d2 = torch.empty(B, n, 3, dtype=torch.float32, device=unknown.device)
+        idx = torch.empty(B, n, 3, dtype=torch.int32, device=unknown.device)
+        with TIMER.span("three_nn", B * (12 * (n + m) + 24 * n)):
+            _lib.check(self.lib.ogc_three_nn(B, n, m, _ptr(unknown), _ptr(known), _ptr(d2), _ptr(idx), _stream()),
+                       "ogc_three_nn")
+        self.launches += 1
+        return d2, idx
+
+    # ---- K6 / K7 ---------------------------------------------------------------------------
+    def three_interpolate(self, features, idx, weight):
+        _chk_f32(features, "features")
+        _chk_i32(idx, "idx")
+        _chk_f32(weight, "weight")
+        B, c, m = features.shape
+        n = idx.shape[1]
+        out = torch.empty(B, c, n, dtype=torch.float32, device=features.device)
+        with TIMER.span("three_interpolate", B * (4 * c * m + 24 * n + 4 * c * n)):
+            _lib.check(self.lib.ogc_three_interpolate(B, c, m, n, _ptr(features), _ptr(idx), _ptr(weight),
+                                                      _ptr(out), _stream()), "ogc_three_interpolate")
+        self.launches += 1
+        return out
+
+    def three_interpolate_grad(self, grad_out, idx, weight, m):
+        _chk_f32(grad_out, "grad_out")
+        _chk_i32(idx, "idx")
+        _chk_f32(weight, "weight")
+        B, c, n = grad_out.shape
+        g = torch.zeros(B, c, m, dtype=torch.float32, device=grad_out.device)
+        with TIMER.span("three_interpolate_grad", B * (4 * c * m + 24 * n + 4 * c * n)):
+            _lib.check(self.lib.ogc_three_interpolate_grad(B, c, n, m, _ptr(grad_out), _ptr(idx), _ptr(weight),
+                                                           _ptr(g), _stream()), "ogc_three_interpolate_grad")
+        self.launches += 1
+        return g
+
+    # ---- K8 / K9 ---------------------------------------------------------------------------
+    def group_points(self, features, idx):
+        _chk_f32(features, "features")
+        _chk_i32(idx, "idx")
+        B, C, N = features.shape
+        _, M, S = idx.shape
+        out = torch.empty(B, C, M, S, dtype=torch.float32, device=features.device)
+        with TIMER.span("group_points", B * (4 * C * N + 4 * M * S + 4 * C * M * S)):
+            _lib.check(self.lib.ogc_group_points(B, C, N, M, S, _ptr(features), _ptr(idx), _ptr(out), _stream()),
+                       "ogc_group_points")
+        self.launches += 1
+        return out
+
+    def group_points_grad(self, grad_out, idx, N):
+        _chk_f32(grad_out, "grad_out")
+        _chk_i32(idx, "idx")
+        B, C, M, S = grad_out.shape
+        g = torch.zeros(B, C, N, dtype=torch.float32, device=grad_out.device)
+        with TIMER.span("group_points_grad", B * (4 * C * N + 4 * M * S + 4 * C * M * S)):
+            _lib.check(self.lib.ogc_group_points_grad(B, C, N, M, S, _ptr(grad_out), _ptr(idx), _ptr(g),
+                                                      _stream()), "ogc_group_points_grad")
+        self.launches += 1
+        return g
+
+    # ---- K2 / K3 ---------------------------------------------------------------------------
+    def gather_points(self, features, idx):
+        _chk_f32(features, "features")
+        _chk_i32(idx, "idx")
+        B, C, N = features.shape
+        M = idx.shape[1]
+        out = torch.empty(B, C, M, dtype=torch.float32, device=features.device)
+        with TIMER.span("gather_points", B * (4 * C * N + 4 * M + 4 * C * M)):
+            _lib.check(self.lib.ogc_gather_points(B, C, N, M, _ptr(features), _ptr(idx), _ptr(out), _stream()),
+                       "ogc_gather_points")
+        self.launches += 1
+        return out
+
+    def gather_points_grad(self, grad_out, idx, N):
+        _chk_f32(grad_out, "grad_out")
+        _chk_i32(idx, "idx")
+        B, C, M = grad_out.shape
+        g = torch.zeros(B, C, N, dtype=torch.float32, device=grad_out.device)
+        with TIMER.span("gather_points_grad", B * (4 * C * N + 4 * M + 4 * C * M)):
+            _lib.check(self.lib.ogc_gather_points_grad(B, C, N, M, _ptr(grad_out), _ptr(idx), _ptr(g), _stream()),
+                       "ogc_gather_points_grad")
+        self.launches += 1
+        return g
+
+    # ---- K10 -------------------------------------------------------------------------------
+    def ball_query(self, radius, nsample, xyz, new_xyz):
+        _chk_f32(xyz, "xyz")
+        _chk_f32(new_xyz, "new_xyz")
+        B, N, _ = xyz.shape
+        M = new_xyz.shape[1]
+        idx = torch.empty(B, M, nsample, dtype=torch.int32, device=xyz.device)
+        with TIMER.span("ball_query", B * (12 * (N + M) + 4 * M * nsample)):
+            _lib.check(self.lib.ogc_ball_query(B, N, M, float(radius), nsample, _ptr(new_xyz), _ptr(xyz), _ptr(idx),
+                                               _stream()), "ogc_ball_query")
+        self.launches += 1
+        return idx
+
+
+_backend = None
+
+
+def get_backend():
+    """The active back-end; the B200 library is loaded on first use and its absence is fatal."""
+    global _backend
+    if _backend is None:
+        _backend = B200Backend()
+    return _backend
+
+
+def set_backend(backend):
+    """Install another back-end object (tests: CPU oracle / reference extension). Returns the previous one."""
+    global _backend
+    prev = _backend
+    _backend = backend
+    return prev
