@@ -116,6 +116,70 @@ OGC_API int ogc_group_points_grad(int b, int c, int n, int npoints, int nsample,
 OGC_API int ogc_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz,
                    const float *xyz, int *idx, void *stream);
 
+/* =======================================================================================
+ * Fused OGC-loss entry points.  These replace torch-level code of the reference (there is no
+ * reference CUDA kernel for them); each cites the Python it restates.  K = n_slot <= 32.
+ * ===================================================================================== */
+
+/* Per-segment weighted Kabsch: replaces fit_motion_svd_batch(pc1, pc2, mask)
+ * losses/seg_loss_unsup.py:10-61 for the call pattern of DynamicLoss (:81-87), weighted_kabsch
+ * (oa_icp.py:16-38) and object_aware_icp (oa_icp.py:77-79), where pc1/pc2 are one cloud repeated
+ * over the K segments.
+ *   pc (b,n,3); second (b,n,3) = flow (second_is_flow=1: pc2 = pc + flow) or pc2 itself;
+ *   mask (b,n,k) soft assignment  ->  Rt (b,k,12): R (3x3 row-major) then t (3).
+ *   Segments whose covariance contains NaN get R = I, t = 0 (:40-42,58-59). */
+OGC_API int ogc_weighted_kabsch(int b, int n, int k, int second_is_flow, const float *pc,
+                                const float *second, const float *mask, float *Rt, void *stream);
+
+/* DynamicLoss.forward + backward: losses/seg_loss_unsup.py:72-98.
+ *   loss_pt (b,n) = || sum_k m_k (R_k p + t_k) - (p + flow) ||_2   (the caller takes the mean)
+ *   grad_mask (b,n,k) = d (sum_n loss_pt) / d mask with R,t constant (they are .detach()ed, :91);
+ *   may be NULL.  Rt (b,k,12) optional output. */
+OGC_API int ogc_dynamic_loss(int b, int n, int k, const float *pc, const float *flow, const float *mask,
+                             float *loss_pt, float *grad_mask, float *Rt, void *stream);
+
+/* flow_out (b,n,3) = sum_k m_k (R_k p + t_k) - p      oa_icp.py:33-38, :80-83 */
+OGC_API int ogc_apply_rigid_flow(int b, int n, int k, const float *pc, const float *mask, const float *Rt,
+                                 float *flow_out, void *stream);
+
+/* KnnLoss / BallQLoss with loss_norm = 1: losses/seg_loss_unsup.py:112-129, :143-158, forward +
+ * backward.  mask (b,n,k); idx (b,n,nsample) neighbour indices; dist (b,n,nsample) = sqrt'ed k-NN
+ * distances or NULL: when given, neighbours with dist > radius are replaced by idx[.,.,0] (:121-122).
+ *   loss_pt (b,n) = mean_s sum_c | m[n,c] - m[nbr(n,s),c] |      (may be NULL)
+ *   grad_mask (b,n,k) += coef * d (sum_n loss_pt) / d mask       (ACCUMULATES; may be NULL) */
+OGC_API int ogc_neighbor_l1(int b, int n, int k, int nsample, const float *mask, const int *idx,
+                            const float *dist, float radius, float coef, float *loss_pt, float *grad_mask,
+                            void *stream);
+
+/* match_mask_by_iou's hard-assignment statistics: losses/seg_loss_unsup.py:221-232.
+ *   inter (b,k,k) int32 += #{n : argmax mask1[n] = g, argmax mask2[n] = p}   (ACCUMULATES: zero it first)
+ *   intersection = inter, segment sizes = its row / column sums, so the caller forms the IoU. */
+OGC_API int ogc_mask_contingency(int b, int n, int k, const float *mask1, const float *mask2, int *inter,
+                                 void *stream);
+
+/* InvarianceLoss.forward + backward given the Hungarian matches: losses/seg_loss_unsup.py:252-280.
+ *   perm12 (b,k): column of mask2 matched to slot i of mask1 (scipy col_ind); perm21 the converse.
+ *   loss_pt (b,n) = ||m1 - m2[perm12]||_2 + ||m2 - m1[perm21]||_2 ; grad1/grad2 (b,n,k) the gradients
+ *   of sum_n loss_pt w.r.t. mask1 / mask2 (targets are constants). */
+OGC_API int ogc_invariance_loss(int b, int n, int k, const float *mask1, const float *mask2, const int *perm12,
+                                const int *perm21, float *loss_pt, float *grad1, float *grad2, void *stream);
+
+/* =======================================================================================
+ * Training-step plumbing on one flat fp32 buffer (data-parallel step).
+ * ===================================================================================== */
+
+/* counter[0] += (number of warps that saw a NaN in grad[0..n)); replaces the per-parameter
+ * `torch.any(torch.isnan(param.grad))` scan of train_seg.py:81-83 without a host sync. */
+OGC_API int ogc_count_nan(long long n, const float *grad, float *counter, void *stream);
+
+/* torch.optim.Adam step (train_seg.py:85, :328) over flat buffers: g = grad*grad_scale (+ wd*p);
+ * m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps).
+ * `step` = t >= 1.  If skip_counter != NULL and *skip_counter != 0 nothing is updated (the
+ * reference returns before optimizer.step() when a gradient holds a NaN). */
+OGC_API int ogc_adam_step(long long n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq,
+                          float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                          float grad_scale, const float *skip_counter, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libogc_b200.so")
 _P = ctypes.c_void_p
 _I = ctypes.c_int
 _F = ctypes.c_float
+_LL = ctypes.c_longlong
 
 # name -> argtypes; every function returns int (0 ok, <0 ogc_status, >0 cudaError_t)
 SIGNATURES = {
@@ -27,6 +28,14 @@ SIGNATURES = {
     "ogc_group_points": [_I, _I, _I, _I, _I, _P, _P, _P, _P],
     "ogc_group_points_grad": [_I, _I, _I, _I, _I, _P, _P, _P, _P],
     "ogc_ball_query": [_I, _I, _I, _F, _I, _P, _P, _P, _P],
+    "ogc_weighted_kabsch": [_I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "ogc_dynamic_loss": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+    "ogc_apply_rigid_flow": [_I, _I, _I, _P, _P, _P, _P, _P],
+    "ogc_neighbor_l1": [_I, _I, _I, _I, _P, _P, _P, _F, _F, _P, _P, _P],
+    "ogc_mask_contingency": [_I, _I, _I, _P, _P, _P, _P],
+    "ogc_invariance_loss": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
+    "ogc_count_nan": [_LL, _P, _P, _P],
+    "ogc_adam_step": [_LL, _P, _P, _P, _P, _F, _F, _F, _F, _F, _I, _F, _P, _P],
 }
 
 _lib = None

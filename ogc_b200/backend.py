@@ -213,6 +213,79 @@ class B200Backend:
         self.launches += 1
         return idx
 
+    # ---- fused OGC-loss kernels (csrc/losses.cu) -------------------------------------------
+    def weighted_kabsch(self, pc, second, mask, second_is_flow=True):
+        """pc, second (B,N,3), mask (B,N,K) -> Rt (B,K,12) = [R row-major | t]."""
+        _chk_f32(pc, "pc"); _chk_f32(second, "second"); _chk_f32(mask, "mask")
+        B, N, K = mask.shape
+        Rt = torch.empty(B, K, 12, dtype=torch.float32, device=pc.device)
+        with TIMER.span("weighted_kabsch", B * N * (24 + 4 * K) * 2):
+            _lib.check(self.lib.ogc_weighted_kabsch(B, N, K, int(bool(second_is_flow)), _ptr(pc), _ptr(second),
+                                                    _ptr(mask), _ptr(Rt), _stream()), "ogc_weighted_kabsch")
+        self.launches += 1
+        return Rt
+
+    def dynamic_loss(self, pc, flow, mask, need_grad=True):
+        """-> loss_pt (B,N), grad_mask (B,N,K) or None, Rt (B,K,12)."""
+        _chk_f32(pc, "pc"); _chk_f32(flow, "flow"); _chk_f32(mask, "mask")
+        B, N, K = mask.shape
+        loss_pt = torch.empty(B, N, dtype=torch.float32, device=pc.device)
+        grad = torch.empty(B, N, K, dtype=torch.float32, device=pc.device) if need_grad else None
+        Rt = torch.empty(B, K, 12, dtype=torch.float32, device=pc.device)
+        with TIMER.span("dynamic_loss", B * N * ((24 + 4 * K) * 3 + 4 + 4 * K)):
+            _lib.check(self.lib.ogc_dynamic_loss(B, N, K, _ptr(pc), _ptr(flow), _ptr(mask), _ptr(loss_pt),
+                                                 _ptr(grad), _ptr(Rt), _stream()), "ogc_dynamic_loss")
+        self.launches += 1
+        return loss_pt, grad, Rt
+
+    def apply_rigid_flow(self, pc, mask, Rt):
+        _chk_f32(pc, "pc"); _chk_f32(mask, "mask"); _chk_f32(Rt, "Rt")
+        B, N, K = mask.shape
+        out = torch.empty(B, N, 3, dtype=torch.float32, device=pc.device)
+        with TIMER.span("apply_rigid_flow", B * N * (24 + 4 * K)):
+            _lib.check(self.lib.ogc_apply_rigid_flow(B, N, K, _ptr(pc), _ptr(mask), _ptr(Rt), _ptr(out), _stream()),
+                       "ogc_apply_rigid_flow")
+        self.launches += 1
+        return out
+
+    def neighbor_l1(self, mask, idx, dist, radius, coef, grad_accum=None, need_loss=True):
+        """loss_pt (B,N); grad_accum (B,N,K) += coef * d(sum loss_pt)/d mask when given."""
+        _chk_f32(mask, "mask"); _chk_i32(idx, "idx")
+        if dist is not None:
+            _chk_f32(dist, "dist")
+        B, N, K = mask.shape
+        S = idx.shape[2]
+        loss_pt = torch.empty(B, N, dtype=torch.float32, device=mask.device) if need_loss else None
+        with TIMER.span("neighbor_l1", B * N * (8 * S + 4 * K * (S + 2))):
+            _lib.check(self.lib.ogc_neighbor_l1(B, N, K, S, _ptr(mask), _ptr(idx), _ptr(dist),
+                                                float(radius if radius is not None else 0.0), float(coef),
+                                                _ptr(loss_pt), _ptr(grad_accum), _stream()), "ogc_neighbor_l1")
+        self.launches += 1
+        return loss_pt
+
+    def mask_contingency(self, mask1, mask2):
+        _chk_f32(mask1, "mask1"); _chk_f32(mask2, "mask2")
+        B, N, K = mask1.shape
+        inter = torch.zeros(B, K, K, dtype=torch.int32, device=mask1.device)
+        with TIMER.span("mask_contingency", B * N * 8 * K):
+            _lib.check(self.lib.ogc_mask_contingency(B, N, K, _ptr(mask1), _ptr(mask2), _ptr(inter), _stream()),
+                       "ogc_mask_contingency")
+        self.launches += 1
+        return inter
+
+    def invariance_loss(self, mask1, mask2, perm12, perm21, need_grad=True):
+        _chk_f32(mask1, "mask1"); _chk_f32(mask2, "mask2"); _chk_i32(perm12, "perm12"); _chk_i32(perm21, "perm21")
+        B, N, K = mask1.shape
+        loss_pt = torch.empty(B, N, dtype=torch.float32, device=mask1.device)
+        g1 = torch.empty_like(mask1) if need_grad else None
+        g2 = torch.empty_like(mask2) if need_grad else None
+        with TIMER.span("invariance_loss", B * N * (16 * K + 4)):
+            _lib.check(self.lib.ogc_invariance_loss(B, N, K, _ptr(mask1), _ptr(mask2), _ptr(perm12), _ptr(perm21),
+                                                    _ptr(loss_pt), _ptr(g1), _ptr(g2), _stream()),
+                       "ogc_invariance_loss")
+        self.launches += 1
+        return loss_pt, g1, g2
+
 
 _backend = None
 

@@ -1,0 +1,477 @@
+// Fused OGC-loss kernels for sm_100a (forward AND the gradient w.r.t. the soft mask in one pass).
+//
+// They replace torch-level code of the reference, not CUDA kernels:
+//   ogc_weighted_kabsch / ogc_dynamic_loss   losses/seg_loss_unsup.py:10-61 (fit_motion_svd_batch) and
+//                                            :72-98 (DynamicLoss.forward) + its autograd backward.
+//       The reference builds diag_embed(mask): a (B*K, N, N) tensor = 10.7 GB at B=4, K=10, N=8192
+//       (:36) to obtain 3x3 covariances.  Here: one CTA per cloud, two passes over the N points for the
+//       weighted means and the centred 3x3 covariances of all K segments, a per-segment 3x3 SVD in
+//       fp64 on one thread each, then one pass for the loss and d loss / d mask.  Nothing N x N exists.
+//   ogc_neighbor_l1                          :112-129 (KnnLoss) / :143-158 (BallQLoss), loss_norm = 1:
+//       radius clip + grouping_operation(mask) + |.|_1 + mean over neighbours, and the backward
+//       (group_points_grad's atomicAdd scatter + the centre term) fused in one kernel: the (B,K,N,S)
+//       gathered-mask tensor (21 MB / cloud at S=64) is never materialised.
+//   ogc_mask_contingency / ogc_invariance_loss   :212-280 (match_mask_by_iou's one-hot einsum IoU;
+//       InvarianceLoss.distance with the permutation given as an index vector).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace ogc {
+
+constexpr int kLossThreads = 1024;
+constexpr int kMaxSlots = 32;  // K (n_slot) limit of the fused loss kernels
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(OGC_FULL_MASK, v, o);
+    return v;
+}
+
+// ---- 3x3 rotation from the covariance S = sum w (p1-mu1)(p2-mu2)^T  (Kabsch) ---------------------
+// torch: U,S,V = svd(S); R = V diag(1,1,det(V U^T)) U^T.  Algebraically R = v1 u1^T + v2 u2^T +
+// (v1 x v2)(u1 x u2)^T for the two leading singular pairs -- the reflection fix is implicit and the
+// smallest singular pair is never needed, so rank-2 covariances (planar segments) are handled
+// exactly.  V from a cyclic Jacobi eigen-decomposition of S^T S in fp64.
+__device__ void kabsch_rotation(const double S[9], double R[9]) {
+    double B[3][3], V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double s = 0;
+            for (int r = 0; r < 3; ++r) s += S[r * 3 + i] * S[r * 3 + j];
+            B[i][j] = s;
+        }
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        const double off = fabs(B[0][1]) + fabs(B[0][2]) + fabs(B[1][2]);
+        const double diag = fabs(B[0][0]) + fabs(B[1][1]) + fabs(B[2][2]);
+        if (off <= 1e-300 || off <= 1e-17 * diag) break;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                if (fabs(B[p][q]) < 1e-300) continue;
+                const double theta = (B[q][q] - B[p][p]) / (2.0 * B[p][q]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int r = 0; r < 3; ++r) {  // B <- B J
+                    const double bp = B[r][p], bq = B[r][q];
+                    B[r][p] = c * bp - s * bq;
+                    B[r][q] = s * bp + c * bq;
+                }
+                for (int r = 0; r < 3; ++r) {  // B <- J^T B
+                    const double bp = B[p][r], bq = B[q][r];
+                    B[p][r] = c * bp - s * bq;
+                    B[q][r] = s * bp + c * bq;
+                }
+                for (int r = 0; r < 3; ++r) {  // V <- V J
+                    const double vp = V[r][p], vq = V[r][q];
+                    V[r][p] = c * vp - s * vq;
+                    V[r][q] = s * vp + c * vq;
+                }
+            }
+    }
+    // order eigenvalues descending -> i0 >= i1 >= i2
+    int i0 = 0, i1 = 1, i2 = 2;
+    if (B[i1][i1] > B[i0][i0]) { int t = i0; i0 = i1; i1 = t; }
+    if (B[i2][i2] > B[i0][i0]) { int t = i0; i0 = i2; i2 = t; }
+    if (B[i2][i2] > B[i1][i1]) { int t = i1; i1 = i2; i2 = t; }
+    double v1[3] = {V[0][i0], V[1][i0], V[2][i0]}, v2[3] = {V[0][i1], V[1][i1], V[2][i1]};
+    double u1[3], u2[3];
+    for (int r = 0; r < 3; ++r) {
+        u1[r] = S[r * 3 + 0] * v1[0] + S[r * 3 + 1] * v1[1] + S[r * 3 + 2] * v1[2];
+        u2[r] = S[r * 3 + 0] * v2[0] + S[r * 3 + 1] * v2[1] + S[r * 3 + 2] * v2[2];
+    }
+    const double n1 = sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+    if (!(n1 > 0.0)) {  // S == 0: every rotation is optimal; torch.svd returns U = V = I here
+        for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+        return;
+    }
+    for (int r = 0; r < 3; ++r) u1[r] /= n1;
+    const double dot = u1[0] * u2[0] + u1[1] * u2[1] + u1[2] * u2[2];
+    for (int r = 0; r < 3; ++r) u2[r] -= dot * u1[r];
+    double n2 = sqrt(u2[0] * u2[0] + u2[1] * u2[1] + u2[2] * u2[2]);
+    if (!(n2 > 1e-14 * n1)) {
+        // rank one: the rotation about u1 / v1 is not determined by the data (also ambiguous in the
+        // reference's SVD); take the minimal rotation that maps u1 to v1's frame via an arbitrary normal
+        const int a = fabs(u1[0]) < fabs(u1[1]) ? (fabs(u1[0]) < fabs(u1[2]) ? 0 : 2) : (fabs(u1[1]) < fabs(u1[2]) ? 1 : 2);
+        double e[3] = {0, 0, 0};
+        e[a] = 1.0;
+        const double d = u1[a];
+        for (int r = 0; r < 3; ++r) u2[r] = e[r] - d * u1[r];
+        n2 = sqrt(u2[0] * u2[0] + u2[1] * u2[1] + u2[2] * u2[2]);
+        const int c = fabs(v1[0]) < fabs(v1[1]) ? (fabs(v1[0]) < fabs(v1[2]) ? 0 : 2) : (fabs(v1[1]) < fabs(v1[2]) ? 1 : 2);
+        double f[3] = {0, 0, 0};
+        f[c] = 1.0;
+        const double dv = v1[c];
+        double nv = 0;
+        for (int r = 0; r < 3; ++r) { v2[r] = f[r] - dv * v1[r]; nv += v2[r] * v2[r]; }
+        nv = sqrt(nv);
+        for (int r = 0; r < 3; ++r) v2[r] /= nv;
+    }
+    for (int r = 0; r < 3; ++r) u2[r] /= n2;
+    const double u3[3] = {u1[1] * u2[2] - u1[2] * u2[1], u1[2] * u2[0] - u1[0] * u2[2], u1[0] * u2[1] - u1[1] * u2[0]};
+    const double v3[3] = {v1[1] * v2[2] - v1[2] * v2[1], v1[2] * v2[0] - v1[0] * v2[2], v1[0] * v2[1] - v1[1] * v2[0]};
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) R[i * 3 + j] = v1[i] * u1[j] + v2[i] * u2[j] + v3[i] * u3[j];
+}
+
+// One CTA per cloud.  mode bits: 1 = second operand is a flow (pc2 = pc + flow), else pc2 itself.
+// Outputs (each optional): Rt (K,12) = R row-major then t; loss_pt (N); grad_mask (N,K).
+__global__ void __launch_bounds__(kLossThreads, 1)
+kabsch_loss_kernel(int n, int K, int second_is_flow, const float *__restrict__ pc, const float *__restrict__ second,
+                   const float *__restrict__ mask, float *__restrict__ Rt_out, float *__restrict__ loss_pt,
+                   float *__restrict__ grad_mask) {
+    __shared__ double acc[kMaxSlots][9];
+    __shared__ float mu[kMaxSlots][6];
+    __shared__ float rt[kMaxSlots][12];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const size_t bo = static_cast<size_t>(blockIdx.x);
+    pc += bo * n * 3;
+    second += bo * n * 3;
+    mask += bo * n * K;
+
+    auto load_p2 = [&](int i, const float p1[3], float p2[3]) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float s = __ldg(second + i * 3 + c);
+            p2[c] = second_is_flow ? __fadd_rn(p1[c], s) : s;
+        }
+    };
+
+    // ---- pass 1: W = sum m, A = sum m p1, C = sum m p2  ------------------------------------------
+    for (int i = tid; i < kMaxSlots * 9; i += blockDim.x) (&acc[0][0])[i] = 0.0;
+    __syncthreads();
+    for (int k0 = 0; k0 < K; k0 += 4) {
+        float a[4][7];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int c = 0; c < 7; ++c) a[u][c] = 0.f;
+        for (int i = tid; i < n; i += blockDim.x) {
+            float p1[3], p2[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) p1[c] = __ldg(pc + i * 3 + c);
+            load_p2(i, p1, p2);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float m = (k0 + u < K) ? __ldg(mask + static_cast<size_t>(i) * K + k0 + u) : 0.f;
+                a[u][0] += m;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    a[u][1 + c] = fmaf(m, p1[c], a[u][1 + c]);
+                    a[u][4 + c] = fmaf(m, p2[c], a[u][4 + c]);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int c = 0; c < 7; ++c) {
+                const float s = warp_sum(a[u][c]);
+                if (lane == 0 && k0 + u < K) atomicAdd(&acc[k0 + u][c], static_cast<double>(s));
+            }
+    }
+    __syncthreads();
+    if (tid < K) {
+        // fp32 quotient, as einsum(...)/sum(mask) in the reference (:25-28)
+        const float w = static_cast<float>(acc[tid][0]);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) mu[tid][c] = static_cast<float>(acc[tid][1 + c]) / w;
+    }
+    __syncthreads();
+    for (int i = tid; i < kMaxSlots * 9; i += blockDim.x) (&acc[0][0])[i] = 0.0;
+    __syncthreads();
+
+    // ---- pass 2: S = sum m (p1 - mu1)(p2 - mu2)^T  (rows from pc1, columns from pc2, :36) ---------
+    for (int k0 = 0; k0 < K; k0 += 4) {
+        float a[4][9];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int c = 0; c < 9; ++c) a[u][c] = 0.f;
+        for (int i = tid; i < n; i += blockDim.x) {
+            float p1[3], p2[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) p1[c] = __ldg(pc + i * 3 + c);
+            load_p2(i, p1, p2);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = min(k0 + u, K - 1);
+                const float m = (k0 + u < K) ? __ldg(mask + static_cast<size_t>(i) * K + k) : 0.f;
+                float x[3], y[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { x[c] = p1[c] - mu[k][c]; y[c] = m * (p2[c] - mu[k][3 + c]); }
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) a[u][r * 3 + c] = fmaf(x[r], y[c], a[u][r * 3 + c]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int c = 0; c < 9; ++c) {
+                const float s = warp_sum(a[u][c]);
+                if (lane == 0 && k0 + u < K) atomicAdd(&acc[k0 + u][c], static_cast<double>(s));
+            }
+    }
+    __syncthreads();
+
+    // ---- per-segment rotation + translation ------------------------------------------------------
+    if (tid < K) {
+        double S[9], R[9];
+        bool bad = false;
+        for (int c = 0; c < 9; ++c) {
+            S[c] = static_cast<double>(static_cast<float>(acc[tid][c]));  // the reference's S is fp32
+            bad |= isnan(S[c]);
+        }
+        float Rf[9], tf[3];
+        if (bad) {  // ill-posed segment -> identity (:40-42, :58-59)
+            for (int c = 0; c < 9; ++c) Rf[c] = (c % 4 == 0) ? 1.f : 0.f;
+            tf[0] = tf[1] = tf[2] = 0.f;
+        } else {
+            kabsch_rotation(S, R);
+            for (int c = 0; c < 9; ++c) Rf[c] = static_cast<float>(R[c]);
+            for (int r = 0; r < 3; ++r)  // t = mu2 - R mu1  (:56)
+                tf[r] = mu[tid][3 + r] - (Rf[r * 3 + 0] * mu[tid][0] + Rf[r * 3 + 1] * mu[tid][1] + Rf[r * 3 + 2] * mu[tid][2]);
+        }
+        for (int c = 0; c < 9; ++c) rt[tid][c] = Rf[c];
+        for (int c = 0; c < 3; ++c) rt[tid][9 + c] = tf[c];
+        if (Rt_out)
+            for (int c = 0; c < 12; ++c) Rt_out[(bo * K + tid) * 12 + c] = rt[tid][c];
+    }
+    if (!loss_pt && !grad_mask) return;
+    __syncthreads();
+
+    // ---- pass 3: loss_n = || sum_k m_k (R_k p + t_k) - p2 ||_2 ; grad_{n,k} = qhat . (R_k p + t_k) ----
+    for (int i = tid; i < n; i += blockDim.x) {
+        float p1[3], p2[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) p1[c] = __ldg(pc + i * 3 + c);
+        load_p2(i, p1, p2);
+        float q[3] = {0.f, 0.f, 0.f};
+        for (int k = 0; k < K; ++k) {
+            const float m = __ldg(mask + static_cast<size_t>(i) * K + k);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const float tp = rt[k][r * 3 + 0] * p1[0] + rt[k][r * 3 + 1] * p1[1] + rt[k][r * 3 + 2] * p1[2] + rt[k][9 + r];
+                q[r] += m * tp;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) q[r] -= p2[r];
+        const float nrm = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+        if (loss_pt) loss_pt[bo * n + i] = nrm;
+        if (grad_mask) {
+            const float inv = nrm > 0.f ? 1.0f / nrm : 0.f;  // torch: subgradient 0 at the origin
+            for (int k = 0; k < K; ++k) {
+                float g = 0.f;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const float tp = rt[k][r * 3 + 0] * p1[0] + rt[k][r * 3 + 1] * p1[1] + rt[k][r * 3 + 2] * p1[2] + rt[k][9 + r];
+                    g += q[r] * inv * tp;
+                }
+                grad_mask[(bo * n + i) * K + k] = g;
+            }
+        }
+    }
+}
+
+// out_n = sum_k m_k (R_k p_n + t_k) - p_n     (weighted_kabsch / object_aware_icp flow update,
+// oa_icp.py:33-38, :78-83)
+__global__ void __launch_bounds__(256)
+apply_rigid_flow_kernel(int n, int K, const float *__restrict__ pc, const float *__restrict__ mask,
+                        const float *__restrict__ Rt, float *__restrict__ flow_out) {
+    __shared__ float rt[kMaxSlots][12];
+    const size_t bo = blockIdx.y;
+    for (int i = threadIdx.x; i < K * 12; i += blockDim.x) (&rt[0][0])[i] = __ldg(Rt + bo * K * 12 + i);
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *p = pc + (bo * n + i) * 3;
+    const float p1[3] = {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
+    float q[3] = {0.f, 0.f, 0.f};
+    for (int k = 0; k < K; ++k) {
+        const float m = __ldg(mask + (bo * n + i) * K + k);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+            q[r] += m * (rt[k][r * 3 + 0] * p1[0] + rt[k][r * 3 + 1] * p1[1] + rt[k][r * 3 + 2] * p1[2] + rt[k][9 + r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) flow_out[(bo * n + i) * 3 + r] = q[r] - p1[r];
+}
+
+// ---- smoothness: one warp per point, lanes over the S neighbour slots -----------------------------
+// loss_pt[n] = (1/S) sum_s sum_c | m[n,c] - m[nbr(n,s),c] |, nbr = idx[n,s] unless dist[n,s] > radius
+// (then idx[n,0]).  grad_mask += coef * d(sum_n loss_pt)/d mask  (both the centre and the gathered
+// term), accumulated with red.global.add like the reference's group_points_grad.
+__global__ void __launch_bounds__(256)
+neighbor_l1_kernel(int n, int K, int S, const float *__restrict__ mask, const int *__restrict__ idx,
+                   const float *__restrict__ dist, float radius, int clip, float coef, float *__restrict__ loss_pt,
+                   float *__restrict__ grad_mask) {
+    const int lane = threadIdx.x & 31;
+    const int pt = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pt >= n) return;
+    const size_t bo = blockIdx.y;
+    mask += bo * n * K;
+    if (grad_mask) grad_mask += bo * n * K;
+    const int *irow = idx + (bo * n + pt) * S;
+    const float *drow = dist ? dist + (bo * n + pt) * S : nullptr;
+    const int first = __ldg(irow);
+    const float *crow = mask + static_cast<size_t>(pt) * K;
+    float total = 0.f;
+    const float gscale = coef / static_cast<float>(S);
+    // K is small (8-16): loop over channels inside, neighbours across lanes
+    for (int s0 = 0; s0 < S; s0 += 32) {
+        const int s = s0 + lane;
+        int j = -1;
+        if (s < S) {
+            j = __ldg(irow + s);
+            if (clip && __ldg(drow + s) > radius) j = first;
+        }
+        if (j >= 0 && j != pt) {
+            const float *nrow = mask + static_cast<size_t>(j) * K;
+            for (int c = 0; c < K; ++c) {
+                const float d = __ldg(crow + c) - __ldg(nrow + c);
+                total += fabsf(d);
+                if (grad_mask && d != 0.f) {
+                    const float g = d > 0.f ? gscale : -gscale;
+                    atomicAdd(grad_mask + static_cast<size_t>(pt) * K + c, g);
+                    atomicAdd(grad_mask + static_cast<size_t>(j) * K + c, -g);
+                }
+            }
+        }
+    }
+    total = warp_sum(total);
+    if (lane == 0 && loss_pt) loss_pt[bo * n + pt] = total / static_cast<float>(S);
+}
+
+// ---- invariance: hard-assignment contingency table -------------------------------------------------
+// inter[b,g,p] = #{n : argmax m1[n] = g and argmax m2[n] = p}; row / column sums give the one-hot
+// segment sizes.  argmax takes the FIRST maximum like torch.argmax.
+__global__ void __launch_bounds__(256)
+contingency_kernel(int n, int K, const float *__restrict__ m1, const float *__restrict__ m2, int *__restrict__ inter) {
+    __shared__ int hist[kMaxSlots * kMaxSlots];
+    const size_t bo = blockIdx.y;
+    for (int i = threadIdx.x; i < K * K; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float *r1 = m1 + (bo * n + i) * K, *r2 = m2 + (bo * n + i) * K;
+        int a1 = 0, a2 = 0;
+        float b1 = __ldg(r1), b2 = __ldg(r2);
+        for (int c = 1; c < K; ++c) {
+            const float v1 = __ldg(r1 + c), v2 = __ldg(r2 + c);
+            if (v1 > b1) { b1 = v1; a1 = c; }
+            if (v2 > b2) { b2 = v2; a2 = c; }
+        }
+        atomicAdd(&hist[a1 * K + a2], 1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K * K; i += blockDim.x)
+        if (hist[i]) atomicAdd(inter + bo * K * K + i, hist[i]);
+}
+
+// loss_pt[n] = || m1[n] - m2[n, perm12] ||_2 + || m2[n] - m1[n, perm21] ||_2 ; targets are constants
+// (detached, :270-273).  perm12[i] = column matched to row i (scipy col_ind).
+__global__ void __launch_bounds__(256)
+invariance_kernel(int n, int K, const float *__restrict__ m1, const float *__restrict__ m2,
+                  const int *__restrict__ perm12, const int *__restrict__ perm21, float *__restrict__ loss_pt,
+                  float *__restrict__ g1, float *__restrict__ g2) {
+    __shared__ int p12[kMaxSlots], p21[kMaxSlots];
+    const size_t bo = blockIdx.y;
+    if (threadIdx.x < K) {
+        p12[threadIdx.x] = perm12[bo * K + threadIdx.x];
+        p21[threadIdx.x] = perm21[bo * K + threadIdx.x];
+    }
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *r1 = m1 + (bo * n + i) * K, *r2 = m2 + (bo * n + i) * K;
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = 0; c < K; ++c) {
+        const float d1 = __ldg(r1 + c) - __ldg(r2 + p12[c]);
+        const float d2 = __ldg(r2 + c) - __ldg(r1 + p21[c]);
+        s1 += d1 * d1;
+        s2 += d2 * d2;
+    }
+    const float n1 = sqrtf(s1), n2 = sqrtf(s2);
+    if (loss_pt) loss_pt[bo * n + i] = n1 + n2;
+    const float i1 = n1 > 0.f ? 1.f / n1 : 0.f, i2 = n2 > 0.f ? 1.f / n2 : 0.f;
+    for (int c = 0; c < K; ++c) {
+        if (g1) g1[(bo * n + i) * K + c] = (__ldg(r1 + c) - __ldg(r2 + p12[c])) * i1;
+        if (g2) g2[(bo * n + i) * K + c] = (__ldg(r2 + c) - __ldg(r1 + p21[c])) * i2;
+    }
+}
+
+}  // namespace ogc
+
+extern "C" int ogc_weighted_kabsch(int b, int n, int k, int second_is_flow, const float *pc, const float *second,
+                                   const float *mask, float *Rt, void *stream) {
+    using namespace ogc;
+    if (b < 0 || n <= 0 || k < 1 || k > kMaxSlots) return OGC_ERR_INVALID_ARG;
+    if (b == 0) return OGC_OK;
+    if (!pc || !second || !mask || !Rt) return OGC_ERR_INVALID_ARG;
+    kabsch_loss_kernel<<<b, kLossThreads, 0, static_cast<cudaStream_t>(stream)>>>(n, k, second_is_flow, pc, second, mask, Rt,
+                                                                                 nullptr, nullptr);
+    OGC_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int ogc_dynamic_loss(int b, int n, int k, const float *pc, const float *flow, const float *mask,
+                                float *loss_pt, float *grad_mask, float *Rt, void *stream) {
+    using namespace ogc;
+    if (b < 0 || n <= 0 || k < 1 || k > kMaxSlots) return OGC_ERR_INVALID_ARG;
+    if (b == 0) return OGC_OK;
+    if (!pc || !flow || !mask || !loss_pt) return OGC_ERR_INVALID_ARG;
+    kabsch_loss_kernel<<<b, kLossThreads, 0, static_cast<cudaStream_t>(stream)>>>(n, k, 1, pc, flow, mask, Rt, loss_pt,
+                                                                                 grad_mask);
+    OGC_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int ogc_apply_rigid_flow(int b, int n, int k, const float *pc, const float *mask, const float *Rt,
+                                    float *flow_out, void *stream) {
+    using namespace ogc;
+    if (b < 0 || n < 0 || k < 1 || k > kMaxSlots) return OGC_ERR_INVALID_ARG;
+    if (b == 0 || n == 0) return OGC_OK;
+    if (!pc || !mask || !Rt || !flow_out) return OGC_ERR_INVALID_ARG;
+    if (b > 65535) return OGC_ERR_UNSUPPORTED;
+    dim3 grid((n + 255) / 256, b);
+    apply_rigid_flow_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(n, k, pc, mask, Rt, flow_out);
+    OGC_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int ogc_neighbor_l1(int b, int n, int k, int nsample, const float *mask, const int *idx, const float *dist,
+                               float radius, float coef, float *loss_pt, float *grad_mask, void *stream) {
+    using namespace ogc;
+    if (b < 0 || n < 0 || k < 1 || k > kMaxSlots || nsample < 1) return OGC_ERR_INVALID_ARG;
+    if (b == 0 || n == 0) return OGC_OK;
+    if (!mask || !idx) return OGC_ERR_INVALID_ARG;
+    if (b > 65535) return OGC_ERR_UNSUPPORTED;
+    dim3 grid((n + 7) / 8, b);
+    neighbor_l1_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(n, k, nsample, mask, idx, dist, radius,
+                                                                          dist != nullptr, coef, loss_pt, grad_mask);
+    OGC_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int ogc_mask_contingency(int b, int n, int k, const float *mask1, const float *mask2, int *inter,
+                                    void *stream) {
+    using namespace ogc;
+    if (b < 0 || n < 0 || k < 1 || k > kMaxSlots) return OGC_ERR_INVALID_ARG;
+    if (b == 0 || n == 0) return OGC_OK;
+    if (!mask1 || !mask2 || !inter) return OGC_ERR_INVALID_ARG;
+    if (b > 65535) return OGC_ERR_UNSUPPORTED;
+    dim3 grid((n + 255) / 256, b);
+    contingency_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(n, k, mask1, mask2, inter);
+    OGC_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int ogc_invariance_loss(int b, int n, int k, const float *mask1, const float *mask2, const int *perm12,
+                                   const int *perm21, float *loss_pt, float *grad1, float *grad2, void *stream) {
+    using namespace ogc;
+    if (b < 0 || n < 0 || k < 1 || k > kMaxSlots) return OGC_ERR_INVALID_ARG;
+    if (b == 0 || n == 0) return OGC_OK;
+    if (!mask1 || !mask2 || !perm12 || !perm21) return OGC_ERR_INVALID_ARG;
+    if (b > 65535) return OGC_ERR_UNSUPPORTED;
+    dim3 grid((n + 255) / 256, b);
+    invariance_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(n, k, mask1, mask2, perm12, perm21, loss_pt,
+                                                                         grad1, grad2);
+    OGC_RETURN_LAUNCH_STATUS();
+}

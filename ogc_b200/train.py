@@ -1,0 +1,123 @@
+"""The benchmarked training step -- host-side mirror of `Trainer._train_it` (train_seg.py:47-86) for the
+data-parallel hot path, one process per GPU.
+
+    batch (b,t,N,3) --H2D--> segnet fwd --> UnsupervisedOGCLoss --> backward --> NaN guard --> Adam
+
+Differences from the reference (all behaviour-preserving):
+  * parameters, gradients and the Adam moments live in three flat fp32 buffers; `zero_grad` is one
+    memset, the NaN scan (train_seg.py:81-83: one host sync per parameter) is one kernel leaving a
+    device-side counter, `optimizer.step()` is one kernel that is skipped ON THE DEVICE when the
+    counter is non-zero (csrc/optim.cu) -- no host sync between backward and the update;
+  * multi-GPU (the reference has none): clouds are independent, so ranks hold disjoint
+    sample shards and exchange exactly ONE NCCL all-reduce per step over [flat grads | NaN counter];
+    the 1/world_size scale is folded into the Adam kernel.  The step-weight schedule and `lr_curve`
+    use the GLOBAL batch size (train_seg.py:70, :230-234).
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .backend import TIMER, get_backend
+
+
+def lr_curve(it, batch_size, lr, lr_decay, decay_step, lr_clip):
+    """train_seg.py:230-234"""
+    return max(lr_decay ** (int(it * batch_size / decay_step)), lr_clip / lr)
+
+
+class FlatAdam:
+    """Adam over one flat buffer; parameters and their .grad are re-pointed to views of it."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        self.params = [p for p in params if p.requires_grad]
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        self.n = n
+        self.flat_p = torch.empty(n, dtype=torch.float32, device=dev)
+        # gradient buffer carries one extra float: the NaN counter rides the same all-reduce
+        self.flat_g_ext = torch.zeros(n + 1, dtype=torch.float32, device=dev)
+        self.flat_g = self.flat_g_ext[:n]
+        self.nan_counter = self.flat_g_ext[n:]
+        self.m = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            self.flat_p[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat_p[off:off + k].view_as(p.data)
+            p.grad = self.flat_g[off:off + k].view_as(p.data)
+            off += k
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.t = 0
+        self.lib = _lib.load() if dev.type == "cuda" else None
+
+    def zero_grad(self):
+        self.flat_g_ext.zero_()
+
+    def step(self, lr_scale=1.0, grad_scale=1.0):
+        self.t += 1
+        if self.lib is None:      # CPU arm of bench.py (--impl reference): same arithmetic in torch
+            if bool(torch.isnan(self.flat_g).any()):
+                return
+            g = self.flat_g * grad_scale
+            if self.weight_decay:
+                g = g + self.weight_decay * self.flat_p
+            b1, b2 = self.betas
+            self.m.mul_(b1).add_(g, alpha=1 - b1)
+            self.v.mul_(b2).addcmul_(g, g, value=1 - b2)
+            denom = self.v.sqrt() / (1 - b2 ** self.t) ** 0.5 + self.eps
+            self.flat_p.addcdiv_(self.m, denom, value=-self.lr * lr_scale / (1 - b1 ** self.t))
+            return
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        P = lambda t: ctypes.c_void_p(t.data_ptr())
+        with TIMER.span("adam_step", 28 * self.n):
+            _lib.check(self.lib.ogc_adam_step(self.n, P(self.flat_p), P(self.flat_g), P(self.m), P(self.v),
+                                              self.lr * lr_scale, self.betas[0], self.betas[1], self.eps,
+                                              self.weight_decay, self.t, grad_scale, P(self.nan_counter), st),
+                       "ogc_adam_step")
+        get_backend().launches += 1
+
+    def count_nan(self):
+        if self.lib is None:
+            return
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        with TIMER.span("count_nan", 4 * self.n):
+            _lib.check(self.lib.ogc_count_nan(self.n, ctypes.c_void_p(self.flat_g.data_ptr()),
+                                              ctypes.c_void_p(self.nan_counter.data_ptr()), st), "ogc_count_nan")
+        get_backend().launches += 1
+
+
+class SegTrainer:
+    def __init__(self, segnet, criterion, lr=1e-3, weight_decay=0.0, lr_decay=0.7, lr_clip=1e-5,
+                 decay_step=200000, global_batch_size=4, world_size=1):
+        self.segnet, self.criterion = segnet, criterion
+        self.opt = FlatAdam(segnet.parameters(), lr=lr, weight_decay=weight_decay)
+        self.sched = dict(lr=lr, lr_decay=lr_decay, decay_step=decay_step, lr_clip=lr_clip)
+        self.global_batch_size, self.world_size = global_batch_size, world_size
+        self.device = self.opt.flat_p.device
+
+    def train_step(self, it, batch, aug_transform=False):
+        """batch = (pcs (b,t,N,3), segms, flows (b,t,N,3), valids) on host or device.  Returns loss_dict."""
+        self.segnet.train()
+        lr_scale = lr_curve(it, self.global_batch_size, **self.sched)
+        self.opt.zero_grad()
+        pcs, segms, flows, _ = batch
+        b, t, n = segms.shape
+        pcs = pcs.to(self.device, non_blocking=True).view(b * t, n, 3)
+        flows = flows.to(self.device, non_blocking=True)
+        masks = self.segnet(pcs, pcs)
+        pcs = pcs.view(b, t, n, 3)
+        masks = masks.view(b, t, n, -1)
+        pcs_l = [pcs[:, i].contiguous() for i in range(t)]
+        masks_l = [masks[:, i].contiguous() for i in range(t)]
+        flows_l = [flows[:, i].contiguous() for i in range(t)]
+        loss, loss_dict = self.criterion(pcs_l, masks_l, flows_l, step_w=True, it=it * self.global_batch_size,
+                                         aug_transform=aug_transform)
+        loss.backward()
+        self.opt.count_nan()
+        if self.world_size > 1:
+            dist.all_reduce(self.opt.flat_g_ext)          # the step's only collective: grads + NaN counter
+        self.opt.step(lr_scale=lr_scale, grad_scale=1.0 / self.world_size)
+        return loss_dict

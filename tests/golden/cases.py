@@ -1,0 +1,81 @@
+"""Seeded definitions of the golden cases (shared by make_golden.py and the tests)."""
+import numpy as np
+import torch
+
+KITTI_LOSS = {
+    "weights": [10.0, 0.1, 0.1], "start_steps": [0, 100, 1000],
+    "dynamic_loss_params": {"loss_norm": 2},
+    "smooth_loss_params": {"w_knn": 3.0, "w_ball_q": 1.0,
+                           "knn_loss_params": {"k": 32, "radius": 1.0, "loss_norm": 1},
+                           "ball_q_loss_params": {"k": 64, "radius": 2.0, "loss_norm": 1}},
+    "invariance_loss_params": {"loss_norm": 2},
+}
+SAPIEN_LOSS = {   # config/seg/sapien/sapien_unsup.yaml
+    "weights": [10.0, 0.1, 0.1], "start_steps": [0, 0, 0],
+    "dynamic_loss_params": {"loss_norm": 2},
+    "smooth_loss_params": {"w_knn": 3.0, "w_ball_q": 1.0,
+                           "knn_loss_params": {"k": 8, "radius": 0.1, "loss_norm": 1},
+                           "ball_q_loss_params": {"k": 16, "radius": 0.2, "loss_norm": 1}},
+    "invariance_loss_params": {"loss_norm": 2},
+}
+
+CASES = {
+    # BASELINE.json configs[0]: SAPIEN 512-pt cloud through segnet_sapien (+ a probe backward)
+    "segnet_sapien_512": {"kind": "segnet", "variant": "sapien", "n_slot": 8, "n_point": 512, "B": 2, "seed": 10,
+                          "scale": 0.5,
+                          "grad_params": ["SA_modules.0.mlps.0.layer0.conv.weight", "FP_modules.0.mlp.layer2.conv.weight",
+                                          "MF_head.query.weight"]},
+    # a reduced KITTI-shaped net (n_point 1024 -> 256/128/64 centres), metre-scale scene
+    "segnet_kitti_1024": {"kind": "segnet", "variant": "kitti", "n_slot": 10, "n_point": 1024, "B": 2, "seed": 11,
+                          "scale": 12.0,
+                          "grad_params": ["SA_modules.0.mlps.1.layer2.conv.weight", "SA_modules.2.mlps.0.layer0.conv.weight",
+                                          "object_mlp.1.conv.bias"]},
+    "ogc_loss_aug": {"kind": "ogc_loss", "B": 2, "N": 640, "K": 6, "seed": 12, "aug": True, "it": 5000,
+                     "scale": 6.0, "loss_cfg": KITTI_LOSS},
+    "ogc_loss_noaug": {"kind": "ogc_loss", "B": 3, "N": 512, "K": 8, "seed": 13, "aug": False, "it": 50,
+                       "scale": 0.4, "loss_cfg": SAPIEN_LOSS},
+}
+
+
+def make_inputs(case):
+    rng = np.random.default_rng(case["seed"])
+    f32 = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float32))
+    if case["kind"] == "segnet":
+        pc = f32(rng.uniform(-1, 1, size=(case["B"], case["n_point"], 3)) * case["scale"])
+        probe = f32(rng.normal(size=(case["B"], case["n_point"], case["n_slot"])))
+        return {"pc": pc, "probe": probe}
+    V = 4 if case["aug"] else 2
+    B, N, K = case["B"], case["N"], case["K"]
+    pcs, flows, logits = [], [], []
+    for v in range(V):
+        pc = rng.uniform(-1, 1, size=(B, N, 3)) * case["scale"]
+        # piecewise-rigid flow: K blobs along x, each with its own small rotation + translation
+        seg = np.clip(((pc[..., 0] / case["scale"] + 1) / 2 * K).astype(int), 0, K - 1)
+        flow = np.zeros_like(pc)
+        for k in range(K):
+            ang = rng.uniform(-0.1, 0.1)
+            Rz = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]])
+            t = rng.uniform(-0.05, 0.05, size=3) * case["scale"]
+            sel = seg == k
+            flow[sel] = pc[sel] @ Rz.T + t - pc[sel]
+        flow += rng.normal(size=flow.shape) * 0.002 * case["scale"]
+        lg = rng.normal(size=(B, N, K)) * 0.5
+        lg[np.arange(B)[:, None], np.arange(N)[None, :], seg] += 2.0
+        pcs.append(f32(pc)); flows.append(f32(flow)); logits.append(f32(lg))
+    return {"pcs": pcs, "flows": flows, "logits": logits}
+
+
+def build_my_segnet(case):
+    from ogc_b200.segnet import MaskFormer3D
+    torch.manual_seed(10)
+    net = MaskFormer3D(n_slot=case["n_slot"], n_point=case["n_point"], variant=case["variant"])
+    # non-trivial norm parameters (fresh GroupNorm / LayerNorm are identity-affine)
+    g = torch.Generator().manual_seed(case["seed"])
+    with torch.no_grad():
+        for n, p in net.named_parameters():
+            if n.endswith("gn.weight") or (("norm" in n) and n.endswith("weight")):
+                p.add_(0.2 * torch.randn(p.shape, generator=g))
+            elif n.endswith("gn.bias") or (("norm" in n) and n.endswith("bias")):
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+    net.train()
+    return net

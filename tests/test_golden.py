@@ -1,0 +1,105 @@
+"""Golden-vector tests.  tests/golden/*.npz were produced by the UNMODIFIED reference Python
+(models/segnet_*.py, losses/seg_loss_unsup.py) on CPU over this repo's operator layer + CPU oracle
+(tests/golden/make_golden.py).  Here this repo's own network / loss mirrors must reproduce them:
+  * on CPU through the oracle back-end (composed implementation)        -- not gpu
+  * on a B200 through libogc_b200 (composed AND fused implementations)  -- gpu
+Tolerance: 1e-4 absolute on masks / losses (BASELINE.json north_star), 1e-4 relative-to-max on
+gradients.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.golden.cases import CASES, make_inputs, build_my_segnet
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def golden(name):
+    return dict(np.load(os.path.join(HERE, "golden", name + ".npz")))
+
+
+def assert_close_rel_to_max(got, ref, tol, what):
+    scale = max(float(np.abs(ref).max()), 1e-12)
+    err = float(np.abs(got - ref).max())
+    assert err <= tol * scale, f"{what}: max abs err {err:.3e} vs scale {scale:.3e}"
+
+
+def run_segnet_case(name, device):
+    case = CASES[name]
+    inp = make_inputs(case)
+    net = build_my_segnet(case).to(device)
+    pc = inp["pc"].to(device)
+    mask = net(pc, pc)
+    (mask * inp["probe"].to(device)).sum().backward()
+    g = golden(name)
+    err = float((mask.detach().cpu() - torch.from_numpy(g["mask"])).abs().max())
+    assert err <= 1e-4, f"{name}: mask max abs err {err:.3e}"
+    params = dict(net.named_parameters())
+    for pname in case["grad_params"]:
+        assert_close_rel_to_max(params[pname].grad.cpu().numpy(), g["grad:" + pname], 2e-4, f"{name} grad {pname}")
+
+
+def run_loss_case(name, device, force_composed):
+    from ogc_b200 import losses as L
+    case = CASES[name]
+    inp = make_inputs(case)
+    g = golden(name)
+    crit = L.build_ogc_loss(case["loss_cfg"])
+    logits = [l.clone().to(device).requires_grad_(True) for l in inp["logits"]]
+    masks = [l.softmax(-1) for l in logits]
+    pcs = [p.to(device) for p in inp["pcs"]]
+    flows = [f.to(device) for f in inp["flows"]]
+    L.FORCE_COMPOSED = force_composed
+    try:
+        loss, d = crit(pcs, masks, flows, step_w=True, it=case["it"], aug_transform=case["aug"])
+        loss.backward()
+    finally:
+        L.FORCE_COMPOSED = False
+    assert abs(loss.item() - float(g["loss"])) <= 1e-4 * max(1.0, abs(float(g["loss"])))
+    for k in ["dynamic", "smooth", "invariance", "entropy", "sum"]:
+        assert abs(d[k] - float(g["dict:" + k])) <= 1e-4 * max(1.0, abs(float(g["dict:" + k]))), k
+    assert abs(d["rank"] - float(g["dict:rank"])) <= 1e-4 * abs(float(g["dict:rank"])), "rank"
+    for i, l in enumerate(logits):
+        assert_close_rel_to_max(l.grad.cpu().numpy(), g["grad_logits%d" % i], 2e-4, f"{name} grad_logits{i}")
+    return pcs, flows, masks, g
+
+
+# ------------------------------------------------------------------------------- CPU (oracle)
+@pytest.mark.parametrize("name", ["segnet_sapien_512", "segnet_kitti_1024"])
+def test_segnet_matches_reference_cpu(oracle_ops, name):
+    torch.set_num_threads(8)
+    run_segnet_case(name, "cpu")
+
+
+@pytest.mark.parametrize("name", ["ogc_loss_aug", "ogc_loss_noaug"])
+def test_ogc_loss_matches_reference_cpu(oracle_ops, name):
+    from ogc_b200 import losses as L
+    pcs, flows, masks, g = run_loss_case(name, "cpu", force_composed=True)
+    case = CASES[name]
+    rep = lambda x: x.unsqueeze(1).repeat(1, case["K"], 1, 1).reshape(-1, case["N"], 3)
+    R, t = L.fit_motion_svd_batch(rep(pcs[0]), rep(pcs[0] + flows[0]), masks[0].detach().transpose(1, 2).reshape(-1, case["N"]))
+    np.testing.assert_allclose(R.numpy(), g["kabsch_R"], atol=2e-5)
+    np.testing.assert_allclose(t.numpy(), g["kabsch_t"], atol=2e-4)
+
+
+# ------------------------------------------------------------------------------- GPU (B200)
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["segnet_sapien_512", "segnet_kitti_1024"])
+def test_segnet_matches_reference_gpu(b200, name):
+    run_segnet_case(name, "cuda")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["ogc_loss_aug", "ogc_loss_noaug"])
+@pytest.mark.parametrize("force_composed", [True, False], ids=["composed", "fused"])
+def test_ogc_loss_matches_reference_gpu(b200, name, force_composed):
+    pcs, flows, masks, g = run_loss_case(name, "cuda", force_composed)
+    case = CASES[name]
+    Rt = b200.weighted_kabsch(pcs[0], flows[0], masks[0].detach().contiguous(), second_is_flow=True)
+    R = Rt[..., :9].reshape(-1, 3, 3).cpu().numpy()
+    t = Rt[..., 9:].reshape(-1, 3).cpu().numpy()
+    np.testing.assert_allclose(R, g["kabsch_R"], atol=2e-5)
+    np.testing.assert_allclose(t, g["kabsch_t"], atol=2e-4)

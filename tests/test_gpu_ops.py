@@ -188,7 +188,7 @@ def test_operator_layer_autograd_on_gpu(oracle):
 
     def run(dev):
         x = xyz.to(dev)
-        f = feats.to(dev).requires_grad_(True)
+        f = feats.to(dev).detach().clone().requires_grad_(True)
         inds = ops.furthest_point_sample(x, 128)
         new_xyz = ops.gather_nd(x, inds.long())
         grouped, _ = ops.QueryAndGroup(0.8, 16)(x, new_xyz.contiguous(), f)
