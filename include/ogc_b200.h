@@ -180,6 +180,70 @@ OGC_API int ogc_adam_step(long long n, float *param, const float *grad, float *e
                           float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                           float grad_scale, const float *skip_counter, void *stream);
 
+/* =======================================================================================
+ * Fused set-abstraction MLP (csrc/mlp.cu, csrc/mlp_bwd.cu).  Replaces the torch-level stack of the
+ * reference SA module: QueryAndGroup's two grouping_operation calls + concat
+ * (pointnet2/pointnet2.py:287-294), SharedMLP = (Conv2d 1x1, GroupNorm(4), ReLU) x L
+ * (utils/nn_util.py:151-168) and max_pool2d over nsample (utils/pointnet2_util.py:38-42), forward
+ * and backward.  P = m*nsample positions per cloud, position p = centre*nsample + slot.
+ * Per layer l: y_l = W_l a_{l-1} (pre-norm, stored once), a_l = relu(scale*y_l + shift).
+ * ===================================================================================== */
+
+/* One layer forward.  gather=1 (layer 1): a_0 is built on the fly from xyz (b,n,3), new_xyz (b,m,3),
+ * point-major features feat_pm (b,n,cin-3) and neighbour indices idx (b,m,nsample): channels
+ * [xyz_j - centre, feat_j].  gather=0: a_{l-1} = relu(ss_prev[.,0]*y_prev + ss_prev[.,1]).
+ * wt = W^T (cin,cout).  y (b,cout,P) may be NULL.  sums (b,4,2) fp64 += [sum y, sum y^2] per
+ * GroupNorm group (zero it first).  last=1 (nsample == 64): also ymax/ymin (b,cout,m) = max/min of y
+ * over the nsample axis and amax/amin their first positions. */
+OGC_API int ogc_sa_mlp_layer_fwd(int b, int n, int m, int nsample, int cin, int cout, int gather, int last,
+                                 const float *xyz, const float *new_xyz, const float *feat_pm, const int *idx,
+                                 const float *y_prev, const float *ss_prev, const float *wt, float *y,
+                                 double *sums, float *ymax, float *ymin, unsigned char *amax,
+                                 unsigned char *amin, void *stream);
+
+/* GroupNorm(4) statistics -> per-channel affine: scale_shift (b,c,2) = [gamma*rstd, beta - mean*gamma*rstd],
+ * mean_rstd (b,4,2).  count_per_group = (c/4)*P.  Biased variance, eps 1e-5 (nn.GroupNorm defaults). */
+OGC_API int ogc_gn_finalize(int b, int c, long long count_per_group, const double *sums, const float *gamma,
+                            const float *beta, float *scale_shift, float *mean_rstd, void *stream);
+
+/* Pooled output of the last layer: out[b, c_offset+c, m] = relu(max_s(scale*y+shift)) written into a
+ * (b,c_total,m) tensor (multi-scale concat) and optionally its point-major twin out_pm (b,m,c_total);
+ * sel (b,c,m) = winning slot (255: clamped by the ReLU), ysel = its pre-norm value. */
+OGC_API int ogc_sa_finish(int b, int c, int m, const float *ymax, const float *ymin, const unsigned char *amax,
+                          const unsigned char *amin, const float *scale_shift, float *out, float *out_pm,
+                          int c_total, int c_offset, unsigned char *sel, float *ysel, void *stream);
+
+/* Backward, last layer: GroupNorm-backward sums from the sparse pooled gradient go (b,go_ctotal,m).
+ * ab (b,4,2) fp64 += [sum gamma dz, sum gamma dz yhat]; dgamma/dbeta (c) += their per-channel parts. */
+OGC_API int ogc_sa_last_stats(int b, int c, int m, const float *go, int go_ctotal, int go_coff,
+                              const unsigned char *sel, const float *ysel, const float *mean_rstd,
+                              const float *gamma, double *ab, float *dgamma, float *dbeta, void *stream);
+
+/* coef (b,c,4) = [rstd*gamma, rstd*A/n, rstd^2*B/n, mean]: dY = coef0*dz - coef1 - (y - coef3)*coef2 */
+OGC_API int ogc_gn_bwd_coef(int b, int c, long long count_per_group, const double *ab, const float *mean_rstd,
+                            const float *gamma, float *coef, void *stream);
+
+/* Input gradient of layer l: rows [row_off,row_off+rows) of W^T dY_l with W (cout,cin_full).
+ * dY_l is rebuilt from dz (b,cout,P) -- or, when dz == NULL (last layer), from go/sel -- plus y and coef.
+ * Dense mode (dfeat_pm == NULL): dz_prev (b,rows,P) = relu'(.) * result, and the GroupNorm-backward sums
+ * of layer l-1 (ab_prev, dgamma_prev, dbeta_prev) are accumulated.
+ * Scatter mode (layer 1): result is scatter-added through idx into dfeat_pm (b,n,dfeat_stride) at
+ * channel offset dfeat_off (replaces group_points_grad, src/group_points_gpu.cu:8-25). rows <= 128. */
+OGC_API int ogc_sa_mlp_layer_dx(int b, int n, int m, int nsample, int cout, int cin_full, int row_off, int rows,
+                                const float *dz, const float *go, int go_ctotal, int go_coff,
+                                const unsigned char *sel, const float *y, const float *coef, const float *w,
+                                const float *y_prev, const float *ss_prev, const float *mean_rstd_prev,
+                                const float *gamma_prev, float *dz_prev, double *ab_prev, float *dgamma_prev,
+                                float *dbeta_prev, const int *idx, float *dfeat_pm, int dfeat_stride,
+                                int dfeat_off, void *stream);
+
+/* Weight gradient of layer l: dw (cout,cin) += sum_{b,p} dY_l a_{l-1}^T (a_{l-1} as in the forward). */
+OGC_API int ogc_sa_mlp_layer_dw(int b, int n, int m, int nsample, int cout, int cin, int gather, const float *dz,
+                                const float *go, int go_ctotal, int go_coff, const unsigned char *sel,
+                                const float *y, const float *coef, const float *y_prev, const float *ss_prev,
+                                const float *xyz, const float *new_xyz, const float *feat_pm, const int *idx,
+                                float *dw, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,6 +36,13 @@ SIGNATURES = {
     "ogc_invariance_loss": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "ogc_count_nan": [_LL, _P, _P, _P],
     "ogc_adam_step": [_LL, _P, _P, _P, _P, _F, _F, _F, _F, _F, _I, _F, _P, _P],
+    "ogc_sa_mlp_layer_fwd": [_I] * 8 + [_P] * 14,
+    "ogc_gn_finalize": [_I, _I, _LL, _P, _P, _P, _P, _P, _P],
+    "ogc_sa_finish": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P],
+    "ogc_sa_last_stats": [_I, _I, _I, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
+    "ogc_gn_bwd_coef": [_I, _I, _LL, _P, _P, _P, _P, _P],
+    "ogc_sa_mlp_layer_dx": [_I] * 8 + [_P, _P, _I, _I] + [_P] * 14 + [_I, _I, _P],
+    "ogc_sa_mlp_layer_dw": [_I] * 7 + [_P, _P, _I, _I] + [_P] * 11,
 }
 
 _lib = None

@@ -1,0 +1,32 @@
+// Shared pieces of the fused SharedMLP kernels (mlp.cu: forward, mlp_bwd.cu: backward).
+#pragma once
+#include "common.cuh"
+
+namespace ogc {
+
+constexpr int kMlpThreads = 256;
+constexpr int kGnGroups = 4;
+constexpr float kGnEps = 1e-5f;  // nn.GroupNorm default (utils/nn_util.py:9)
+
+// acc[i][j] += sum_k A[k][row_i] * B[k][col_j];  rows {ty*4..+3, R_T/2+ty*4..+3}, cols likewise with tx.
+template <int R_T, int P_T>
+__device__ __forceinline__ void tile_gemm(const float *__restrict__ As, const float *__restrict__ Bs, int ldb, int K,
+                                          int ty, int tx, float (&acc)[8][8]) {
+    const float *a0p = As + ty * 4, *a1p = As + R_T / 2 + ty * 4;
+    const float *b0p = Bs + tx * 4, *b1p = Bs + P_T / 2 + tx * 4;
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+        const float4 a0 = *reinterpret_cast<const float4 *>(a0p + k * R_T);
+        const float4 a1 = *reinterpret_cast<const float4 *>(a1p + k * R_T);
+        const float4 b0 = *reinterpret_cast<const float4 *>(b0p + k * ldb);
+        const float4 b1 = *reinterpret_cast<const float4 *>(b1p + k * ldb);
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+}
+
+}  // namespace ogc

@@ -1,0 +1,171 @@
+"""Fused set-abstraction MLP: autograd wrapper over csrc/mlp.cu + csrc/mlp_bwd.cu.
+
+    fused_sa_mlp(xyz, new_xyz, feat_pm, idx, layers) -> (B, C_L, M)
+
+computes, for one grouper of a PointNet++ SA level (utils/pointnet2_util.py:33-44),
+    max_s  relu(GN(W_L ... relu(GN(W_1 [xyz_j - centre ; feat_j])))),   j = idx[b, m, s]
+without materialising the grouped (B,3+C,M,S) tensor or any normalised / rectified activation:
+one kernel per layer in the forward, two per layer in the backward (see the .cu headers).
+"""
+import ctypes
+
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from .backend import TIMER, get_backend
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _st():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class _FusedSAMLP(Function):
+    @staticmethod
+    def forward(ctx, xyz, new_xyz, feat_pm, idx, *params):
+        """params = (W_1, gamma_1, beta_1, ..., W_L, gamma_L, beta_L); W_l (Cout,Cin,1,1)."""
+        be = get_backend()
+        lib = be.lib
+        L = len(params) // 3
+        B, N, _ = xyz.shape
+        M, S = idx.shape[1], idx.shape[2]
+        P = M * S
+        dev = xyz.device
+        Cf = 0 if feat_pm is None else feat_pm.shape[2]
+        f32 = dict(dtype=torch.float32, device=dev)
+        ys, sss, mrs = [], [], []
+        y_prev = ss_prev = None
+        for l in range(L):
+            W, gamma, beta = params[3 * l], params[3 * l + 1], params[3 * l + 2]
+            cout, cin = W.shape[0], W.shape[1]
+            wt = W.detach().reshape(cout, cin).t().contiguous()
+            last = l == L - 1
+            y = torch.empty(B, cout, P, **f32)
+            sums = torch.zeros(B, 4, 2, dtype=torch.float64, device=dev)
+            if last:
+                ymax = torch.empty(B, cout, M, **f32)
+                ymin = torch.empty(B, cout, M, **f32)
+                amax = torch.empty(B, cout, M, dtype=torch.uint8, device=dev)
+                amin = torch.empty(B, cout, M, dtype=torch.uint8, device=dev)
+            else:
+                ymax = ymin = amax = amin = None
+            flops_bytes = B * (4 * cout * P + (4 * cin * P if l else 4 * P + 12 * N + 4 * N * Cf))
+            with TIMER.span(f"sa_mlp_fwd", flops_bytes):
+                _lib.check(lib.ogc_sa_mlp_layer_fwd(
+                    B, N, M, S, cin, cout, int(l == 0), int(last), _p(xyz), _p(new_xyz), _p(feat_pm), _p(idx),
+                    _p(y_prev), _p(ss_prev), _p(wt), _p(y), _p(sums), _p(ymax), _p(ymin), _p(amax), _p(amin), _st()),
+                    "ogc_sa_mlp_layer_fwd")
+            ss = torch.empty(B, cout, 2, **f32)
+            mr = torch.empty(B, 4, 2, **f32)
+            _lib.check(lib.ogc_gn_finalize(B, cout, (cout // 4) * P, _p(sums), _p(gamma.detach()), _p(beta.detach()),
+                                           _p(ss), _p(mr), _st()), "ogc_gn_finalize")
+            be.launches += 2
+            ys.append(y); sss.append(ss); mrs.append(mr)
+            y_prev, ss_prev = y, ss
+        cout = params[3 * (L - 1)].shape[0]
+        out = torch.empty(B, cout, M, **f32)
+        sel = torch.empty(B, cout, M, dtype=torch.uint8, device=dev)
+        ysel = torch.empty(B, cout, M, **f32)
+        _lib.check(lib.ogc_sa_finish(B, cout, M, _p(ymax), _p(ymin), _p(amax), _p(amin), _p(sss[-1]), _p(out), None,
+                                     cout, 0, _p(sel), _p(ysel), _st()), "ogc_sa_finish")
+        be.launches += 1
+        ctx.dims = (B, N, M, S, Cf, L)
+        ctx.feat_needs_grad = feat_pm is not None and feat_pm.requires_grad
+        ctx.has_feat = feat_pm is not None
+        ctx.save_for_backward(xyz, new_xyz, feat_pm if feat_pm is not None else xyz.new_empty(0), idx, sel, ysel,
+                              *ys, *sss, *mrs, *[p.detach() for p in params])
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        be = get_backend()
+        lib = be.lib
+        B, N, M, S, Cf, L = ctx.dims
+        P = M * S
+        saved = ctx.saved_tensors
+        xyz, new_xyz, feat_pm, idx, sel, ysel = saved[:6]
+        if not ctx.has_feat:
+            feat_pm = None
+        ys, sss, mrs = saved[6:6 + L], saved[6 + L:6 + 2 * L], saved[6 + 2 * L:6 + 3 * L]
+        params = saved[6 + 3 * L:]
+        dev = xyz.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        go = go.contiguous()
+        grads = [None] * (3 * L)
+        dfeat_pm = None
+
+        cL = params[3 * (L - 1)].shape[0]
+        ab = torch.zeros(B, 4, 2, dtype=torch.float64, device=dev)
+        dgamma = torch.zeros(cL, **f32)
+        dbeta = torch.zeros(cL, **f32)
+        _lib.check(lib.ogc_sa_last_stats(B, cL, M, _p(go), cL, 0, _p(sel), _p(ysel), _p(mrs[-1]), _p(params[3 * (L - 1) + 1]),
+                                         _p(ab), _p(dgamma), _p(dbeta), _st()), "ogc_sa_last_stats")
+        be.launches += 1
+        dz = None                      # last layer: synthesised from go / sel inside the kernels
+        for l in range(L - 1, -1, -1):
+            W, gamma = params[3 * l], params[3 * l + 1]
+            cout, cin = W.shape[0], W.shape[1]
+            w2d = W.reshape(cout, cin).contiguous()
+            coef = torch.empty(B, cout, 4, **f32)
+            _lib.check(lib.ogc_gn_bwd_coef(B, cout, (cout // 4) * P, _p(ab), _p(mrs[l]), _p(gamma), _p(coef), _st()),
+                       "ogc_gn_bwd_coef")
+            grads[3 * l + 1], grads[3 * l + 2] = dgamma, dbeta
+            dW = torch.zeros(cout, cin, **f32)
+            gather = l == 0
+            with TIMER.span("sa_mlp_dw", B * P * 4 * (2 * cout + cin)):
+                _lib.check(lib.ogc_sa_mlp_layer_dw(
+                    B, N, M, S, cout, cin, int(gather), _p(dz), _p(go), cL, 0, _p(sel), _p(ys[l]), _p(coef),
+                    _p(ys[l - 1]) if l else None, _p(sss[l - 1]) if l else None,
+                    _p(xyz), _p(new_xyz), _p(feat_pm), _p(idx), _p(dW), _st()), "ogc_sa_mlp_layer_dw")
+            be.launches += 2
+            grads[3 * l] = dW.view_as(W)
+            if l > 0:
+                cprev = params[3 * (l - 1)].shape[0]
+                dz_prev = torch.empty(B, cprev, P, **f32)
+                ab_prev = torch.zeros(B, 4, 2, dtype=torch.float64, device=dev)
+                dgamma_prev = torch.zeros(cprev, **f32)
+                dbeta_prev = torch.zeros(cprev, **f32)
+                with TIMER.span("sa_mlp_dx", B * P * 4 * (2 * cout + 2 * cprev)):
+                    _lib.check(lib.ogc_sa_mlp_layer_dx(
+                        B, N, M, S, cout, cin, 0, cprev, _p(dz), _p(go), cL, 0, _p(sel), _p(ys[l]), _p(coef), _p(w2d),
+                        _p(ys[l - 1]), _p(sss[l - 1]), _p(mrs[l - 1]), _p(params[3 * (l - 1) + 1]), _p(dz_prev),
+                        _p(ab_prev), _p(dgamma_prev), _p(dbeta_prev), None, None, 0, 0, _st()), "ogc_sa_mlp_layer_dx")
+                be.launches += 1
+                dz, ab, dgamma, dbeta = dz_prev, ab_prev, dgamma_prev, dbeta_prev
+            elif ctx.feat_needs_grad:
+                dfeat_pm = torch.zeros(B, N, Cf, **f32)
+                for off in range(0, Cf, 128):
+                    rows = min(128, Cf - off)
+                    with TIMER.span("sa_mlp_dx", B * P * 4 * (2 * cout + rows)):
+                        _lib.check(lib.ogc_sa_mlp_layer_dx(
+                            B, N, M, S, cout, cin, 3 + off, rows, _p(dz), _p(go), cL, 0, _p(sel), _p(ys[l]), _p(coef),
+                            _p(w2d), None, None, None, None, None, None, None, None, _p(idx), _p(dfeat_pm), Cf, off,
+                            _st()), "ogc_sa_mlp_layer_dx")
+                    be.launches += 1
+        return (None, None, dfeat_pm, None, *grads)
+
+
+def fused_sa_mlp(xyz, new_xyz, feat_pm, idx, layers):
+    """xyz (B,N,3), new_xyz (B,M,3), feat_pm (B,N,Cf) point-major or None, idx (B,M,64) int32,
+    layers = [(W, gamma, beta), ...]  ->  (B, C_L, M)."""
+    flat = [t for layer in layers for t in layer]
+    return _FusedSAMLP.apply(xyz.contiguous(), new_xyz.contiguous(),
+                             None if feat_pm is None else feat_pm.contiguous(), idx.contiguous(), *flat)
+
+
+def supported(nsample, channels):
+    """Shapes the fused kernels cover: nsample 64, output widths multiples of 16 up to 256, and the
+    (weights + operand tile) of every layer within one CTA's shared memory."""
+    if nsample != 64:
+        return False
+    for cin, cout in zip(channels[:-1], channels[1:]):
+        if cout % 16 != 0 or cout > 256:
+            return False
+        r_t, p_t = (32, 512) if cout <= 32 else (64, 256) if cout <= 64 else (128, 128) if cout <= 128 else (256, 64)
+        if cin * (r_t + p_t + 4) * 4 > 225 * 1024:
+            return False
+    return True

@@ -24,6 +24,10 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 import pointnet2.pointnet2 as ops
+from ogc_b200 import backend as _backend_mod
+from ogc_b200 import sa_fused
+
+FORCE_COMPOSED = False   # tests: run the torch-composed SA path on the GPU to compare with the fused kernels
 
 GN_GROUPS = 4  # models/segnet_kitti.py:8  BN_CONFIG = GroupNorm, 4 groups
 
@@ -114,8 +118,15 @@ class SetAbstraction(nn.Module):
         """xyz (B,N,3), features (B,C,N) -> new_xyz (B,M,3), new_features (B,sum Cout,M)."""
         sel = ops.furthest_point_sample(xyz, self.npoint).long()
         new_xyz = ops.gather_nd(xyz, sel).contiguous()
-        xyz_t = xyz.transpose(1, 2).contiguous()
-        centre = new_xyz.transpose(1, 2).unsqueeze(-1)
+        fused = (not FORCE_COMPOSED and xyz.is_cuda and getattr(_backend_mod.get_backend(), "name", "") == "b200"
+                 and all(sa_fused.supported(ns, [m.layer0.conv.weight.shape[1]] +
+                                            [getattr(m, f"layer{i}").conv.weight.shape[0] for i in range(m.n_layers)])
+                         for ns, m in zip(self.nsamples, self.mlps)))
+        if fused:
+            feat_pm = features.transpose(1, 2).contiguous()          # point-major rows for coalesced gathers
+        else:
+            xyz_t = xyz.transpose(1, 2).contiguous()
+            centre = new_xyz.transpose(1, 2).unsqueeze(-1)
         outs = []
         knn_cache = {}
         for radius, nsample, mlp in zip(self.radii, self.nsamples, self.mlps):
@@ -123,6 +134,11 @@ class SetAbstraction(nn.Module):
                 knn_cache[nsample] = ops.knn(nsample, new_xyz, xyz)
             dist, idx = knn_cache[nsample]
             idx = ops.clip_neighbours_by_radius(dist, idx, radius)
+            if fused:
+                layers = [(getattr(mlp, f"layer{i}").conv.weight, getattr(mlp, f"layer{i}").normlayer.gn.weight,
+                           getattr(mlp, f"layer{i}").normlayer.gn.bias) for i in range(mlp.n_layers)]
+                outs.append(sa_fused.fused_sa_mlp(xyz, new_xyz, feat_pm, idx, layers))
+                continue
             grouped = torch.cat([ops.grouping_operation(xyz_t, idx) - centre,
                                  ops.grouping_operation(features, idx)], dim=1)   # (B,3+C,M,S)
             outs.append(mlp(grouped).max(dim=3).values)

@@ -1,0 +1,88 @@
+"""GPU: the fused set-abstraction MLP kernels (csrc/mlp.cu, mlp_bwd.cu) against the torch-composed path
+(group -> conv1x1 as fp32 matmul -> GroupNorm -> ReLU -> max) on the same device, values and every gradient.
+fp32 tolerance: summation order differs (tiled FMA chains / atomics), nothing else."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+@pytest.mark.parametrize("N,M,Cf,widths", [
+    (512, 128, 3, [32, 32, 32]),          # SA1 scale a (features = raw coordinates)
+    (512, 128, 3, [32, 32, 64]),          # SA1 scale b
+    (400, 100, 96, [64, 64, 128]),        # SA2
+    (300, 70, 128, [128, 128, 256]),      # SA3 (ragged: P not a multiple of the tile)
+    (256, 64, 192, [128, 128, 256]),      # sapien SA2: 195 input channels, feature gradient in two row blocks
+    (256, 64, 16, [64, 64]),              # two-layer MLP
+])
+def test_fused_sa_mlp_matches_composed(b200, N, M, Cf, widths):
+    from ogc_b200 import segnet
+    from ogc_b200.sa_fused import fused_sa_mlp
+    import pointnet2.pointnet2 as ops
+    torch.manual_seed(N + Cf)
+    B, S = 3, 64
+    dev = "cuda"
+    xyz = torch.randn(B, N, 3, device=dev)
+    new_xyz = xyz[:, :M].contiguous()
+    feats = torch.randn(B, Cf, N, device=dev)
+    mlp = segnet.SharedMLP([Cf + 3] + widths).to(dev)
+    with torch.no_grad():
+        for p_name, p in mlp.named_parameters():
+            if "gn.weight" in p_name:
+                p.copy_(torch.randn_like(p) * 0.5 + 0.8)     # some negative gammas exercise the min branch
+            if "gn.bias" in p_name:
+                p.copy_(torch.randn_like(p) * 0.3)
+    dist, idx = ops.knn(S, new_xyz, xyz)
+    idx = ops.clip_neighbours_by_radius(dist, idx, 1.2)      # duplicates inside neighbourhoods, as in the model
+    probe = torch.randn(B, widths[-1], M, device=dev)
+
+    f1 = feats.clone().requires_grad_(True)
+    grouped = torch.cat([ops.grouping_operation(xyz.transpose(1, 2).contiguous(), idx) - new_xyz.transpose(1, 2).unsqueeze(-1),
+                         ops.grouping_operation(f1, idx)], dim=1)
+    ref = mlp(grouped).max(dim=3).values
+    (ref * probe).sum().backward()
+    ref_grads = {n: p.grad.clone() for n, p in mlp.named_parameters()}
+    ref_df = f1.grad.clone()
+    mlp.zero_grad()
+
+    f2 = feats.clone().requires_grad_(True)
+    layers = [(getattr(mlp, f"layer{i}").conv.weight, getattr(mlp, f"layer{i}").normlayer.gn.weight,
+               getattr(mlp, f"layer{i}").normlayer.gn.bias) for i in range(mlp.n_layers)]
+    out = fused_sa_mlp(xyz, new_xyz, f2.transpose(1, 2).contiguous(), idx, layers)
+    (out * probe).sum().backward()
+
+    assert out.shape == ref.shape
+    assert rel_err(out, ref) < 2e-5, rel_err(out, ref)
+    assert rel_err(f2.grad, ref_df) < 2e-4, rel_err(f2.grad, ref_df)
+    for n, p in mlp.named_parameters():
+        assert rel_err(p.grad, ref_grads[n]) < 2e-4, (n, rel_err(p.grad, ref_grads[n]))
+
+
+def test_segnet_fused_equals_composed_full_model(b200):
+    """Whole MaskFormer3D (kitti variant, 2048 points): fused SA path vs composed path, masks and gradients."""
+    from ogc_b200 import segnet
+    torch.manual_seed(3)
+    net = segnet.MaskFormer3D(n_slot=10, n_point=2048, variant="kitti").cuda()
+    pc = (torch.rand(2, 2048, 3, device="cuda") - 0.5) * torch.tensor([40.0, 4.0, 30.0], device="cuda")
+    probe = torch.randn(2, 2048, 10, device="cuda")
+
+    def run(force):
+        segnet.FORCE_COMPOSED = force
+        try:
+            net.zero_grad()
+            mask = net(pc, pc)
+            (mask * probe).sum().backward()
+            return mask.detach().clone(), {n: p.grad.clone() for n, p in net.named_parameters()}
+        finally:
+            segnet.FORCE_COMPOSED = False
+
+    m_ref, g_ref = run(True)
+    m_fused, g_fused = run(False)
+    assert float((m_fused - m_ref).abs().max()) < 1e-4
+    for n in g_ref:
+        assert rel_err(g_fused[n], g_ref[n]) < 2e-3, (n, rel_err(g_fused[n], g_ref[n]))
