@@ -49,6 +49,7 @@ class OpTimer:
 
     def __init__(self):
         self.enabled = False
+        self.detail = False   # per-shape span names (profiling scripts)
         self.records = []  # (name, start_event, end_event, algorithmic_bytes)
 
     @contextmanager

@@ -100,7 +100,7 @@ __device__ __forceinline__ void load_tile_dense(const float *__restrict__ y_prev
 
 // ------------------------------------------------------------------------------------------ forward
 template <int R_T, int P_T, bool GATHER, bool LAST>
-__global__ void __launch_bounds__(kMlpThreads)
+__global__ void __launch_bounds__(kMlpThreads, 2)
 mlp_fwd_kernel(MlpFwdParams q) {
     constexpr int TX = P_T / 8;
     constexpr int LDB = P_T + 4;

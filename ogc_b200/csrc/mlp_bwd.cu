@@ -124,7 +124,7 @@ struct MlpDxParams {
 };
 
 template <int R_T, int P_T, bool SCATTER>
-__global__ void __launch_bounds__(kMlpThreads)
+__global__ void __launch_bounds__(kMlpThreads, 2)
 mlp_dx_kernel(MlpDxParams q) {
     constexpr int TX = P_T / 8, LDB = P_T + 4, KC = 64;
     extern __shared__ __align__(16) float smem[];
@@ -255,7 +255,7 @@ struct MlpDwParams {
 };
 
 template <int RPT, int NC, bool GATHER>
-__global__ void __launch_bounds__(kMlpThreads)
+__global__ void __launch_bounds__(kMlpThreads, 2)
 mlp_dw_kernel(MlpDwParams q) {
     constexpr int R_T = 16 * RPT, C_T = 16 * NC, PK = kDwPK;
     __shared__ __align__(16) float As[PK][R_T];   // dY^T  [p][co]

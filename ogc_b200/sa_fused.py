@@ -54,7 +54,7 @@ class _FusedSAMLP(Function):
             else:
                 ymax = ymin = amax = amin = None
             flops_bytes = B * (4 * cout * P + (4 * cin * P if l else 4 * P + 12 * N + 4 * N * Cf))
-            with TIMER.span(f"sa_mlp_fwd", flops_bytes):
+            with TIMER.span(f"sa_mlp_fwd[{cin}>{cout}]" if TIMER.detail else "sa_mlp_fwd", flops_bytes):
                 _lib.check(lib.ogc_sa_mlp_layer_fwd(
                     B, N, M, S, cin, cout, int(l == 0), int(last), _p(xyz), _p(new_xyz), _p(feat_pm), _p(idx),
                     _p(y_prev), _p(ss_prev), _p(wt), _p(y), _p(sums), _p(ymax), _p(ymin), _p(amax), _p(amin), _st()),
@@ -116,7 +116,7 @@ class _FusedSAMLP(Function):
             grads[3 * l + 1], grads[3 * l + 2] = dgamma, dbeta
             dW = torch.zeros(cout, cin, **f32)
             gather = l == 0
-            with TIMER.span("sa_mlp_dw", B * P * 4 * (2 * cout + cin)):
+            with TIMER.span(f"sa_mlp_dw[{cin}>{cout}]" if TIMER.detail else "sa_mlp_dw", B * P * 4 * (2 * cout + cin)):
                 _lib.check(lib.ogc_sa_mlp_layer_dw(
                     B, N, M, S, cout, cin, int(gather), _p(dz), _p(go), cL, 0, _p(sel), _p(ys[l]), _p(coef),
                     _p(ys[l - 1]) if l else None, _p(sss[l - 1]) if l else None,
@@ -129,7 +129,7 @@ class _FusedSAMLP(Function):
                 ab_prev = torch.zeros(B, 4, 2, dtype=torch.float64, device=dev)
                 dgamma_prev = torch.zeros(cprev, **f32)
                 dbeta_prev = torch.zeros(cprev, **f32)
-                with TIMER.span("sa_mlp_dx", B * P * 4 * (2 * cout + 2 * cprev)):
+                with TIMER.span(f"sa_mlp_dx[{cout}>{cprev}]" if TIMER.detail else "sa_mlp_dx", B * P * 4 * (2 * cout + 2 * cprev)):
                     _lib.check(lib.ogc_sa_mlp_layer_dx(
                         B, N, M, S, cout, cin, 0, cprev, _p(dz), _p(go), cL, 0, _p(sel), _p(ys[l]), _p(coef), _p(w2d),
                         _p(ys[l - 1]), _p(sss[l - 1]), _p(mrs[l - 1]), _p(params[3 * (l - 1) + 1]), _p(dz_prev),
@@ -140,7 +140,7 @@ class _FusedSAMLP(Function):
                 dfeat_pm = torch.zeros(B, N, Cf, **f32)
                 for off in range(0, Cf, 128):
                     rows = min(128, Cf - off)
-                    with TIMER.span("sa_mlp_dx", B * P * 4 * (2 * cout + rows)):
+                    with TIMER.span(f"sa_mlp_dx[{cout}>scatter{rows}]" if TIMER.detail else "sa_mlp_dx", B * P * 4 * (2 * cout + rows)):
                         _lib.check(lib.ogc_sa_mlp_layer_dx(
                             B, N, M, S, cout, cin, 3 + off, rows, _p(dz), _p(go), cL, 0, _p(sel), _p(ys[l]), _p(coef),
                             _p(w2d), None, None, None, None, None, None, None, None, _p(idx), _p(dfeat_pm), Cf, off,
