@@ -127,6 +127,40 @@ def run_cpu_port(steps, warmup, pairs_per_step, threads):
     return clouds / dt, dt * 1e3, clouds
 
 
+def run_ref_cuda_ext(device, steps, warmup, pairs, aug):
+    """The reference's OWN CUDA extension (oracle/_ref, built from /root/reference) under the reference's op
+    sequence (segnet.REFERENCE_FAITHFUL / losses.REFERENCE_FAITHFUL) on this GPU: the denominator of
+    BASELINE.json's ">= 20x the reference pointnet2 CUDA ext" target.  Returns None when the extension was not
+    built.  The reference Python itself cannot travel to the GPU box; the mirror reproduces its call sequence."""
+    from oracle import refext
+    if not refext.available():
+        return None
+    from ogc_b200 import backend, data, losses, segnet
+    prev = backend.set_backend(refext.RefExtBackend())
+    segnet.REFERENCE_FAITHFUL = losses.REFERENCE_FAITHFUL = True
+    try:
+        trainer = build_trainer(device, 1)
+        batches = [tuple(x.to(device) for x in data.make_batch(500 + i, pairs, N_POINT, aug=aug)) for i in range(2)]
+        for i in range(warmup):
+            trainer.train_step(100000 + i, batches[i % 2], aug_transform=aug)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(steps):
+            trainer.train_step(100000 + i, batches[i % 2], aug_transform=aug)
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / steps
+    finally:
+        segnet.REFERENCE_FAITHFUL = losses.REFERENCE_FAITHFUL = False
+        backend.set_backend(prev)
+        torch.cuda.empty_cache()
+    clouds = pairs * (4 if aug else 2)
+    return {"value": clouds / (ms * 1e-3), "unit": "clouds/s", "ms_per_step": ms, "steps": steps,
+            "what": "reference pointnet2 CUDA extension (unchanged .cu, sm_100a) + reference op sequence "
+                    "(cuDNN TF32 convs, diag_embed Kabsch, per-scale kNN, SVD nuclear norm) on the same B200"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -136,6 +170,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=4, help="KITTI-SF pairs per GPU per step (reference batch_size)")
     ap.add_argument("--no-aug", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-ext", action="store_true", help="skip timing the reference CUDA extension arm")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", 0))
@@ -254,6 +289,11 @@ def main():
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "ops": op_rows,
             "loss": last_dict}
 
+    if world == 1 and not args.no_ref_ext:
+        ref = run_ref_cuda_ext(device, 2, 1, args.pairs, aug)
+        if ref is not None:
+            ref["speedup_e2e"] = line["e2e"]["value"] / ref["value"]
+            line["ref_cuda_ext"] = ref
     if world == 1 and not args.no_cpu_baseline:
         v, ms, clouds = run_cpu_port(1, 0, 1, cores)
         line["cpu_baseline"] = {"value": v, "unit": "clouds/s", "cores": cores, "kind": "port", "ms_per_step": ms,
