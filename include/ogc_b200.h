@@ -244,6 +244,13 @@ OGC_API int ogc_sa_mlp_layer_dw(int b, int n, int m, int nsample, int cout, int 
                                 const float *xyz, const float *new_xyz, const float *feat_pm, const int *idx,
                                 float *dw, void *stream);
 
+/* Diagnostic: one 128 x n x k GEMM through tcgen05.mma kind::tf32 (accumulator in TMEM, 128B-swizzled
+ * shared-memory operands).  mode 0: a (128,k), b (n,k) -> d = a b^T (K-major operands); mode 1: a (k,128),
+ * b (k,n) -> d = a^T b (MN-major operands).  split3 != 0: 3xTF32 (hi*hi + hi*lo + lo*hi), fp32-grade.
+ * n, k multiples of 32, n <= 256.  Used by the tests to pin the descriptor conventions on hardware. */
+OGC_API int ogc_tc_probe_gemm(int mode, int n, int k, int split3, const float *a, const float *b, float *d,
+                              void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -116,6 +116,7 @@ class OracleBackend:
     the operator layer (:103,134).
     """
     name = "oracle"
+    launches = 0   # interface parity with B200Backend (bench.py counts OUR kernels only)
 
     def fps(self, xyz, npoint):
         B, N, _ = xyz.shape

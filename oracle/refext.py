@@ -31,6 +31,7 @@ def module():
 
 class RefExtBackend:
     name = "refext"
+    launches = 0   # interface parity with B200Backend (bench.py counts OUR kernels only)
 
     def __init__(self):
         self.m = module()
