@@ -50,14 +50,14 @@ tc_probe_kernel(int mode, int N, int K, int split3, const float *__restrict__ A,
         for (int e = tid; e < K * M; e += blockDim.x) {
             const int k = e / M, m = e - k * M;
             const float v = A[e], hi = split3 ? tc::tf32_hi(v) : v;
-            const uint32_t off = static_cast<uint32_t>(m >> 5) * (K * 128u) + tc::sw128_offset(k, m & 31);
+            const uint32_t off = static_cast<uint32_t>(m >> 5) * (K * 128u) + tc::sw128_32b_offset(k, m & 31);
             *reinterpret_cast<float *>(a_hi + off) = hi;
             if (split3) *reinterpret_cast<float *>(a_lo + off) = v - hi;
         }
         for (int e = tid; e < K * N; e += blockDim.x) {
             const int k = e / N, n = e - k * N;
             const float v = B[e], hi = split3 ? tc::tf32_hi(v) : v;
-            const uint32_t off = static_cast<uint32_t>(n >> 5) * (K * 128u) + tc::sw128_offset(k, n & 31);
+            const uint32_t off = static_cast<uint32_t>(n >> 5) * (K * 128u) + tc::sw128_32b_offset(k, n & 31);
             *reinterpret_cast<float *>(b_hi + off) = hi;
             if (split3) *reinterpret_cast<float *>(b_lo + off) = v - hi;
         }
@@ -73,7 +73,8 @@ tc_probe_kernel(int mode, int N, int K, int split3, const float *__restrict__ A,
         const int ksteps = K / 8;
         uint32_t acc = 0;
         for (int s = 0; s < ksteps; ++s) {
-            uint32_t a_off, b_off, a_lbo, b_lbo, sbo = 1024;
+            uint32_t a_off, b_off, a_lbo, b_lbo, sbo = mode == 0 ? 1024 : 512;
+            const uint32_t layout = mode == 0 ? tc::kLayoutSw128 : tc::kLayoutSw128Base32;
             if (mode == 0) {
                 a_off = static_cast<uint32_t>(s >> 2) * (M * 128u) + static_cast<uint32_t>(s & 3) * 32u;
                 b_off = static_cast<uint32_t>(s >> 2) * (N * 128u) + static_cast<uint32_t>(s & 3) * 32u;
@@ -86,8 +87,8 @@ tc_probe_kernel(int mode, int N, int K, int split3, const float *__restrict__ A,
             for (int p = 0; p < passes; ++p) {
                 const uint8_t *ap = (p == 2) ? a_lo : a_hi;       // hi*hi, hi*lo, lo*hi
                 const uint8_t *bp = (p == 1) ? b_lo : b_hi;
-                const uint64_t ad = tc::make_desc_sw128(smem_u32(ap) + a_off, a_lbo, sbo);
-                const uint64_t bd = tc::make_desc_sw128(smem_u32(bp) + b_off, b_lbo, sbo);
+                const uint64_t ad = tc::make_desc(smem_u32(ap) + a_off, a_lbo, sbo, layout);
+                const uint64_t bd = tc::make_desc(smem_u32(bp) + b_off, b_lbo, sbo, layout);
                 tc::mma_tf32(tmem_base, ad, bd, idesc, acc);
                 acc = 1;
             }

@@ -7,8 +7,11 @@
 //   * K-major  (rows = M/N index, the 32 columns = K):  SBO = 1024 B between 8-row groups; one K=8 MMA step
 //              reads 32 B of every row, successive steps advance the start address by 32 B, the next column
 //              block after 4 steps;
-//   * MN-major (rows = K index, the 32 columns = M/N):  LBO = byte stride between column blocks, one K=8 step
-//              reads 8 rows, successive steps advance the start address by 1024 B.
+//   * MN-major (rows = K index, the 32 columns = M/N): for 32-bit (tf32) operands the hardware only accepts the
+//              "128B swizzle with 32 B base" layout: 32-byte chunk c of row r stored at chunk (c ^ (r & 3)),
+//              atoms of 4 rows (SBO = 512 B between 4-row groups), LBO = byte stride between column blocks;
+//              one K=8 step reads 8 rows, successive steps advance the start address by 1024 B.
+//              (so a tile is written for ONE of the two uses: sw128_offset vs sw128_32b_offset)
 // Descriptor bit layout: cute/arch/mma_sm100_desc.hpp (SmemDescriptor, InstrDescriptor) of CUTLASS.
 #pragma once
 #include "common.cuh"
@@ -24,15 +27,27 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int col) {
     return static_cast<uint32_t>(row) * 128u + static_cast<uint32_t>(chunk) * 16u + static_cast<uint32_t>(col & 3) * 4u;
 }
 
-// Shared-memory matrix descriptor, SWIZZLE_128B, version 1 (Blackwell).
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// byte offset of element (row, col) inside one column block for MN-major tf32 use (32 B swizzle base)
+__device__ __forceinline__ uint32_t sw128_32b_offset(int row, int col) {
+    const int chunk = (col >> 3) ^ (row & 3);
+    return static_cast<uint32_t>(row) * 128u + static_cast<uint32_t>(chunk) * 32u + static_cast<uint32_t>(col & 7) * 4u;
+}
+
+constexpr uint32_t kLayoutSw128 = 2;        // UMMA::LayoutType::SWIZZLE_128B
+constexpr uint32_t kLayoutSw128Base32 = 1;  // UMMA::LayoutType::SWIZZLE_128B_BASE32B
+
+// Shared-memory matrix descriptor, version 1 (Blackwell).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
     d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
     d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
     d |= static_cast<uint64_t>(1) << 46;   // descriptor version
-    d |= static_cast<uint64_t>(2) << 61;   // layout type: SWIZZLE_128B
+    d |= static_cast<uint64_t>(layout) << 61;
     return d;
+}
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return make_desc(smem_addr, lbo_bytes, sbo_bytes, kLayoutSw128);
 }
 
 // Instruction descriptor for kind::tf32, fp32 accumulate.  a_mn / b_mn: 1 = MN-major operand.
