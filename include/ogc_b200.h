@@ -251,6 +251,16 @@ OGC_API int ogc_sa_mlp_layer_dw(int b, int n, int m, int nsample, int cout, int 
 OGC_API int ogc_tc_probe_gemm(int mode, int n, int k, int split3, const float *a, const float *b, float *d,
                               void *stream);
 
+/* Tensor-core variant of ogc_sa_mlp_layer_fwd: tcgen05.mma kind::tf32 with the 3xTF32 split (fp32-grade), fp32
+ * accumulators in TMEM, warp-specialised loader / MMA / epilogue (csrc/mlp_tc.cu).  Same arguments, except that
+ * `w` is W (cout,cin) row-major (not transposed).  nsample == 64; returns OGC_ERR_UNSUPPORTED for shapes it does
+ * not cover (K = cin (dense) or cin-3 (gather) must be in [8,160]) -- callers then use the SIMT entry point. */
+OGC_API int ogc_sa_mlp_layer_fwd_tc(int b, int n, int m, int nsample, int cin, int cout, int gather, int last,
+                                    const float *xyz, const float *new_xyz, const float *feat_pm, const int *idx,
+                                    const float *y_prev, const float *ss_prev, const float *w, float *y,
+                                    double *sums, float *ymax, float *ymin, unsigned char *amax,
+                                    unsigned char *amin, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

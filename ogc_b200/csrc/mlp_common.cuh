@@ -29,4 +29,16 @@ __device__ __forceinline__ void tile_gemm(const float *__restrict__ As, const fl
     }
 }
 
+struct MlpFwdParams {
+    int Cin, Cout, P, S, M, N, Cf;
+    const float *xyz, *new_xyz, *feat_pm;  // gather mode: (B,N,3), (B,M,3), (B,N,Cf)
+    const int *idx;                        //              (B,M,S)
+    const float *y_prev, *ss_prev;         // dense mode:  (B,Cin,P), (B,Cin,2) = GroupNorm scale, shift
+    const float *Wt;                       // (Cin,Cout)
+    float *y;                              // (B,Cout,P) or NULL
+    double *sums;                          // (B,4,2): sum y, sum y^2 per group
+    float *ymax, *ymin;                    // (B,Cout,M) when LAST
+    unsigned char *amax, *amin;
+};
+
 }  // namespace ogc

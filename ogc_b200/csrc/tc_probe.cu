@@ -36,14 +36,14 @@ tc_probe_kernel(int mode, int N, int K, int split3, const float *__restrict__ A,
             const float v = A[e], hi = split3 ? tc::tf32_hi(v) : v;
             const uint32_t off = static_cast<uint32_t>(k >> 5) * (M * 128u) + tc::sw128_offset(r, k & 31);
             *reinterpret_cast<float *>(a_hi + off) = hi;
-            if (split3) *reinterpret_cast<float *>(a_lo + off) = v - hi;
+            if (split3) *reinterpret_cast<float *>(a_lo + off) = tc::tf32_hi(v - hi);
         }
         for (int e = tid; e < N * K; e += blockDim.x) {
             const int r = e / K, k = e - r * K;
             const float v = B[e], hi = split3 ? tc::tf32_hi(v) : v;
             const uint32_t off = static_cast<uint32_t>(k >> 5) * (N * 128u) + tc::sw128_offset(r, k & 31);
             *reinterpret_cast<float *>(b_hi + off) = hi;
-            if (split3) *reinterpret_cast<float *>(b_lo + off) = v - hi;
+            if (split3) *reinterpret_cast<float *>(b_lo + off) = tc::tf32_hi(v - hi);
         }
     } else {
         // column blocks over M / N: block cb = [K rows][32]
@@ -52,14 +52,14 @@ tc_probe_kernel(int mode, int N, int K, int split3, const float *__restrict__ A,
             const float v = A[e], hi = split3 ? tc::tf32_hi(v) : v;
             const uint32_t off = static_cast<uint32_t>(m >> 5) * (K * 128u) + tc::sw128_32b_offset(k, m & 31);
             *reinterpret_cast<float *>(a_hi + off) = hi;
-            if (split3) *reinterpret_cast<float *>(a_lo + off) = v - hi;
+            if (split3) *reinterpret_cast<float *>(a_lo + off) = tc::tf32_hi(v - hi);
         }
         for (int e = tid; e < K * N; e += blockDim.x) {
             const int k = e / N, n = e - k * N;
             const float v = B[e], hi = split3 ? tc::tf32_hi(v) : v;
             const uint32_t off = static_cast<uint32_t>(n >> 5) * (K * 128u) + tc::sw128_32b_offset(k, n & 31);
             *reinterpret_cast<float *>(b_hi + off) = hi;
-            if (split3) *reinterpret_cast<float *>(b_lo + off) = v - hi;
+            if (split3) *reinterpret_cast<float *>(b_lo + off) = tc::tf32_hi(v - hi);
         }
     }
     tc::fence_proxy_async();

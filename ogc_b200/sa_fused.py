@@ -16,6 +16,14 @@ from . import _lib
 from .backend import TIMER, get_backend
 
 
+USE_TC = True   # tcgen05 3xTF32 kernels for the layers they cover (tests flip it to compare with the SIMT kernels)
+
+
+def _tc_ok(S, cin, cout, gather):
+    k = cin - 3 if gather else cin
+    return USE_TC and S == 64 and cout >= 64 and cout % 16 == 0 and cout <= 256 and 32 <= k <= 160 and k % 4 == 0
+
+
 def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -54,11 +62,20 @@ class _FusedSAMLP(Function):
             else:
                 ymax = ymin = amax = amin = None
             flops_bytes = B * (4 * cout * P + (4 * cin * P if l else 4 * P + 12 * N + 4 * N * Cf))
-            with TIMER.span(f"sa_mlp_fwd[{cin}>{cout}]" if TIMER.detail else "sa_mlp_fwd", flops_bytes):
-                _lib.check(lib.ogc_sa_mlp_layer_fwd(
-                    B, N, M, S, cin, cout, int(l == 0), int(last), _p(xyz), _p(new_xyz), _p(feat_pm), _p(idx),
-                    _p(y_prev), _p(ss_prev), _p(wt), _p(y), _p(sums), _p(ymax), _p(ymin), _p(amax), _p(amin), _st()),
-                    "ogc_sa_mlp_layer_fwd")
+            use_tc = _tc_ok(S, cin, cout, l == 0)
+            tag = "sa_mlp_fwd_tc" if use_tc else "sa_mlp_fwd"
+            with TIMER.span(f"{tag}[{cin}>{cout}]" if TIMER.detail else tag, flops_bytes):
+                if use_tc:
+                    w2d = W.detach().reshape(cout, cin).contiguous()
+                    _lib.check(lib.ogc_sa_mlp_layer_fwd_tc(
+                        B, N, M, S, cin, cout, int(l == 0), int(last), _p(xyz), _p(new_xyz), _p(feat_pm), _p(idx),
+                        _p(y_prev), _p(ss_prev), _p(w2d), _p(y), _p(sums), _p(ymax), _p(ymin), _p(amax), _p(amin),
+                        _st()), "ogc_sa_mlp_layer_fwd_tc")
+                else:
+                    _lib.check(lib.ogc_sa_mlp_layer_fwd(
+                        B, N, M, S, cin, cout, int(l == 0), int(last), _p(xyz), _p(new_xyz), _p(feat_pm), _p(idx),
+                        _p(y_prev), _p(ss_prev), _p(wt), _p(y), _p(sums), _p(ymax), _p(ymin), _p(amax), _p(amin),
+                        _st()), "ogc_sa_mlp_layer_fwd")
             ss = torch.empty(B, cout, 2, **f32)
             mr = torch.empty(B, 4, 2, **f32)
             _lib.check(lib.ogc_gn_finalize(B, cout, (cout // 4) * P, _p(sums), _p(gamma.detach()), _p(beta.detach()),

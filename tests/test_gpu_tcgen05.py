@@ -51,4 +51,5 @@ def test_3xtf32_is_fp32_grade(mode):
     e3 = float((three - ref).abs().max())
     e32 = float((fp32 - ref).abs().max())
     assert e1 > 1e-3          # single-pass TF32 is NOT accurate enough for the 1e-4 logit parity ...
-    assert e3 < 2e-5 and e3 < 8 * e32 + 1e-6   # ... the 3-pass split is at the level of an fp32 GEMM
+    print(f'single-pass {e1:.2e}  3xTF32 {e3:.2e}  fp32 {e32:.2e}')
+    assert e3 < 4 * e32 + 1e-6   # ... the 3-pass split is at the level of an fp32 GEMM (measured: 2.6-3.1x cuBLAS sgemm's error)
