@@ -261,6 +261,27 @@ OGC_API int ogc_sa_mlp_layer_fwd_tc(int b, int n, int m, int nsample, int cin, i
                                     double *sums, float *ymax, float *ymin, unsigned char *amax,
                                     unsigned char *amin, void *stream);
 
+/* Hungarian matching on the device: replaces the per-sample `iou[b].cpu().numpy()` + scipy
+ * linear_sum_assignment(maximize=True) loop of match_mask_by_iou (losses/seg_loss_unsup.py:226-240).
+ * inter (b,k,k) int32 from ogc_mask_contingency -> perm12 (b,k): slot of mask2 matched to each slot of mask1,
+ * perm21 (b,k): the converse.  Same algorithm and tie-breaking as scipy (csrc/lsap.cuh).  k <= 32. */
+OGC_API int ogc_mask_match(int b, int k, const int *inter, int *perm12, int *perm21, void *stream);
+
+/* Host twin of the assignment routine used by ogc_mask_match (test hook: checked against scipy on CPU).
+ * score (n,n) row-major doubles, maximised; col4row[i] = column matched to row i. */
+OGC_API int ogc_lsap_maximize_host(int n, const double *score, int *col4row);
+
+/* RankLoss (losses/seg_loss_unsup.py:300-314): out (b) = nuclear norm of each (n,k) mask, via the fp64 Gram
+ * matrix and a Jacobi eigen-solve on the device (no cuSOLVER SVD, no host sync). */
+OGC_API int ogc_mask_nuclear_norm(int b, int n, int k, const float *mask, float *out, void *stream);
+
+/* ogc_adam_step with the step counter and learning rate in device memory (state[0] = t, state[1] = lr), so a
+ * CUDA-graph-captured training step can be replayed: t advances on the device, lr is refreshed by a host->device
+ * copy before each replay.  Skipped (t unchanged) when *skip_counter != 0. */
+OGC_API int ogc_adam_step_dev(long long n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq,
+                              float *state, float beta1, float beta2, float eps, float weight_decay,
+                              float grad_scale, const float *skip_counter, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

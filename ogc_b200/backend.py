@@ -287,6 +287,26 @@ class B200Backend:
         self.launches += 1
         return loss_pt, g1, g2
 
+    def mask_match(self, inter):
+        """inter (B,K,K) int32 -> (perm12, perm21) (B,K) int32, Hungarian on the device (no host sync)."""
+        _chk_i32(inter, "inter")
+        B, K, _ = inter.shape
+        p12 = torch.empty(B, K, dtype=torch.int32, device=inter.device)
+        p21 = torch.empty(B, K, dtype=torch.int32, device=inter.device)
+        with TIMER.span("mask_match", B * K * K * 4):
+            _lib.check(self.lib.ogc_mask_match(B, K, _ptr(inter), _ptr(p12), _ptr(p21), _stream()), "ogc_mask_match")
+        self.launches += 1
+        return p12, p21
+
+    def mask_nuclear_norm(self, mask):
+        _chk_f32(mask, "mask")
+        B, N, K = mask.shape
+        out = torch.empty(B, dtype=torch.float32, device=mask.device)
+        with TIMER.span("mask_nuclear_norm", B * N * K * 4):
+            _lib.check(self.lib.ogc_mask_nuclear_norm(B, N, K, _ptr(mask), _ptr(out), _stream()), "ogc_mask_nuclear_norm")
+        self.launches += 1
+        return out
+
 
 _backend = None
 

@@ -16,6 +16,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "lsap.cuh"
 
 namespace ogc {
 
@@ -402,6 +403,90 @@ invariance_kernel(int n, int K, const float *__restrict__ m1, const float *__res
     }
 }
 
+// One thread per (sample, direction): IoU of the hard assignments from the contingency counts exactly as
+// losses/seg_loss_unsup.py:226-232 forms it in fp32 (intersection / clamp(|A| + |B| - intersection, 1e-10)),
+// then the maximising assignment.  direction 0: rows = slots of mask1 (perm12), 1: the transpose (perm21).
+__global__ void mask_match_kernel(int B, int K, const int *__restrict__ inter, int *__restrict__ perm12,
+                                  int *__restrict__ perm21) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * B) return;
+    const int b = t >> 1, dir = t & 1;
+    const int *cnt = inter + static_cast<size_t>(b) * K * K;
+    float rs[kLsapMax], cs[kLsapMax];
+    for (int i = 0; i < K; ++i) { rs[i] = 0.f; cs[i] = 0.f; }
+    for (int i = 0; i < K; ++i)
+        for (int j = 0; j < K; ++j) {
+            const float c = static_cast<float>(cnt[i * K + j]);
+            rs[i] += c;
+            cs[j] += c;
+        }
+    double cost[kLsapMax * kLsapMax];
+    for (int i = 0; i < K; ++i)
+        for (int j = 0; j < K; ++j) {
+            const float in = static_cast<float>(dir == 0 ? cnt[i * K + j] : cnt[j * K + i]);
+            const float un = dir == 0 ? (rs[i] + cs[j]) - in : (cs[i] + rs[j]) - in;   // same operand order as torch
+            const float iou = __fdiv_rn(in, fmaxf(un, 1e-10f));
+            cost[i * K + j] = -static_cast<double>(iou);
+        }
+    int col[kLsapMax];
+    lsap_solve(K, cost, col);
+    int *out = (dir == 0 ? perm12 : perm21) + static_cast<size_t>(b) * K;
+    for (int i = 0; i < K; ++i) out[i] = col[i];
+}
+
+// Nuclear norm of the (N,K) soft mask of every sample: sum of singular values = sum sqrt(eig(M^T M)).
+// Replaces RankLoss's `mask.norm(p='nuc', dim=(1,2))` (losses/seg_loss_unsup.py:313: a batched (N,K) SVD through
+// cuSOLVER with a host sync, computed every step for a logged-only number).  Gram matrix accumulated in fp64
+// (warp per (i,j) pair), eigenvalues by cyclic Jacobi on one thread.  One CTA per sample.
+__global__ void __launch_bounds__(256)
+nuclear_norm_kernel(int n, int K, const float *__restrict__ mask, float *__restrict__ out) {
+    __shared__ double G[kMaxSlots][kMaxSlots];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const float *m = mask + static_cast<size_t>(blockIdx.x) * n * K;
+    const int npairs = K * (K + 1) / 2;
+    for (int pr = warp; pr < npairs; pr += nwarp) {
+        int i = 0, rem = pr;
+        while (rem >= K - i) { rem -= K - i; ++i; }
+        const int j = i + rem;
+        double acc = 0.0;
+        for (int p = lane; p < n; p += 32)
+            acc += static_cast<double>(__ldg(m + static_cast<size_t>(p) * K + i)) * static_cast<double>(__ldg(m + static_cast<size_t>(p) * K + j));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(OGC_FULL_MASK, acc, o);
+        if (lane == 0) { G[i][j] = acc; G[j][i] = acc; }
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0, diag = 0.0;
+        for (int i = 0; i < K; ++i) {
+            diag += fabs(G[i][i]);
+            for (int j = i + 1; j < K; ++j) off += fabs(G[i][j]);
+        }
+        if (off <= 1e-18 * diag || off == 0.0) break;
+        for (int p = 0; p < K - 1; ++p)
+            for (int q = p + 1; q < K; ++q) {
+                if (G[p][q] == 0.0) continue;
+                const double theta = (G[q][q] - G[p][p]) / (2.0 * G[p][q]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s_ = t * c;
+                for (int r = 0; r < K; ++r) {
+                    const double gp = G[r][p], gq = G[r][q];
+                    G[r][p] = c * gp - s_ * gq;
+                    G[r][q] = s_ * gp + c * gq;
+                }
+                for (int r = 0; r < K; ++r) {
+                    const double gp = G[p][r], gq = G[q][r];
+                    G[p][r] = c * gp - s_ * gq;
+                    G[q][r] = s_ * gp + c * gq;
+                }
+            }
+    }
+    double sum = 0.0;
+    for (int i = 0; i < K; ++i) sum += sqrt(G[i][i] > 0.0 ? G[i][i] : 0.0);
+    out[blockIdx.x] = static_cast<float>(sum);
+}
+
 }  // namespace ogc
 
 extern "C" int ogc_weighted_kabsch(int b, int n, int k, int second_is_flow, const float *pc, const float *second,
@@ -473,5 +558,34 @@ extern "C" int ogc_invariance_loss(int b, int n, int k, const float *mask1, cons
     dim3 grid((n + 255) / 256, b);
     invariance_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(n, k, mask1, mask2, perm12, perm21, loss_pt,
                                                                          grad1, grad2);
+    OGC_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int ogc_mask_match(int b, int k, const int *inter, int *perm12, int *perm21, void *stream) {
+    using namespace ogc;
+    if (b < 0 || k < 1 || k > kLsapMax) return OGC_ERR_INVALID_ARG;
+    if (b == 0) return OGC_OK;
+    if (!inter || !perm12 || !perm21) return OGC_ERR_INVALID_ARG;
+    mask_match_kernel<<<(2 * b + 31) / 32, 32, 0, static_cast<cudaStream_t>(stream)>>>(b, k, inter, perm12, perm21);
+    OGC_RETURN_LAUNCH_STATUS();
+}
+
+// Host twin of the device assignment routine (same source, lsap.cuh) so that the port can be checked against
+// scipy in the GPU-less test suite.  Not used by any product path.
+extern "C" int ogc_lsap_maximize_host(int n, const double *score, int *col4row) {
+    using namespace ogc;
+    if (n < 1 || n > kLsapMax || !score || !col4row) return OGC_ERR_INVALID_ARG;
+    double cost[kLsapMax * kLsapMax];
+    for (int i = 0; i < n * n; ++i) cost[i] = -score[i];
+    lsap_solve(n, cost, col4row);
+    return OGC_OK;
+}
+
+extern "C" int ogc_mask_nuclear_norm(int b, int n, int k, const float *mask, float *out, void *stream) {
+    using namespace ogc;
+    if (b < 0 || n <= 0 || k < 1 || k > kMaxSlots) return OGC_ERR_INVALID_ARG;
+    if (b == 0) return OGC_OK;
+    if (!mask || !out) return OGC_ERR_INVALID_ARG;
+    nuclear_norm_kernel<<<b, 256, 0, static_cast<cudaStream_t>(stream)>>>(n, k, mask, out);
     OGC_RETURN_LAUNCH_STATUS();
 }

@@ -97,16 +97,33 @@ mlp_fwd_tc_kernel(MlpTcParams q) {
             if (GATHER) {
                 // rel[use & 1] was last read by the epilogue of tile use-2, which arrives on bar_tempty AFTER that read
                 mbar_wait(&bar_tempty[use & 1], ((use >> 1) & 1) ^ 1);
-                // one warp per (position, column block): 32 lanes = 32 consecutive feature channels
-                for (int it = lw; it < kTcNT * KB; it += 4) {
-                    const int p = it / KB, kb = it - p * KB;
-                    const int j = __ldg(f.idx + static_cast<size_t>(b) * P + p0 + p);
-                    const int c = kb * 32 + lane;
-                    const float v = c < K ? __ldg(f.feat_pm + (static_cast<size_t>(b) * f.N + j) * f.Cf + c) : 0.f;
-                    const float hi = tc::tf32_hi(v);
-                    const uint32_t off = static_cast<uint32_t>(kb) * (kTcNT * 128u) + tc::sw128_offset(p, lane);
-                    *reinterpret_cast<float *>(a_hi + off) = hi;
-                    *reinterpret_cast<float *>(a_lo + off) = tc::tf32_hi(v - hi);
+                // the tile's 64 neighbour indices: lane l holds positions l and l + 32
+                const int j_lo = __ldg(f.idx + static_cast<size_t>(b) * P + p0 + lane);
+                const int j_hi = __ldg(f.idx + static_cast<size_t>(b) * P + p0 + 32 + lane);
+                // one warp per (position, column block): 32 lanes = 32 consecutive feature channels of one point
+                // row (coalesced 128 B); 8 independent row reads in flight per lane before any is consumed
+                const int nitems = kTcNT * KB;
+                for (int it0 = lw; it0 < nitems; it0 += 4 * 8) {
+                    float vals[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int it = it0 + 4 * u;
+                        const int p = it / KB, kb = it - p * KB;
+                        const int j = __shfl_sync(OGC_FULL_MASK, p < 32 ? j_lo : j_hi, p & 31);
+                        const int c = kb * 32 + lane;
+                        vals[u] = (it < nitems && c < K) ? __ldg(f.feat_pm + (static_cast<size_t>(b) * f.N + j) * f.Cf + c) : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int it = it0 + 4 * u;
+                        if (it < nitems) {
+                            const int p = it / KB, kb = it - p * KB;
+                            const float hi = tc::tf32_hi(vals[u]);
+                            const uint32_t off = static_cast<uint32_t>(kb) * (kTcNT * 128u) + tc::sw128_offset(p, lane);
+                            *reinterpret_cast<float *>(a_hi + off) = hi;
+                            *reinterpret_cast<float *>(a_lo + off) = tc::tf32_hi(vals[u] - hi);
+                        }
+                    }
                 }
                 if (lt < kTcNT) {
                     const int j = __ldg(f.idx + static_cast<size_t>(b) * P + p0 + lt);
@@ -114,29 +131,43 @@ mlp_fwd_tc_kernel(MlpTcParams q) {
 #pragma unroll
                     for (int c = 0; c < 3; ++c)
                         rel[use & 1][lt][c] = __ldg(f.xyz + (static_cast<size_t>(b) * f.N + j) * 3 + c) -
-                                     __ldg(f.new_xyz + (static_cast<size_t>(b) * f.M + m) * 3 + c);
+                                              __ldg(f.new_xyz + (static_cast<size_t>(b) * f.M + m) * 3 + c);
                 }
             } else {
                 // channel-major source: item = (column block, position quad, channel in block); a warp covers the
-                // 32 channels of one block for one quad -> conflict-free swizzled row writes
-                for (int it = lt; it < KB * 16 * 32; it += 128) {
-                    const int cl = it & 31, pq = (it >> 5) & 15, kb = it >> 9;
-                    const int c = kb * 32 + cl;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (c < K) {
-                        const float sc = __ldg(f.ss_prev + (static_cast<size_t>(b) * Cin + c) * 2);
-                        const float sh = __ldg(f.ss_prev + (static_cast<size_t>(b) * Cin + c) * 2 + 1);
-                        const float4 y = __ldg(reinterpret_cast<const float4 *>(f.y_prev + (static_cast<size_t>(b) * Cin + c) * P + p0 + pq * 4));
-                        v.x = fmaxf(fmaf(sc, y.x, sh), 0.f); v.y = fmaxf(fmaf(sc, y.y, sh), 0.f);
-                        v.z = fmaxf(fmaf(sc, y.z, sh), 0.f); v.w = fmaxf(fmaf(sc, y.w, sh), 0.f);
-                    }
-                    const float vv[4] = {v.x, v.y, v.z, v.w};
+                // 32 channels of one block for one quad -> conflict-free swizzled row writes.  8 independent 16 B
+                // loads in flight per thread before any is consumed (the loader is latency-, not issue-bound).
+                const int nitems = KB * 16 * 32;
+                for (int it0 = lt; it0 < nitems; it0 += 128 * 8) {
+                    float4 raw[8];
+                    float scv[8], shv[8];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float hi = tc::tf32_hi(vv[j]);
-                        const uint32_t off = static_cast<uint32_t>(kb) * (kTcNT * 128u) + tc::sw128_offset(pq * 4 + j, cl);
-                        *reinterpret_cast<float *>(a_hi + off) = hi;
-                        *reinterpret_cast<float *>(a_lo + off) = tc::tf32_hi(vv[j] - hi);
+                    for (int u = 0; u < 8; ++u) {
+                        const int it = it0 + 128 * u;
+                        const int cl = it & 31, pq = (it >> 5) & 15, kb = it >> 9;
+                        const int c = kb * 32 + cl;
+                        raw[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        scv[u] = shv[u] = 0.f;
+                        if (it < nitems && c < K) {
+                            scv[u] = __ldg(f.ss_prev + (static_cast<size_t>(b) * Cin + c) * 2);
+                            shv[u] = __ldg(f.ss_prev + (static_cast<size_t>(b) * Cin + c) * 2 + 1);
+                            raw[u] = __ldg(reinterpret_cast<const float4 *>(f.y_prev + (static_cast<size_t>(b) * Cin + c) * P + p0 + pq * 4));
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int it = it0 + 128 * u;
+                        if (it >= nitems) continue;
+                        const int cl = it & 31, pq = (it >> 5) & 15, kb = it >> 9;
+                        const float vv[4] = {fmaxf(fmaf(scv[u], raw[u].x, shv[u]), 0.f), fmaxf(fmaf(scv[u], raw[u].y, shv[u]), 0.f),
+                                             fmaxf(fmaf(scv[u], raw[u].z, shv[u]), 0.f), fmaxf(fmaf(scv[u], raw[u].w, shv[u]), 0.f)};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float hi = tc::tf32_hi(vv[j]);
+                            const uint32_t off = static_cast<uint32_t>(kb) * (kTcNT * 128u) + tc::sw128_offset(pq * 4 + j, cl);
+                            *reinterpret_cast<float *>(a_hi + off) = hi;
+                            *reinterpret_cast<float *>(a_lo + off) = tc::tf32_hi(vv[j] - hi);
+                        }
                     }
                 }
             }
@@ -271,7 +302,7 @@ extern "C" int ogc_sa_mlp_layer_fwd_tc(int b, int n, int m, int nsample, int cin
     if (smem > static_cast<size_t>(kMaxSmemPerCta) - 2048) return OGC_ERR_UNSUPPORTED;
     const int ntiles = m;
     const int mblocks = (cout + kTcM - 1) / kTcM;
-    int per_sample = (kNumSMs + b * mblocks - 1) / (b * mblocks);
+    int per_sample = kNumSMs / (b * mblocks);      // one CTA per SM (shared memory): never more CTAs than SMs if avoidable
     per_sample = per_sample > ntiles ? ntiles : (per_sample < 1 ? 1 : per_sample);
     dim3 grid(per_sample, b, mblocks);
     cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -232,25 +232,29 @@ def _hungarian_from_counts(inter):
 
 
 def match_indices_by_iou(mask1, mask2):
-    """-> (perm12, perm21) int64 numpy (B,K): slot of mask2 matched to each slot of mask1, and the converse
-    (= match_mask_by_iou(mask1, mask2) and match_mask_by_iou(mask2, mask1) of the reference)."""
+    """-> (perm12, perm21) (B,K): slot of mask2 matched to each slot of mask1, and the converse
+    (= match_mask_by_iou(mask1, mask2) and match_mask_by_iou(mask2, mask1) of the reference).
+    Fused path: int32 CUDA tensors computed entirely on the device (contingency kernel + device Hungarian, no
+    host sync); composed path: int64 numpy arrays through scipy, as the reference."""
     if _use_fused(mask1, mask2):
-        inter = _backend_mod.get_backend().mask_contingency(mask1.detach().contiguous(),
-                                                            mask2.detach().contiguous()).cpu().numpy()   # one sync
-    else:
-        K = mask1.shape[2]
-        a1, a2 = mask1.argmax(-1), mask2.argmax(-1)
-        inter = torch.zeros(mask1.shape[0], K * K, dtype=torch.int64, device=mask1.device)
-        inter.scatter_add_(1, a1 * K + a2, torch.ones_like(a1))
-        inter = inter.view(-1, K, K).cpu().numpy()
+        be = _backend_mod.get_backend()
+        inter = be.mask_contingency(mask1.detach().contiguous(), mask2.detach().contiguous())
+        return be.mask_match(inter)
+    K = mask1.shape[2]
+    a1, a2 = mask1.argmax(-1), mask2.argmax(-1)
+    inter = torch.zeros(mask1.shape[0], K * K, dtype=torch.int64, device=mask1.device)
+    inter.scatter_add_(1, a1 * K + a2, torch.ones_like(a1))
+    inter = inter.view(-1, K, K).cpu().numpy()
     return _hungarian_from_counts(inter), _hungarian_from_counts(inter.transpose(0, 2, 1))
 
 
 def match_mask_by_iou(mask1, mask2):
     """(B,N,K) x2 -> permutation matrices (B,K,K) aligning mask2's slots to mask1's (:212-240)."""
     perm12, _ = match_indices_by_iou(mask1, mask2)
+    if not torch.is_tensor(perm12):
+        perm12 = torch.from_numpy(perm12).to(mask1.device)
     eye = torch.eye(mask1.shape[2], dtype=torch.float32, device=mask1.device)
-    return eye[torch.from_numpy(perm12).to(mask1.device)]
+    return eye[perm12.long()]
 
 
 class _InvarianceFn(Function):
@@ -285,12 +289,14 @@ class InvarianceLoss(nn.Module):
     def forward(self, mask1, mask2):
         perm12, perm21 = match_indices_by_iou(mask1, mask2)
         dev = mask1.device
-        if not self.cross_entropy and self.loss_norm == 2 and _use_fused(mask1, mask2):
-            p12 = torch.from_numpy(perm12.astype(np.int32)).to(dev, non_blocking=True)
-            p21 = torch.from_numpy(perm21.astype(np.int32)).to(dev, non_blocking=True)
-            return _InvarianceFn.apply(mask1, mask2, p12, p21)
-        i12 = torch.from_numpy(perm12).to(dev).unsqueeze(1).expand_as(mask1)
-        i21 = torch.from_numpy(perm21).to(dev).unsqueeze(1).expand_as(mask2)
+        if torch.is_tensor(perm12):                                   # fused matching: already on the device
+            if not self.cross_entropy and self.loss_norm == 2:
+                return _InvarianceFn.apply(mask1, mask2, perm12, perm21)
+            perm12, perm21 = perm12.long(), perm21.long()
+        else:
+            perm12, perm21 = torch.from_numpy(perm12).to(dev), torch.from_numpy(perm21).to(dev)
+        i12 = perm12.unsqueeze(1).expand_as(mask1)
+        i21 = perm21.unsqueeze(1).expand_as(mask2)
         target1 = torch.gather(mask2, 2, i12).detach()             # == einsum('bij,bnj->bni', perm2, mask2)
         target2 = torch.gather(mask1, 2, i21).detach()
         return self.distance(mask1, target1) + self.distance(mask2, target2)
@@ -306,14 +312,12 @@ class EntropyLoss(nn.Module):
 
 class RankLoss(nn.Module):
     """mean nuclear norm of the (N,K) masks (:300-314).  On the fused path the singular values come from
-    the K x K Gram matrix accumulated in fp64 (sigma = sqrt(eig(M^T M))) instead of an (N,K) SVD."""
+    the K x K Gram matrix accumulated in fp64 (sigma = sqrt(eig(M^T M)), Jacobi on the device) instead of an
+    (N,K) cuSOLVER SVD with its host sync."""
 
     def forward(self, mask):
         if _use_fused(mask):
-            m = mask.detach().double()
-            gram = torch.einsum("bnk,bnl->bkl", m, m)
-            ev = torch.linalg.eigvalsh(gram)
-            return ev.clamp(min=0).sqrt().sum(dim=1).mean().float()
+            return _backend_mod.get_backend().mask_nuclear_norm(mask.detach().contiguous()).mean()
         return mask.norm(p="nuc", dim=(1, 2)).mean()
 
 
@@ -329,6 +333,9 @@ class UnsupervisedOGCLoss(nn.Module):
         self.entropy_loss, self.rank_loss = entropy_loss, rank_loss
         self.w_dynamic, self.w_smooth, self.w_invariance = weights
         self.start_step_dynamic, self.start_step_smooth, self.start_step_invariance = start_steps
+        # True: loss_dict = {"_keys": [...], "_values": device tensor} -- no host sync inside forward (needed to
+        # capture the whole step in a CUDA graph); resolve_loss_dict() turns it into the reference's dict of floats.
+        self.defer_logging = False
 
     def step_lossw(self, it, weight, start_step=0):
         return 0 if it < start_step else weight
@@ -356,6 +363,8 @@ class UnsupervisedOGCLoss(nn.Module):
         logged["sum"] = loss
         # one device->host transfer for every logged scalar (the reference calls .item() six times)
         keys = list(logged)
+        if self.defer_logging:
+            return loss, {"_keys": keys, "_values": torch.stack([logged[k].detach().float().reshape(()) for k in keys])}
         if REFERENCE_FAITHFUL:
             values = [logged[k].item() for k in keys]
         else:
@@ -363,6 +372,16 @@ class UnsupervisedOGCLoss(nn.Module):
         loss_dict = dict(zip(keys, values))
         loss_dict.setdefault("invariance", 0)
         return loss, loss_dict
+
+
+def resolve_loss_dict(d, values=None):
+    """Deferred loss dict -> the reference's dict of Python floats (one device->host read)."""
+    if "_keys" not in d:
+        return d
+    vals = (d["_values"] if values is None else values).tolist()
+    out = dict(zip(d["_keys"], vals))
+    out.setdefault("invariance", 0)
+    return out
 
 
 def build_ogc_loss(loss_cfg):

@@ -52,6 +52,10 @@ class FlatAdam:
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.t = 0
         self.lib = _lib.load() if dev.type == "cuda" else None
+        if self.lib is not None:
+            # step counter + learning rate live on the device so a captured step can be replayed
+            self.state = torch.zeros(2, dtype=torch.float32, device=dev)
+            self.lr_host = torch.zeros(1, dtype=torch.float32).pin_memory()
 
     def zero_grad(self):
         self.flat_g_ext.zero_()
@@ -70,14 +74,24 @@ class FlatAdam:
             denom = self.v.sqrt() / (1 - b2 ** self.t) ** 0.5 + self.eps
             self.flat_p.addcdiv_(self.m, denom, value=-self.lr * lr_scale / (1 - b1 ** self.t))
             return
+        self.set_lr(self.lr * lr_scale)
+        self.launch_step(grad_scale)
+
+    def set_lr(self, lr):
+        """Host -> device copy of this step's learning rate (outside any CUDA graph)."""
+        self.lr_host[0] = lr
+        self.state[1:2].copy_(self.lr_host, non_blocking=True)
+
+    def launch_step(self, grad_scale=1.0):
+        """The update kernels only (capturable): t += 1 on the device, then Adam with state[1] as lr."""
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         P = lambda t: ctypes.c_void_p(t.data_ptr())
         with TIMER.span("adam_step", 28 * self.n):
-            _lib.check(self.lib.ogc_adam_step(self.n, P(self.flat_p), P(self.flat_g), P(self.m), P(self.v),
-                                              self.lr * lr_scale, self.betas[0], self.betas[1], self.eps,
-                                              self.weight_decay, self.t, grad_scale, P(self.nan_counter), st),
-                       "ogc_adam_step")
-        get_backend().launches += 1
+            _lib.check(self.lib.ogc_adam_step_dev(self.n, P(self.flat_p), P(self.flat_g), P(self.m), P(self.v),
+                                                  P(self.state), self.betas[0], self.betas[1], self.eps,
+                                                  self.weight_decay, grad_scale, P(self.nan_counter), st),
+                       "ogc_adam_step_dev")
+        get_backend().launches += 2
 
     def count_nan(self):
         if self.lib is None:
@@ -98,26 +112,97 @@ class SegTrainer:
         self.global_batch_size, self.world_size = global_batch_size, world_size
         self.device = self.opt.flat_p.device
 
-    def train_step(self, it, batch, aug_transform=False):
-        """batch = (pcs (b,t,N,3), segms, flows (b,t,N,3), valids) on host or device.  Returns loss_dict."""
+    def _step_body(self, pcs, flows, it, aug_transform, defer):
+        """zero_grad -> forward -> loss -> backward -> NaN count -> all-reduce -> Adam launch (no host sync when
+        `defer`).  pcs, flows: (b,t,N,3) on the device."""
         self.segnet.train()
-        lr_scale = lr_curve(it, self.global_batch_size, **self.sched)
         self.opt.zero_grad()
-        pcs, segms, flows, _ = batch
-        b, t, n = segms.shape
-        pcs = pcs.to(self.device, non_blocking=True).view(b * t, n, 3)
-        flows = flows.to(self.device, non_blocking=True)
-        masks = self.segnet(pcs, pcs)
-        pcs = pcs.view(b, t, n, 3)
-        masks = masks.view(b, t, n, -1)
+        b, t, n, _ = pcs.shape
+        flat = pcs.view(b * t, n, 3)
+        masks = self.segnet(flat, flat).view(b, t, n, -1)
         pcs_l = [pcs[:, i].contiguous() for i in range(t)]
         masks_l = [masks[:, i].contiguous() for i in range(t)]
         flows_l = [flows[:, i].contiguous() for i in range(t)]
-        loss, loss_dict = self.criterion(pcs_l, masks_l, flows_l, step_w=True, it=it * self.global_batch_size,
-                                         aug_transform=aug_transform)
+        self.criterion.defer_logging = defer
+        try:
+            loss, loss_dict = self.criterion(pcs_l, masks_l, flows_l, step_w=True, it=it * self.global_batch_size,
+                                             aug_transform=aug_transform)
+        finally:
+            self.criterion.defer_logging = False
         loss.backward()
         self.opt.count_nan()
         if self.world_size > 1:
             dist.all_reduce(self.opt.flat_g_ext)          # the step's only collective: grads + NaN counter
+        return loss_dict
+
+    def train_step(self, it, batch, aug_transform=False):
+        """batch = (pcs (b,t,N,3), segms, flows (b,t,N,3), valids) on host or device.  Returns loss_dict.
+        Eager path (one launch per kernel); see train_step_graphed for the CUDA-graph replay."""
+        lr_scale = lr_curve(it, self.global_batch_size, **self.sched)
+        pcs, _, flows, _ = batch
+        pcs = pcs.to(self.device, non_blocking=True)
+        flows = flows.to(self.device, non_blocking=True)
+        loss_dict = self._step_body(pcs, flows, it, aug_transform, defer=False)
         self.opt.step(lr_scale=lr_scale, grad_scale=1.0 / self.world_size)
         return loss_dict
+
+    # ------------------------------------------------------------------------------------------------
+    # CUDA-graph replay: the whole step (H2D copies excluded) is ONE graph launch.  Possible because the
+    # Hungarian matching, the NaN guard, the Adam step counter and the learning rate all live on the device.
+    # ------------------------------------------------------------------------------------------------
+    def _loss_weights(self, it):
+        c = self.criterion
+        k = it * self.global_batch_size
+        return (c.step_lossw(k, c.w_dynamic, c.start_step_dynamic), c.step_lossw(k, c.w_smooth, c.start_step_smooth),
+                c.step_lossw(k, c.w_invariance, c.start_step_invariance))
+
+    def _capture(self, key, it, shape, aug_transform):
+        from .losses import resolve_loss_dict  # noqa: F401
+        dev = self.device
+        g = {"pcs": torch.zeros(shape, dtype=torch.float32, device=dev),
+             "flows": torch.zeros(shape, dtype=torch.float32, device=dev)}
+        g["pcs"].copy_(self._last_inputs[0]); g["flows"].copy_(self._last_inputs[1])
+        opt = self.opt
+        snap = [x.clone() for x in (opt.flat_p, opt.m, opt.v, opt.state)]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                      # warm-up on a side stream (allocator, cuBLAS, NCCL)
+            for _ in range(2):
+                self._step_body(g["pcs"], g["flows"], it, aug_transform, defer=True)
+                opt.launch_step(1.0 / self.world_size)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        for dst, src in zip((opt.flat_p, opt.m, opt.v, opt.state), snap):   # warm-up must not train
+            dst.copy_(src)
+        launches0 = get_backend().launches
+        host = torch.zeros(16, dtype=torch.float32).pin_memory()      # allocated BEFORE capture
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            d = self._step_body(g["pcs"], g["flows"], it, aug_transform, defer=True)
+            opt.launch_step(1.0 / self.world_size)
+            g["keys"] = d["_keys"]
+            g["host"] = host[:len(d["_keys"])]
+            g["host"].copy_(d["_values"], non_blocking=True)           # captured D2H of the logged scalars
+        g["launches"] = get_backend().launches - launches0
+        g["graph"] = graph
+        self._graphs[key] = g
+        return g
+
+    def train_step_graphed(self, it, batch, aug_transform=False):
+        """Same semantics as train_step; the device work is a single CUDA-graph launch.  Re-captures when the
+        batch shape or the active loss weights (start_steps schedule) change."""
+        if not hasattr(self, "_graphs"):
+            self._graphs = {}
+        pcs, _, flows, _ = batch
+        key = (tuple(pcs.shape), bool(aug_transform), self._loss_weights(it))
+        self._last_inputs = (pcs, flows)
+        g = self._graphs.get(key) or self._capture(key, it, tuple(pcs.shape), aug_transform)
+        g["pcs"].copy_(pcs, non_blocking=True)             # H2D from pinned memory (or D2D when resident)
+        g["flows"].copy_(flows, non_blocking=True)
+        self.opt.set_lr(self.opt.lr * lr_curve(it, self.global_batch_size, **self.sched))
+        g["graph"].replay()
+        get_backend().launches += g["launches"]
+        torch.cuda.current_stream().synchronize()          # the logged scalars are in pinned host memory now
+        out = dict(zip(g["keys"], g["host"].tolist()))
+        out.setdefault("invariance", 0)
+        return out

@@ -1,0 +1,76 @@
+"""GPU: the training step -- eager vs CUDA-graph replay, and the device-side pieces that make the capture
+possible (Hungarian, nuclear norm, Adam with device-resident state)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _trainer():
+    from ogc_b200 import losses
+    from ogc_b200.segnet import MaskFormer3D
+    from ogc_b200.train import SegTrainer
+    torch.manual_seed(10)
+    net = MaskFormer3D(n_slot=8, n_point=1024, variant="kitti").cuda()
+    return SegTrainer(net, losses.build_ogc_loss(losses.KITTISF_LOSS_CFG), global_batch_size=2)
+
+
+def test_graphed_step_equals_eager_step(b200):
+    from ogc_b200 import data
+    batches = [data.make_batch(20 + i, 2, 1024, aug=True) for i in range(3)]
+    a, g = _trainer(), _trainer()
+    for i, batch in enumerate(batches):
+        da = a.train_step(5000 + i, batch, aug_transform=True)
+        dg = g.train_step_graphed(5000 + i, batch, aug_transform=True)
+        for k in ("dynamic", "smooth", "invariance", "entropy", "rank", "sum"):
+            assert abs(da[k] - dg[k]) <= 2e-4 * max(1.0, abs(da[k])), (i, k, da[k], dg[k])
+    torch.cuda.synchronize()
+    assert float(g.opt.state[0]) == 3.0                      # the device-side step counter advanced per replay
+    # Adam normalises the update, so compare parameters loosely and the direction of travel tightly
+    diff = (a.opt.flat_p - g.opt.flat_p).abs()
+    assert float(diff.max()) < 3e-3 and float(diff.mean()) < 2e-5
+
+
+def test_device_hungarian_matches_scipy(b200):
+    from scipy.optimize import linear_sum_assignment
+    rng = np.random.default_rng(0)
+    B, K = 64, 10
+    inter = rng.integers(0, 40, (B, K, K)).astype(np.int32)
+    inter[rng.random((B, K, K)) < 0.6] = 0
+    inter[:, 3, :] = 0                                       # an empty slot: all-zero row -> ties
+    p12, p21 = b200.mask_match(torch.from_numpy(inter).cuda())
+    f = inter.astype(np.float32)
+    union = f.sum(2, keepdims=True) + f.sum(1, keepdims=True) - f
+    iou = f / np.maximum(union, np.float32(1e-10))
+    for b in range(B):
+        np.testing.assert_array_equal(p12[b].cpu().numpy(), linear_sum_assignment(iou[b], maximize=True)[1])
+        np.testing.assert_array_equal(p21[b].cpu().numpy(), linear_sum_assignment(iou[b].T, maximize=True)[1])
+
+
+def test_nuclear_norm_matches_torch(b200):
+    torch.manual_seed(1)
+    m = torch.softmax(torch.randn(5, 4096, 10, device="cuda") * 3, dim=-1)
+    got = b200.mask_nuclear_norm(m)
+    ref = torch.linalg.svdvals(m.double()).sum(dim=1)
+    torch.testing.assert_close(got.double(), ref, rtol=1e-5, atol=1e-5)
+
+
+def test_nan_gradient_skips_update_and_step_counter(b200):
+    from ogc_b200.train import FlatAdam
+    p = torch.nn.Parameter(torch.ones(1000, device="cuda"))
+    opt = FlatAdam([p], lr=0.1)
+    opt.zero_grad()
+    p.grad.fill_(1.0)
+    p.grad[17] = float("nan")
+    opt.count_nan()
+    opt.step()
+    torch.cuda.synchronize()
+    assert torch.equal(opt.flat_p, torch.ones_like(opt.flat_p)) and float(opt.state[0]) == 0.0
+    opt.zero_grad()
+    p.grad.fill_(1.0)
+    opt.count_nan()
+    opt.step()
+    torch.cuda.synchronize()
+    assert float(opt.state[0]) == 1.0
+    torch.testing.assert_close(opt.flat_p, torch.full_like(opt.flat_p, 0.9), rtol=1e-5, atol=1e-6)
