@@ -65,25 +65,43 @@ __device__ __forceinline__ void load_tile_gather(const MlpFwdParams &q, int b, i
 __device__ __forceinline__ void load_tile_dense(const float *__restrict__ y_prev, const float *__restrict__ ss, int Cin,
                                                 int P, int b, int p_base, int P_T, float *Bs, int ldb) {
     const int q4 = P_T / 4;
-    for (int e = threadIdx.x; e < Cin * q4; e += kMlpThreads) {
-        const int c = e / q4, p = (e - c * q4) * 4;
-        const float sc = __ldg(ss + (static_cast<size_t>(b) * Cin + c) * 2), sh = __ldg(ss + (static_cast<size_t>(b) * Cin + c) * 2 + 1);
-        const float *src = y_prev + (static_cast<size_t>(b) * Cin + c) * P + p_base + p;
-        float4 v;
-        if (p_base + p + 3 < P && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0)) {
-            v = __ldg(reinterpret_cast<const float4 *>(src));
-        } else {
-            v.x = p_base + p + 0 < P ? __ldg(src + 0) : 0.f;
-            v.y = p_base + p + 1 < P ? __ldg(src + 1) : 0.f;
-            v.z = p_base + p + 2 < P ? __ldg(src + 2) : 0.f;
-            v.w = p_base + p + 3 < P ? __ldg(src + 3) : 0.f;
+    const int total = Cin * q4;
+    // 4 independent 16-byte loads in flight per thread before any is consumed (latency-bound loader)
+    for (int e0 = threadIdx.x; e0 < total; e0 += kMlpThreads * 4) {
+        float4 v[4];
+        float sc[4], sh[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * kMlpThreads;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            sc[u] = sh[u] = 0.f;
+            if (e < total) {
+                const int c = e / q4, p = (e - c * q4) * 4;
+                sc[u] = __ldg(ss + (static_cast<size_t>(b) * Cin + c) * 2);
+                sh[u] = __ldg(ss + (static_cast<size_t>(b) * Cin + c) * 2 + 1);
+                const float *src = y_prev + (static_cast<size_t>(b) * Cin + c) * P + p_base + p;
+                if (p_base + p + 3 < P && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0)) {
+                    v[u] = __ldg(reinterpret_cast<const float4 *>(src));
+                } else {
+                    v[u].x = p_base + p + 0 < P ? __ldg(src + 0) : 0.f;
+                    v[u].y = p_base + p + 1 < P ? __ldg(src + 1) : 0.f;
+                    v[u].z = p_base + p + 2 < P ? __ldg(src + 2) : 0.f;
+                    v[u].w = p_base + p + 3 < P ? __ldg(src + 3) : 0.f;
+                }
+            }
         }
-        float4 o;
-        o.x = p_base + p + 0 < P ? fmaxf(fmaf(sc, v.x, sh), 0.f) : 0.f;
-        o.y = p_base + p + 1 < P ? fmaxf(fmaf(sc, v.y, sh), 0.f) : 0.f;
-        o.z = p_base + p + 2 < P ? fmaxf(fmaf(sc, v.z, sh), 0.f) : 0.f;
-        o.w = p_base + p + 3 < P ? fmaxf(fmaf(sc, v.w, sh), 0.f) : 0.f;
-        *reinterpret_cast<float4 *>(Bs + c * ldb + p) = o;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * kMlpThreads;
+            if (e >= total) continue;
+            const int c = e / q4, p = (e - c * q4) * 4;
+            float4 o;
+            o.x = p_base + p + 0 < P ? fmaxf(fmaf(sc[u], v[u].x, sh[u]), 0.f) : 0.f;
+            o.y = p_base + p + 1 < P ? fmaxf(fmaf(sc[u], v[u].y, sh[u]), 0.f) : 0.f;
+            o.z = p_base + p + 2 < P ? fmaxf(fmaf(sc[u], v[u].z, sh[u]), 0.f) : 0.f;
+            o.w = p_base + p + 3 < P ? fmaxf(fmaf(sc[u], v[u].w, sh[u]), 0.f) : 0.f;
+            *reinterpret_cast<float4 *>(Bs + c * ldb + p) = o;
+        }
     }
 }
 

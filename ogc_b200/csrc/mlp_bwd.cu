@@ -27,35 +27,48 @@ struct DySrc {
     const float *coef;           // (B,C,4): k1, k2, k3r, mean
 };
 
-__device__ __forceinline__ float4 dy_quad(const DySrc &d, int b, int c, int gp) {
-    // 4 consecutive positions gp..gp+3 (gp % 4 == 0) of channel c; zero beyond P
-    const float4 cf = __ldg(reinterpret_cast<const float4 *>(d.coef + (static_cast<size_t>(b) * d.C + c) * 4));
-    const float *yp = d.y + (static_cast<size_t>(b) * d.C + c) * d.P + gp;
+struct DyRaw {
+    float4 cf;        // k1, k2, k3r, mean
     float yv[4], dzv[4];
+};
+
+// Issue the loads for 4 consecutive positions gp..gp+3 (gp % 4 == 0) of channel c (no dependent use).
+__device__ __forceinline__ void dy_quad_load(const DySrc &d, int b, int c, int gp, DyRaw &r) {
+    r.cf = __ldg(reinterpret_cast<const float4 *>(d.coef + (static_cast<size_t>(b) * d.C + c) * 4));
+    const float *yp = d.y + (static_cast<size_t>(b) * d.C + c) * d.P + gp;
     const bool full = gp + 3 < d.P;
     if (full && (reinterpret_cast<uintptr_t>(yp) & 15u) == 0) {
         const float4 t = __ldg(reinterpret_cast<const float4 *>(yp));
-        yv[0] = t.x; yv[1] = t.y; yv[2] = t.z; yv[3] = t.w;
+        r.yv[0] = t.x; r.yv[1] = t.y; r.yv[2] = t.z; r.yv[3] = t.w;
     } else {
-        for (int j = 0; j < 4; ++j) yv[j] = gp + j < d.P ? __ldg(yp + j) : 0.f;
+        for (int j = 0; j < 4; ++j) r.yv[j] = gp + j < d.P ? __ldg(yp + j) : 0.f;
     }
     if (d.dz) {
         const float *zp = d.dz + (static_cast<size_t>(b) * d.C + c) * d.P + gp;
         if (full && (reinterpret_cast<uintptr_t>(zp) & 15u) == 0) {
             const float4 t = __ldg(reinterpret_cast<const float4 *>(zp));
-            dzv[0] = t.x; dzv[1] = t.y; dzv[2] = t.z; dzv[3] = t.w;
+            r.dzv[0] = t.x; r.dzv[1] = t.y; r.dzv[2] = t.z; r.dzv[3] = t.w;
         } else {
-            for (int j = 0; j < 4; ++j) dzv[j] = gp + j < d.P ? __ldg(zp + j) : 0.f;
+            for (int j = 0; j < 4; ++j) r.dzv[j] = gp + j < d.P ? __ldg(zp + j) : 0.f;
         }
     } else {
         const int m = gp / d.S, s0 = gp - m * d.S;   // S % 4 == 0: the quad stays inside one centre
         const int sl = gp < d.P ? __ldg(d.sel + (static_cast<size_t>(b) * d.C + c) * d.M + m) : 255;
         const float g = (sl >= s0 && sl < s0 + 4) ? __ldg(d.go + (static_cast<size_t>(b) * d.go_ctotal + d.go_coff + c) * d.M + m) : 0.f;
-        for (int j = 0; j < 4; ++j) dzv[j] = (sl == s0 + j) ? g : 0.f;
+        for (int j = 0; j < 4; ++j) r.dzv[j] = (sl == s0 + j) ? g : 0.f;
     }
+}
+
+__device__ __forceinline__ float4 dy_quad_finish(const DySrc &d, int gp, const DyRaw &r) {
     float o[4];
-    for (int j = 0; j < 4; ++j) o[j] = gp + j < d.P ? fmaf(cf.x, dzv[j], -cf.y) - (yv[j] - cf.w) * cf.z : 0.f;
+    for (int j = 0; j < 4; ++j) o[j] = gp + j < d.P ? fmaf(r.cf.x, r.dzv[j], -r.cf.y) - (r.yv[j] - r.cf.w) * r.cf.z : 0.f;
     return make_float4(o[0], o[1], o[2], o[3]);
+}
+
+__device__ __forceinline__ float4 dy_quad(const DySrc &d, int b, int c, int gp) {
+    DyRaw r;
+    dy_quad_load(d, b, c, gp, r);
+    return dy_quad_finish(d, gp, r);
 }
 
 // ---- sparse GroupNorm-backward sums of the LAST layer (dz is non-zero only at the arg-max positions) ----
@@ -169,9 +182,26 @@ mlp_dx_kernel(MlpDxParams q) {
                 As[e] = r < q.rows ? __ldg(q.W + static_cast<size_t>(kc + k) * q.cin_full + q.row_off + r) : 0.f;
             }
             constexpr int Q4 = P_T / 4;
-            for (int e = tid; e < kn * Q4; e += kMlpThreads) {
-                const int k = e / Q4, p = (e - k * Q4) * 4;
-                *reinterpret_cast<float4 *>(Bs + k * LDB + p) = dy_quad(q.dy, b, kc + k, p_base + p);
+            // 4 independent (y, dz, coef) quads in flight per thread before any is consumed: the loader is
+            // latency-bound at 1-2 CTAs per SM
+            for (int e0 = tid; e0 < kn * Q4; e0 += kMlpThreads * 4) {
+                DyRaw raw[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int e = e0 + u * kMlpThreads;
+                    if (e < kn * Q4) {
+                        const int k = e / Q4, p = (e - k * Q4) * 4;
+                        dy_quad_load(q.dy, b, kc + k, p_base + p, raw[u]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int e = e0 + u * kMlpThreads;
+                    if (e < kn * Q4) {
+                        const int k = e / Q4, p = (e - k * Q4) * 4;
+                        *reinterpret_cast<float4 *>(Bs + k * LDB + p) = dy_quad_finish(q.dy, p_base + p, raw[u]);
+                    }
+                }
             }
             __syncthreads();
             tile_gemm<R_T, P_T>(As, Bs, LDB, kn, ty, tx, acc);
@@ -275,11 +305,23 @@ mlp_dw_kernel(MlpDwParams q) {
         const int b = ch / chunks_per_sample, p_base = (ch - b * chunks_per_sample) * PK;
         __syncthreads();
         // dY^T: thread -> (channel fastest, position quad)
-        for (int e = tid; e < R_T * (PK / 4); e += kMlpThreads) {
-            const int c = e % R_T, pq = e / R_T;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row0 + c < Cout) v = dy_quad(q.dy, b, row0 + c, p_base + pq * 4);
-            As[pq * 4 + 0][c] = v.x; As[pq * 4 + 1][c] = v.y; As[pq * 4 + 2][c] = v.z; As[pq * 4 + 3][c] = v.w;
+        for (int e0 = tid; e0 < R_T * (PK / 4); e0 += kMlpThreads * 4) {
+            DyRaw raw[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * kMlpThreads;
+                const int c = e % R_T, pq = e / R_T;
+                if (e < R_T * (PK / 4) && row0 + c < Cout) dy_quad_load(q.dy, b, row0 + c, p_base + pq * 4, raw[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * kMlpThreads;
+                if (e >= R_T * (PK / 4)) continue;
+                const int c = e % R_T, pq = e / R_T;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row0 + c < Cout) v = dy_quad_finish(q.dy, p_base + pq * 4, raw[u]);
+                As[pq * 4 + 0][c] = v.x; As[pq * 4 + 1][c] = v.y; As[pq * 4 + 2][c] = v.z; As[pq * 4 + 3][c] = v.w;
+            }
         }
         if (GATHER) {
             const int lane = tid & 31, warp = tid >> 5;

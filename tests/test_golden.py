@@ -91,8 +91,10 @@ def test_ogc_loss_matches_reference_cpu(oracle_ops, name):
 def test_segnet_matches_reference_gpu(b200, name):
     # masks to 1e-4 abs.  Weight gradients pass through softmax(cos/0.05) and atomically-ordered fp32 sums:
     # the golden (CPU fp32) and the GPU differ by summation order alone at the 5e-4 level relative to the
-    # largest entry (the reference cannot reproduce its own gradients bit-for-bit either).
-    run_segnet_case(name, "cuda", grad_tol=1e-3)
+    # largest entry (the reference cannot reproduce its own gradients bit-for-bit either);
+    # a single flipped ReLU / arg-max decision moves one channel's gradient by a few 1e-3 of the tensor max
+    # (analysed in tests/test_gpu_fused_sa.py).
+    run_segnet_case(name, "cuda", grad_tol=5e-3)
 
 
 @pytest.mark.gpu

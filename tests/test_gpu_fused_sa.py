@@ -59,14 +59,52 @@ def test_fused_sa_mlp_matches_composed(b200, N, M, Cf, widths):
 
     assert out.shape == ref.shape
     assert rel_err(out, ref) < 2e-5, rel_err(out, ref)
-    # gradients: an arg-max over the 64 samples can flip between two neighbours whose values differ by ~1 ulp
-    # (different summation order / 3xTF32), which reroutes one pooled gradient entry: bound the max loosely and
-    # the mean tightly.
-    def mean_err(a, b):
-        return float((a - b).abs().mean() / b.abs().mean().clamp_min(1e-12))
-    assert rel_err(f2.grad, ref_df) < 2e-2 and mean_err(f2.grad, ref_df) < 2e-4, (rel_err(f2.grad, ref_df), mean_err(f2.grad, ref_df))
+    # Gradients: a single ReLU decision (z ~ 0) or arg-max among the 64 samples can flip under a 1e-6 change of
+    # the forward values (different summation order / 3xTF32), which toggles one O(1) contribution in the sums
+    # behind a weight gradient (measured: all saved forward tensors agree to 1e-6, one flipped element moves one
+    # channel's gradient by ~3e-3 of the tensor's max).  So: Frobenius-relative error tight, max error loose.
+    def fro_err(a, b):
+        return float((a - b).norm() / b.norm().clamp_min(1e-12))
+    assert fro_err(f2.grad, ref_df) < 2e-3 and rel_err(f2.grad, ref_df) < 3e-2, (fro_err(f2.grad, ref_df), rel_err(f2.grad, ref_df))
     for n, p in mlp.named_parameters():
-        assert rel_err(p.grad, ref_grads[n]) < 2e-3 and mean_err(p.grad, ref_grads[n]) < 2e-4, (n, rel_err(p.grad, ref_grads[n]))
+        assert fro_err(p.grad, ref_grads[n]) < 2e-3 and rel_err(p.grad, ref_grads[n]) < 3e-2, (n, fro_err(p.grad, ref_grads[n]))
+
+
+@pytest.mark.parametrize("N,M,Cf,widths", [(400, 100, 96, [64, 64, 128]), (300, 70, 128, [128, 128, 256])])
+def test_tensor_core_forward_matches_simt_forward(b200, N, M, Cf, widths):
+    """tcgen05 3xTF32 kernels vs the fp32 SIMT kernels: every tensor the forward produces (pooled output, stored
+    pre-norm activations, GroupNorm scale/shift, arg-max positions) to fp32 accuracy."""
+    from ogc_b200 import segnet, sa_fused
+    import pointnet2.pointnet2 as ops
+    torch.manual_seed(N)
+    B, S = 3, 64
+    xyz = torch.randn(B, N, 3, device="cuda")
+    new_xyz = xyz[:, :M].contiguous()
+    feat_pm = torch.randn(B, N, Cf, device="cuda", requires_grad=True)
+    mlp = segnet.SharedMLP([Cf + 3] + widths).cuda()
+    with torch.no_grad():
+        for n_, p_ in mlp.named_parameters():
+            if "gn.weight" in n_:
+                p_.copy_(torch.randn_like(p_) * 0.5 + 0.8)
+            if "gn.bias" in n_:
+                p_.copy_(torch.randn_like(p_) * 0.3)
+    dist, idx = ops.knn(S, new_xyz, xyz)
+    idx = ops.clip_neighbours_by_radius(dist, idx, 1.2)
+    layers = [(getattr(mlp, f"layer{i}").conv.weight, getattr(mlp, f"layer{i}").normlayer.gn.weight,
+               getattr(mlp, f"layer{i}").normlayer.gn.bias) for i in range(mlp.n_layers)]
+    saved = {}
+    for tc in (False, True):
+        sa_fused.USE_TC = tc
+        try:
+            out = sa_fused.fused_sa_mlp(xyz, new_xyz, feat_pm, idx, layers)
+        finally:
+            sa_fused.USE_TC = True
+        saved[tc] = [out.detach().clone()] + [t.clone() for t in out.grad_fn.saved_tensors[4:]]
+    for a, b in zip(saved[False], saved[True]):
+        if a.dtype == torch.uint8:
+            assert float((a != b).float().mean()) < 1e-4       # arg-max positions (ties aside) identical
+        else:
+            assert float((a - b).abs().max()) <= 2e-5 * max(1.0, float(a.abs().max()))
 
 
 def test_segnet_fused_equals_composed_full_model(b200):
