@@ -282,6 +282,22 @@ OGC_API int ogc_adam_step_dev(long long n, float *param, const float *grad, floa
                               float *state, float beta1, float beta2, float eps, float weight_decay,
                               float grad_scale, const float *skip_counter, void *stream);
 
+/* Tensor-core variants of ogc_sa_mlp_layer_dx / ogc_sa_mlp_layer_dw (csrc/mlp_tc_bwd.cu): identical arguments and
+ * results to fp32 accuracy (3xTF32), OGC_ERR_UNSUPPORTED for shapes outside nsample == 64, rows <= 128,
+ * 32 <= cout <= 256 (dx: scatter mode cout <= 128; dw: 16 <= cin <= 160). */
+OGC_API int ogc_sa_mlp_layer_dx_tc(int b, int n, int m, int nsample, int cout, int cin_full, int row_off, int rows,
+                                   const float *dz, const float *go, int go_ctotal, int go_coff,
+                                   const unsigned char *sel, const float *y, const float *coef, const float *w,
+                                   const float *y_prev, const float *ss_prev, const float *mean_rstd_prev,
+                                   const float *gamma_prev, float *dz_prev, double *ab_prev, float *dgamma_prev,
+                                   float *dbeta_prev, const int *idx, float *dfeat_pm, int dfeat_stride,
+                                   int dfeat_off, void *stream);
+OGC_API int ogc_sa_mlp_layer_dw_tc(int b, int n, int m, int nsample, int cout, int cin, int gather, const float *dz,
+                                   const float *go, int go_ctotal, int go_coff, const unsigned char *sel,
+                                   const float *y, const float *coef, const float *y_prev, const float *ss_prev,
+                                   const float *xyz, const float *new_xyz, const float *feat_pm, const int *idx,
+                                   float *dw, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

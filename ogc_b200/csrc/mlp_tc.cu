@@ -34,13 +34,6 @@ struct MlpTcParams {
     int k_off, K;         // tensor-core K range: W columns [k_off, k_off+K); gather: k_off = 3, K = Cf
 };
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
 template <bool GATHER, bool LAST>
 __global__ void __launch_bounds__(kTcThreads, 1)
 mlp_fwd_tc_kernel(MlpTcParams q) {

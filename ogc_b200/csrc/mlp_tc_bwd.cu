@@ -1,0 +1,522 @@
+// Backward of the fused set-abstraction MLP on the tensor cores (tcgen05.mma kind::tf32, 3xTF32 split):
+// tensor-core twins of mlp_dx_kernel / mlp_dw_kernel (mlp_bwd.cu) for the layers where the contraction dominates.
+// Same warp-specialised skeleton as mlp_tc.cu (warps 0-3 epilogue, 4-7 loader, warp 8 MMA issuer + TMEM owner).
+//
+//   dX:  da[ci][p] = sum_co W[co][ci] dY[co][p]     M = 128 input channels (lanes), N = 64 positions, K = co
+//        A = W^T rows ci, K-major (built once per CTA from W), B = dY rows p, K-major (rebuilt per tile from
+//        dz / y / coef).  Epilogue thread = input channel: ReLU mask from y_prev, store dz_prev, per-channel
+//        dgamma / dbeta sums in registers (no shuffles); layer 1: coalesced red.add of 32 consecutive feature
+//        channels per point instead.  K > 128 is split over two launches (partial sums through dz_prev).
+//   dW:  dW[co][ci] = sum_p dY[co][p] a[ci][p]      M = 128 output channels, N = C_in (<= 160), K = positions
+//        both operands MN-major (rows = positions, 128B swizzle with 32 B base), ONE TMEM accumulator per CTA
+//        accumulated over all its position tiles, read out once and red.add'ed into dW.
+#include "mlp_dy.cuh"
+#include "tcgen05.cuh"
+
+namespace ogc {
+
+constexpr int kTbThreads = 288;
+constexpr int kTbNT = 64;     // positions per tile
+constexpr int kTbM = 128;
+
+// ------------------------------------------------------------------------------------------------ dX
+struct MlpDxTcParams {
+    DySrc dy;                     // layer l; its channels [k0, k0+kn) are this launch's K range
+    int k0, kn;
+    int cin_full, row_off, rows;  // W (dy.C, cin_full); output rows = W columns [row_off, row_off+rows), rows <= 128
+    const float *W;
+    int add_partial, final;       // read a partial sum from dz_prev first / apply the epilogue (else store raw)
+    const float *y_prev, *ss_prev, *mean_rstd_prev, *gamma_prev;
+    float *dz_prev;
+    double *ab_prev;
+    float *dgamma_prev, *dbeta_prev;
+    const int *idx;
+    float *dfeat_pm;
+    int N, dfeat_stride, dfeat_off;
+};
+
+template <bool SCATTER>
+__global__ void __launch_bounds__(kTbThreads, 1)
+mlp_dx_tc_kernel(MlpDxTcParams q) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full, bar_empty, bar_tfull[2], bar_tempty[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ double gs[kGnGroups][2];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y;
+    const int KB = (q.kn + 31) / 32;
+    const int P = q.dy.P;
+    const int ntiles = P / kTbNT;
+
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t w_bytes = static_cast<uint32_t>(KB) * kTbM * 128u, a_bytes = static_cast<uint32_t>(KB) * kTbNT * 128u;
+    uint8_t *w_hi = smem, *w_lo = w_hi + w_bytes, *a_hi = w_lo + w_bytes, *a_lo = a_hi + a_bytes;
+
+    if (warp == 8) tc::tmem_alloc(&tmem_base_s, 128);
+    if (tid == 0) {
+        mbar_init(&bar_full, 128);
+        mbar_init(&bar_empty, 1);
+        mbar_init(&bar_tfull[0], 1); mbar_init(&bar_tfull[1], 1);
+        mbar_init(&bar_tempty[0], 128); mbar_init(&bar_tempty[1], 128);
+        mbar_fence_init();
+    }
+    if (tid < kGnGroups * 2) (&gs[0][0])[tid] = 0.0;
+    // A = W^T: row r = input channel row_off + r, column k = output channel k0 + k
+    for (int e = tid; e < kTbM * KB * 32; e += kTbThreads) {
+        const int k = e / kTbM, r = e - k * kTbM;       // consecutive threads -> consecutive r: coalesced W row reads
+        const float v = (r < q.rows && k < q.kn) ? __ldg(q.W + static_cast<size_t>(q.k0 + k) * q.cin_full + q.row_off + r) : 0.f;
+        const float hi = tc::tf32_hi(v);
+        const uint32_t off = static_cast<uint32_t>(k >> 5) * (kTbM * 128u) + tc::sw128_offset(r, k & 31);
+        *reinterpret_cast<float *>(w_hi + off) = hi;
+        *reinterpret_cast<float *>(w_lo + off) = tc::tf32_hi(v - hi);
+    }
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp >= 4 && warp < 8) {
+        // ================================ loader: dY tile, rows = positions, K = channels ================
+        const int lt = tid - 128;
+        int use = 0;
+        const int nitems = KB * 16 * 32;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++use) {
+            const int p0 = t * kTbNT;
+            mbar_wait(&bar_empty, (use & 1) ^ 1);
+            for (int it0 = lt; it0 < nitems; it0 += 128 * 4) {
+                DyRaw raw[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int it = it0 + 128 * u;
+                    const int cl = it & 31, pq = (it >> 5) & 15, kb = it >> 9;
+                    const int c = kb * 32 + cl;
+                    if (it < nitems && c < q.kn) dy_quad_load(q.dy, b, q.k0 + c, p0 + pq * 4, raw[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int it = it0 + 128 * u;
+                    if (it >= nitems) continue;
+                    const int cl = it & 31, pq = (it >> 5) & 15, kb = it >> 9;
+                    const int c = kb * 32 + cl;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (c < q.kn) v = dy_quad_finish(q.dy, p0 + pq * 4, raw[u]);
+                    const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float hi = tc::tf32_hi(vv[j]);
+                        const uint32_t off = static_cast<uint32_t>(kb) * (kTbNT * 128u) + tc::sw128_offset(pq * 4 + j, cl);
+                        *reinterpret_cast<float *>(a_hi + off) = hi;
+                        *reinterpret_cast<float *>(a_lo + off) = tc::tf32_hi(vv[j] - hi);
+                    }
+                }
+            }
+            tc::fence_proxy_async();
+            mbar_arrive(&bar_full);
+        }
+    } else if (warp == 8) {
+        if (lane == 0) {
+            const uint32_t idesc = tc::make_idesc_tf32(kTbM, kTbNT, 0, 0);
+            int use = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++use) {
+                const int buf = use & 1;
+                mbar_wait(&bar_full, use & 1);
+                mbar_wait(&bar_tempty[buf], ((use >> 1) & 1) ^ 1);
+                tc::fence_after_sync();
+                const uint32_t d = tmem_base + static_cast<uint32_t>(buf * kTbNT);
+                uint32_t acc = 0;
+                for (int s = 0; s < KB * 4; ++s) {
+                    const uint32_t wo = static_cast<uint32_t>(s >> 2) * (kTbM * 128u) + static_cast<uint32_t>(s & 3) * 32u;
+                    const uint32_t ao = static_cast<uint32_t>(s >> 2) * (kTbNT * 128u) + static_cast<uint32_t>(s & 3) * 32u;
+                    const uint64_t whd = tc::make_desc_sw128(smem_u32(w_hi) + wo, 16, 1024);
+                    const uint64_t wld = tc::make_desc_sw128(smem_u32(w_lo) + wo, 16, 1024);
+                    const uint64_t ahd = tc::make_desc_sw128(smem_u32(a_hi) + ao, 16, 1024);
+                    const uint64_t ald = tc::make_desc_sw128(smem_u32(a_lo) + ao, 16, 1024);
+                    tc::mma_tf32(d, whd, ahd, idesc, acc);
+                    tc::mma_tf32(d, whd, ald, idesc, 1);
+                    tc::mma_tf32(d, wld, ahd, idesc, 1);
+                    acc = 1;
+                }
+                tc::mma_commit(&bar_empty);
+                tc::mma_commit(&bar_tfull[buf]);
+            }
+        }
+    } else {
+        // ================================ epilogue: thread = input channel r ============================
+        const int r = tid;
+        const bool valid = r < q.rows;
+        float sc = 0.f, sh = 0.f, mu = 0.f, rs = 0.f;
+        if (!SCATTER && q.final && valid) {
+            const int g = r / (q.rows / kGnGroups);
+            sc = __ldg(q.ss_prev + (static_cast<size_t>(b) * q.rows + r) * 2);
+            sh = __ldg(q.ss_prev + (static_cast<size_t>(b) * q.rows + r) * 2 + 1);
+            mu = __ldg(q.mean_rstd_prev + (b * kGnGroups + g) * 2);
+            rs = __ldg(q.mean_rstd_prev + (b * kGnGroups + g) * 2 + 1);
+        }
+        double dsum = 0.0, dsumy = 0.0;
+        int use = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++use) {
+            const int buf = use & 1;
+            const int p0 = t * kTbNT;
+            mbar_wait(&bar_tfull[buf], (use >> 1) & 1);
+            tc::fence_after_sync();
+            float v[kTbNT];
+            {
+                float h[32];
+                const uint32_t ta = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(buf * kTbNT);
+                tc::tmem_ld32(ta, h);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = h[j];
+                tc::tmem_ld32(ta + 32, h);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[32 + j] = h[j];
+            }
+            tc::fence_before_sync();
+            mbar_arrive(&bar_tempty[buf]);
+            if (SCATTER) {
+                // 32 lanes = 32 consecutive feature channels of the same point: one coalesced red per position
+                for (int j = 0; j < kTbNT; ++j) {
+                    const int pt = __ldg(q.idx + static_cast<size_t>(b) * P + p0 + j);
+                    if (valid) atomicAdd(q.dfeat_pm + (static_cast<size_t>(b) * q.N + pt) * q.dfeat_stride + q.dfeat_off + r, v[j]);
+                }
+                continue;
+            }
+            if (!valid) continue;
+            float4 *dp = reinterpret_cast<float4 *>(q.dz_prev + (static_cast<size_t>(b) * q.rows + r) * P + p0);
+            if (q.add_partial) {
+#pragma unroll
+                for (int j = 0; j < kTbNT / 4; ++j) {
+                    const float4 o = dp[j];
+                    v[4 * j] += o.x; v[4 * j + 1] += o.y; v[4 * j + 2] += o.z; v[4 * j + 3] += o.w;
+                }
+            }
+            if (q.final) {
+                const float4 *yp = reinterpret_cast<const float4 *>(q.y_prev + (static_cast<size_t>(b) * q.rows + r) * P + p0);
+                float s = 0.f, sy = 0.f;
+#pragma unroll
+                for (int j = 0; j < kTbNT / 4; ++j) {
+                    const float4 y4 = __ldg(yp + j);
+                    const float yy[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float g = fmaf(sc, yy[e], sh) > 0.f ? v[4 * j + e] : 0.f;
+                        v[4 * j + e] = g;
+                        s += g;
+                        sy = fmaf(g, (yy[e] - mu) * rs, sy);
+                    }
+                }
+                dsum += static_cast<double>(s);
+                dsumy += static_cast<double>(sy);
+            }
+#pragma unroll
+            for (int j = 0; j < kTbNT / 4; ++j) dp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        if (!SCATTER && q.final && valid) {
+            atomicAdd(q.dbeta_prev + r, static_cast<float>(dsum));
+            atomicAdd(q.dgamma_prev + r, static_cast<float>(dsumy));
+            const int g = r / (q.rows / kGnGroups);
+            const double gm = static_cast<double>(__ldg(q.gamma_prev + r));
+            atomicAdd(&gs[g][0], gm * dsum);
+            atomicAdd(&gs[g][1], gm * dsumy);
+        }
+        named_bar_sync(1, 128);
+        if (!SCATTER && q.final && tid < kGnGroups * 2)
+            atomicAdd(q.ab_prev + static_cast<size_t>(b) * kGnGroups * 2 + tid, (&gs[0][0])[tid]);
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 8) tc::tmem_dealloc(tmem_base, 128);
+}
+
+// ------------------------------------------------------------------------------------------------ dW
+struct MlpDwTcParams {
+    DySrc dy;                     // layer l: rows of dW = dy.C
+    int Cin, B, NB;               // NB = number of 32-wide column blocks of the a-tile
+    const float *y_prev, *ss_prev;
+    const float *xyz, *new_xyz, *feat_pm;
+    const int *idx;
+    int N, Cf;
+    float *dW;                    // (Cout, Cin) accumulated with red.add
+};
+
+// a-tile column order: dense: input channel ci; gather: [feat 0..Cf-1, xyz 0..2] (feature rows stay 16 B aligned)
+template <bool GATHER>
+__global__ void __launch_bounds__(kTbThreads, 1)
+mlp_dw_tc_kernel(MlpDwTcParams q) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full, bar_empty, bar_done;
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int mb = blockIdx.y;
+    const int P = q.dy.P, Cout = q.dy.C, NB = q.NB;
+    const int tiles_per_sample = P / kTbNT;
+    const int total = q.B * tiles_per_sample;
+    const int ncols_n = GATHER ? q.Cf + 3 : q.Cin;               // valid a-tile columns
+    const int n_mma = ((ncols_n + 15) / 16) * 16;                // MMA N
+
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t blk = kTbNT * 128u;                          // one column block: 64 rows x 128 B
+    uint8_t *dy_hi = smem, *dy_lo = dy_hi + 4 * blk, *a_hi = dy_lo + 4 * blk, *a_lo = a_hi + NB * blk;
+
+    if (warp == 8) tc::tmem_alloc(&tmem_base_s, 256);
+    if (tid == 0) {
+        mbar_init(&bar_full, 128);
+        mbar_init(&bar_empty, 1);
+        mbar_init(&bar_done, 1);
+        mbar_fence_init();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp >= 4 && warp < 8) {
+        const int lt = tid - 128, lw = warp - 4;
+        int use = 0;
+        for (int w = blockIdx.x; w < total; w += gridDim.x, ++use) {
+            const int b = w / tiles_per_sample, p0 = (w - b * tiles_per_sample) * kTbNT;
+            mbar_wait(&bar_empty, (use & 1) ^ 1);
+            // ---- dY tile: rows = positions, columns = this M block's 128 output channels ----
+            for (int it0 = lt; it0 < 4 * 16 * 32; it0 += 128 * 4) {
+                DyRaw raw[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int it = it0 + 128 * u;
+                    const int cl = it & 31, pq = (it >> 5) & 15, cb = it >> 9;
+                    const int co = mb * kTbM + cb * 32 + cl;
+                    if (co < Cout) dy_quad_load(q.dy, b, co, p0 + pq * 4, raw[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int it = it0 + 128 * u;
+                    const int cl = it & 31, pq = (it >> 5) & 15, cb = it >> 9;
+                    const int co = mb * kTbM + cb * 32 + cl;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (co < Cout) v = dy_quad_finish(q.dy, p0 + pq * 4, raw[u]);
+                    const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float hi = tc::tf32_hi(vv[j]);
+                        const uint32_t off = static_cast<uint32_t>(cb) * blk + tc::sw128_32b_offset(pq * 4 + j, cl);
+                        *reinterpret_cast<float *>(dy_hi + off) = hi;
+                        *reinterpret_cast<float *>(dy_lo + off) = tc::tf32_hi(vv[j] - hi);
+                    }
+                }
+            }
+            // ---- a tile: rows = positions, columns = input channels ----
+            if (GATHER) {
+                const int j_lo = __ldg(q.idx + static_cast<size_t>(b) * P + p0 + lane);
+                const int j_hi = __ldg(q.idx + static_cast<size_t>(b) * P + p0 + 32 + lane);
+                const int nitems = kTbNT * NB;
+                for (int it0 = lw; it0 < nitems; it0 += 4 * 8) {
+                    float vals[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int it = it0 + 4 * u;
+                        const int p = it / NB, cb = it - p * NB;
+                        const int j = __shfl_sync(OGC_FULL_MASK, p < 32 ? j_lo : j_hi, p & 31);
+                        const int c = cb * 32 + lane;
+                        float v = 0.f;
+                        if (it < nitems) {
+                            if (c < q.Cf) v = __ldg(q.feat_pm + (static_cast<size_t>(b) * q.N + j) * q.Cf + c);
+                            else if (c < q.Cf + 3)
+                                v = __ldg(q.xyz + (static_cast<size_t>(b) * q.N + j) * 3 + (c - q.Cf)) -
+                                    __ldg(q.new_xyz + (static_cast<size_t>(b) * q.dy.M + (p0 + p) / q.dy.S) * 3 + (c - q.Cf));
+                        }
+                        vals[u] = v;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int it = it0 + 4 * u;
+                        if (it < nitems) {
+                            const int p = it / NB, cb = it - p * NB;
+                            const float hi = tc::tf32_hi(vals[u]);
+                            const uint32_t off = static_cast<uint32_t>(cb) * blk + tc::sw128_32b_offset(p, lane);
+                            *reinterpret_cast<float *>(a_hi + off) = hi;
+                            *reinterpret_cast<float *>(a_lo + off) = tc::tf32_hi(vals[u] - hi);
+                        }
+                    }
+                }
+            } else {
+                const int nitems = NB * 16 * 32;
+                for (int it0 = lt; it0 < nitems; it0 += 128 * 8) {
+                    float4 raw[8];
+                    float scv[8], shv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int it = it0 + 128 * u;
+                        const int cl = it & 31, pq = (it >> 5) & 15, cb = it >> 9;
+                        const int c = cb * 32 + cl;
+                        raw[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        scv[u] = shv[u] = 0.f;
+                        if (it < nitems && c < q.Cin) {
+                            scv[u] = __ldg(q.ss_prev + (static_cast<size_t>(b) * q.Cin + c) * 2);
+                            shv[u] = __ldg(q.ss_prev + (static_cast<size_t>(b) * q.Cin + c) * 2 + 1);
+                            raw[u] = __ldg(reinterpret_cast<const float4 *>(q.y_prev + (static_cast<size_t>(b) * q.Cin + c) * P + p0 + pq * 4));
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int it = it0 + 128 * u;
+                        if (it >= nitems) continue;
+                        const int cl = it & 31, pq = (it >> 5) & 15, cb = it >> 9;
+                        const float vv[4] = {fmaxf(fmaf(scv[u], raw[u].x, shv[u]), 0.f), fmaxf(fmaf(scv[u], raw[u].y, shv[u]), 0.f),
+                                             fmaxf(fmaf(scv[u], raw[u].z, shv[u]), 0.f), fmaxf(fmaf(scv[u], raw[u].w, shv[u]), 0.f)};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float hi = tc::tf32_hi(vv[j]);
+                            const uint32_t off = static_cast<uint32_t>(cb) * blk + tc::sw128_32b_offset(pq * 4 + j, cl);
+                            *reinterpret_cast<float *>(a_hi + off) = hi;
+                            *reinterpret_cast<float *>(a_lo + off) = tc::tf32_hi(vv[j] - hi);
+                        }
+                    }
+                }
+            }
+            tc::fence_proxy_async();
+            mbar_arrive(&bar_full);
+        }
+    } else if (warp == 8) {
+        if (lane == 0) {
+            const uint32_t idesc = tc::make_idesc_tf32(kTbM, n_mma, 1, 1);
+            int use = 0;
+            uint32_t acc = 0;
+            for (int w = blockIdx.x; w < total; w += gridDim.x, ++use) {
+                mbar_wait(&bar_full, use & 1);
+                tc::fence_after_sync();
+                for (int s = 0; s < kTbNT / 8; ++s) {      // K = 64 positions = 8 steps of 8 rows (1024 B)
+                    const uint32_t o = static_cast<uint32_t>(s) * 1024u;
+                    const uint64_t dhd = tc::make_desc(smem_u32(dy_hi) + o, blk, 512, tc::kLayoutSw128Base32);
+                    const uint64_t dld = tc::make_desc(smem_u32(dy_lo) + o, blk, 512, tc::kLayoutSw128Base32);
+                    const uint64_t ahd = tc::make_desc(smem_u32(a_hi) + o, blk, 512, tc::kLayoutSw128Base32);
+                    const uint64_t ald = tc::make_desc(smem_u32(a_lo) + o, blk, 512, tc::kLayoutSw128Base32);
+                    tc::mma_tf32(tmem_base, dhd, ahd, idesc, acc);
+                    tc::mma_tf32(tmem_base, dhd, ald, idesc, 1);
+                    tc::mma_tf32(tmem_base, dld, ahd, idesc, 1);
+                    acc = 1;
+                }
+                tc::mma_commit(&bar_empty);
+            }
+            tc::mma_commit(&bar_done);
+        }
+    } else {
+        // epilogue: wait for every MMA of this CTA, then lane = output channel adds its row of dW
+        mbar_wait(&bar_done, 0);
+        tc::fence_after_sync();
+        const int co = mb * kTbM + tid;
+        const bool any = blockIdx.x < total;                      // CTAs without work hold garbage in TMEM
+        for (int c0 = 0; c0 < n_mma; c0 += 32) {
+            float h[32];
+            tc::tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(c0), h);
+            if (!any || co >= Cout) continue;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int c = c0 + j;
+                if (c >= ncols_n) continue;
+                const int ci = GATHER ? (c < q.Cf ? 3 + c : c - q.Cf) : c;
+                atomicAdd(q.dW + static_cast<size_t>(co) * q.Cin + ci, h[j]);
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 8) tc::tmem_dealloc(tmem_base, 256);
+}
+
+}  // namespace ogc
+
+// Tensor-core variant of ogc_sa_mlp_layer_dx (same argument meaning).  nsample == 64, rows <= 128, cout a multiple
+// of 4; cout > 128 runs as two launches whose partial sums travel through dz_prev.  Scatter mode needs cout <= 128.
+extern "C" int ogc_sa_mlp_layer_dx_tc(int b, int n, int m, int nsample, int cout, int cin_full, int row_off, int rows,
+                                      const float *dz, const float *go, int go_ctotal, int go_coff,
+                                      const unsigned char *sel, const float *y, const float *coef, const float *w,
+                                      const float *y_prev, const float *ss_prev, const float *mean_rstd_prev,
+                                      const float *gamma_prev, float *dz_prev, double *ab_prev, float *dgamma_prev,
+                                      float *dbeta_prev, const int *idx, float *dfeat_pm, int dfeat_stride,
+                                      int dfeat_off, void *stream) {
+    using namespace ogc;
+    if (b < 0 || m <= 0 || nsample <= 0 || cout <= 0 || rows <= 0 || row_off < 0 || row_off + rows > cin_full || !w)
+        return OGC_ERR_INVALID_ARG;
+    if (b == 0) return OGC_OK;
+    const bool scatter = dfeat_pm != nullptr;
+    if (nsample != kTbNT || rows > kTbM || b > 65535 || cout > 256 || cout < 32 || (scatter && cout > 128))
+        return OGC_ERR_UNSUPPORTED;
+    MlpDxTcParams q;
+    int rc = fill_dy(q.dy, cout, m, nsample, dz, go, go_ctotal, go_coff, sel, y, coef);
+    if (rc != OGC_OK) return rc;
+    if (scatter) {
+        if (!idx) return OGC_ERR_INVALID_ARG;
+    } else {
+        if (!y_prev || !ss_prev || !mean_rstd_prev || !gamma_prev || !dz_prev || !ab_prev || !dgamma_prev || !dbeta_prev)
+            return OGC_ERR_INVALID_ARG;
+        if (rows % 16 != 0) return OGC_ERR_UNSUPPORTED;
+    }
+    q.cin_full = cin_full; q.row_off = row_off; q.rows = rows; q.W = w;
+    q.y_prev = y_prev; q.ss_prev = ss_prev; q.mean_rstd_prev = mean_rstd_prev; q.gamma_prev = gamma_prev;
+    q.dz_prev = dz_prev; q.ab_prev = ab_prev; q.dgamma_prev = dgamma_prev; q.dbeta_prev = dbeta_prev;
+    q.idx = idx; q.dfeat_pm = dfeat_pm; q.N = n; q.dfeat_stride = dfeat_stride; q.dfeat_off = dfeat_off;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int per_sample = kNumSMs / b;
+    per_sample = per_sample > m ? m : (per_sample < 1 ? 1 : per_sample);
+    dim3 grid(per_sample, b);
+    for (int k0 = 0; k0 < cout; k0 += kTbM) {
+        q.k0 = k0;
+        q.kn = cout - k0 < kTbM ? cout - k0 : kTbM;
+        q.add_partial = k0 > 0;
+        q.final = k0 + kTbM >= cout;
+        const int KB = (q.kn + 31) / 32;
+        const size_t smem = static_cast<size_t>(KB) * (kTbM + kTbNT) * 128 * 2 + 1024;
+        cudaError_t e;
+        if (scatter) {
+            e = cudaFuncSetAttribute(mlp_dx_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            if (e != cudaSuccess) return static_cast<int>(e);
+            mlp_dx_tc_kernel<true><<<grid, kTbThreads, smem, st>>>(q);
+        } else {
+            e = cudaFuncSetAttribute(mlp_dx_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            if (e != cudaSuccess) return static_cast<int>(e);
+            mlp_dx_tc_kernel<false><<<grid, kTbThreads, smem, st>>>(q);
+        }
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return static_cast<int>(e);
+    }
+    return OGC_OK;
+}
+
+// Tensor-core variant of ogc_sa_mlp_layer_dw (same argument meaning).  nsample == 64, cin (+3 gathered) <= 160.
+extern "C" int ogc_sa_mlp_layer_dw_tc(int b, int n, int m, int nsample, int cout, int cin, int gather, const float *dz,
+                                      const float *go, int go_ctotal, int go_coff, const unsigned char *sel,
+                                      const float *y, const float *coef, const float *y_prev, const float *ss_prev,
+                                      const float *xyz, const float *new_xyz, const float *feat_pm, const int *idx,
+                                      float *dw, void *stream) {
+    using namespace ogc;
+    if (b < 0 || m <= 0 || nsample <= 0 || cout <= 0 || cin <= 0 || !dw) return OGC_ERR_INVALID_ARG;
+    if (b == 0) return OGC_OK;
+    if (nsample != kTbNT || cin > 160 || cin < 16 || cout < 32 || cout > 256) return OGC_ERR_UNSUPPORTED;
+    MlpDwTcParams q;
+    int rc = fill_dy(q.dy, cout, m, nsample, dz, go, go_ctotal, go_coff, sel, y, coef);
+    if (rc != OGC_OK) return rc;
+    if (gather && (!xyz || !new_xyz || !idx || cin < 3 || (cin > 3 && !feat_pm))) return OGC_ERR_INVALID_ARG;
+    if (!gather && (!y_prev || !ss_prev)) return OGC_ERR_INVALID_ARG;
+    q.Cin = cin; q.B = b; q.y_prev = y_prev; q.ss_prev = ss_prev; q.xyz = xyz; q.new_xyz = new_xyz;
+    q.feat_pm = feat_pm; q.idx = idx; q.N = n; q.Cf = cin - 3; q.dW = dw;
+    q.NB = (cin + 31) / 32;
+    const size_t smem = static_cast<size_t>(8 + 2 * q.NB) * kTbNT * 128 + 1024;
+    const int mblocks = (cout + kTbM - 1) / kTbM;
+    const int total = b * m;
+    int gx = kNumSMs / mblocks;
+    gx = gx > total ? total : (gx < 1 ? 1 : gx);
+    dim3 grid(gx, mblocks);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    if (gather) {
+        e = cudaFuncSetAttribute(mlp_dw_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return static_cast<int>(e);
+        mlp_dw_tc_kernel<true><<<grid, kTbThreads, smem, st>>>(q);
+    } else {
+        e = cudaFuncSetAttribute(mlp_dw_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return static_cast<int>(e);
+        mlp_dw_tc_kernel<false><<<grid, kTbThreads, smem, st>>>(q);
+    }
+    OGC_RETURN_LAUNCH_STATUS();
+}

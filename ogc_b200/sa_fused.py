@@ -24,6 +24,14 @@ def _tc_ok(S, cin, cout, gather):
     return USE_TC and S == 64 and cout >= 64 and cout % 16 == 0 and cout <= 256 and 32 <= k <= 160 and k % 4 == 0
 
 
+def _tc_dw_ok(S, cin, cout):
+    return USE_TC and S == 64 and 32 <= cin <= 160 and 32 <= cout <= 256
+
+
+def _tc_dx_ok(S, cout, rows, scatter):
+    return USE_TC and S == 64 and 32 <= cout <= (128 if scatter else 256) and rows <= 128 and (scatter or rows % 16 == 0)
+
+
 def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -133,8 +141,10 @@ class _FusedSAMLP(Function):
             grads[3 * l + 1], grads[3 * l + 2] = dgamma, dbeta
             dW = torch.zeros(cout, cin, **f32)
             gather = l == 0
-            with TIMER.span(f"sa_mlp_dw[{cin}>{cout}]" if TIMER.detail else "sa_mlp_dw", B * P * 4 * (2 * cout + cin)):
-                _lib.check(lib.ogc_sa_mlp_layer_dw(
+            dw_tc = _tc_dw_ok(S, cin, cout)
+            dw_fn, dw_tag = (lib.ogc_sa_mlp_layer_dw_tc, "sa_mlp_dw_tc") if dw_tc else (lib.ogc_sa_mlp_layer_dw, "sa_mlp_dw")
+            with TIMER.span(f"{dw_tag}[{cin}>{cout}]" if TIMER.detail else dw_tag, B * P * 4 * (2 * cout + cin)):
+                _lib.check(dw_fn(
                     B, N, M, S, cout, cin, int(gather), _p(dz), _p(go), cL, 0, _p(sel), _p(ys[l]), _p(coef),
                     _p(ys[l - 1]) if l else None, _p(sss[l - 1]) if l else None,
                     _p(xyz), _p(new_xyz), _p(feat_pm), _p(idx), _p(dW), _st()), "ogc_sa_mlp_layer_dw")
@@ -146,8 +156,10 @@ class _FusedSAMLP(Function):
                 ab_prev = torch.zeros(B, 4, 2, dtype=torch.float64, device=dev)
                 dgamma_prev = torch.zeros(cprev, **f32)
                 dbeta_prev = torch.zeros(cprev, **f32)
-                with TIMER.span(f"sa_mlp_dx[{cout}>{cprev}]" if TIMER.detail else "sa_mlp_dx", B * P * 4 * (2 * cout + 2 * cprev)):
-                    _lib.check(lib.ogc_sa_mlp_layer_dx(
+                dx_tc = _tc_dx_ok(S, cout, cprev, False)
+                dx_fn, dx_tag = (lib.ogc_sa_mlp_layer_dx_tc, "sa_mlp_dx_tc") if dx_tc else (lib.ogc_sa_mlp_layer_dx, "sa_mlp_dx")
+                with TIMER.span(f"{dx_tag}[{cout}>{cprev}]" if TIMER.detail else dx_tag, B * P * 4 * (2 * cout + 2 * cprev)):
+                    _lib.check(dx_fn(
                         B, N, M, S, cout, cin, 0, cprev, _p(dz), _p(go), cL, 0, _p(sel), _p(ys[l]), _p(coef), _p(w2d),
                         _p(ys[l - 1]), _p(sss[l - 1]), _p(mrs[l - 1]), _p(params[3 * (l - 1) + 1]), _p(dz_prev),
                         _p(ab_prev), _p(dgamma_prev), _p(dbeta_prev), None, None, 0, 0, _st()), "ogc_sa_mlp_layer_dx")
@@ -157,8 +169,10 @@ class _FusedSAMLP(Function):
                 dfeat_pm = torch.zeros(B, N, Cf, **f32)
                 for off in range(0, Cf, 128):
                     rows = min(128, Cf - off)
-                    with TIMER.span(f"sa_mlp_dx[{cout}>scatter{rows}]" if TIMER.detail else "sa_mlp_dx", B * P * 4 * (2 * cout + rows)):
-                        _lib.check(lib.ogc_sa_mlp_layer_dx(
+                    dx_tc = _tc_dx_ok(S, cout, rows, True)
+                    dx_fn, dx_tag = (lib.ogc_sa_mlp_layer_dx_tc, "sa_mlp_dx_tc") if dx_tc else (lib.ogc_sa_mlp_layer_dx, "sa_mlp_dx")
+                    with TIMER.span(f"{dx_tag}[{cout}>scatter{rows}]" if TIMER.detail else dx_tag, B * P * 4 * (2 * cout + rows)):
+                        _lib.check(dx_fn(
                             B, N, M, S, cout, cin, 3 + off, rows, _p(dz), _p(go), cL, 0, _p(sel), _p(ys[l]), _p(coef),
                             _p(w2d), None, None, None, None, None, None, None, None, _p(idx), _p(dfeat_pm), Cf, off,
                             _st()), "ogc_sa_mlp_layer_dx")

@@ -26,7 +26,7 @@ for name,N,M,Cf,w in cfgs:
     P=M*64
     print(f"== {name}: N={N} M={M} P={P} Cin={Cf+3} widths={w}")
     for k,v in backend.TIMER.summary().items():
-        if not k.startswith('sa_mlp'): continue
+        if not k.startswith("sa_mlp"): continue
         ms=v['ms']/v['calls']
         import re
         a,bb=re.findall(r'\[(\d+)>(?:scatter)?(\d+)\]',k)[0]; a=int(a); bb=int(bb)
