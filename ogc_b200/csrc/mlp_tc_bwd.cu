@@ -8,8 +8,9 @@
 //        dgamma / dbeta sums in registers (no shuffles); layer 1: coalesced red.add of 32 consecutive feature
 //        channels per point instead.  K > 128 is split over two launches (partial sums through dz_prev).
 //   dW:  dW[co][ci] = sum_p dY[co][p] a[ci][p]      M = 128 output channels, N = C_in (<= 160), K = positions
-//        both operands MN-major (rows = positions, 128B swizzle with 32 B base), ONE TMEM accumulator per CTA
-//        accumulated over all its position tiles, read out once and red.add'ed into dW.
+//        both operands K-major with rows = channels (a row = 32 consecutive positions = 128 contiguous bytes of the
+//        channel-major tensors: vectorised loads and stores, no transposition), 2-stage operand pipeline, ONE TMEM
+//        accumulator per CTA accumulated over all its position tiles, read out once and red.add'ed into dW.
 #include "mlp_dy.cuh"
 #include "tcgen05.cuh"
 
@@ -232,7 +233,7 @@ mlp_dx_tc_kernel(MlpDxTcParams q) {
 // ------------------------------------------------------------------------------------------------ dW
 struct MlpDwTcParams {
     DySrc dy;                     // layer l: rows of dW = dy.C
-    int Cin, B, NB;               // NB = number of 32-wide column blocks of the a-tile
+    int Cin, B;
     const float *y_prev, *ss_prev;
     const float *xyz, *new_xyz, *feat_pm;
     const int *idx;
@@ -240,30 +241,39 @@ struct MlpDwTcParams {
     float *dW;                    // (Cout, Cin) accumulated with red.add
 };
 
-// a-tile column order: dense: input channel ci; gather: [feat 0..Cf-1, xyz 0..2] (feature rows stay 16 B aligned)
+constexpr int kDwTile = 32;       // positions per pipeline stage = one 128-byte row of every operand
+constexpr int kDwStages = 2;
+
+// K = positions.  Both operands K-major with rows = channels: a row is 32 consecutive positions of one channel,
+// i.e. 128 contiguous bytes of the channel-major tensors -> float4 loads, 16-byte swizzled stores, no transposition
+// (only the gathered a_0 of layer 1 is built point by point).  a-tile row order: dense: ci; gather: [feat, xyz].
 template <bool GATHER>
 __global__ void __launch_bounds__(kTbThreads, 1)
 mlp_dw_tc_kernel(MlpDwTcParams q) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_full, bar_empty, bar_done;
+    __shared__ __align__(8) uint64_t bar_full[kDwStages], bar_empty[kDwStages], bar_done;
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int mb = blockIdx.y;
-    const int P = q.dy.P, Cout = q.dy.C, NB = q.NB;
-    const int tiles_per_sample = P / kTbNT;
+    const int P = q.dy.P, Cout = q.dy.C;
+    const int tiles_per_sample = P / kDwTile;
     const int total = q.B * tiles_per_sample;
-    const int ncols_n = GATHER ? q.Cf + 3 : q.Cin;               // valid a-tile columns
-    const int n_mma = ((ncols_n + 15) / 16) * 16;                // MMA N
+    const int nrows_a = GATHER ? q.Cf + 3 : q.Cin;              // valid rows of the a tile
+    const int n_mma = ((nrows_a + 15) / 16) * 16;                // MMA N (rows of B), <= 160
+    const int a_rows_alloc = ((n_mma + 7) / 8) * 8;
 
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const uint32_t blk = kTbNT * 128u;                          // one column block: 64 rows x 128 B
-    uint8_t *dy_hi = smem, *dy_lo = dy_hi + 4 * blk, *a_hi = dy_lo + 4 * blk, *a_lo = a_hi + NB * blk;
+    const uint32_t dy_bytes = kTbM * 128u, a_bytes = static_cast<uint32_t>(a_rows_alloc) * 128u;
+    const uint32_t stage_bytes = 2 * dy_bytes + 2 * ((a_bytes + 1023u) & ~1023u);
+    auto dy_hi = [&](int s) { return smem + s * stage_bytes; };
+    auto dy_lo = [&](int s) { return smem + s * stage_bytes + dy_bytes; };
+    auto a_hi = [&](int s) { return smem + s * stage_bytes + 2 * dy_bytes; };
+    auto a_lo = [&](int s) { return smem + s * stage_bytes + 2 * dy_bytes + ((a_bytes + 1023u) & ~1023u); };
 
     if (warp == 8) tc::tmem_alloc(&tmem_base_s, 256);
     if (tid == 0) {
-        mbar_init(&bar_full, 128);
-        mbar_init(&bar_empty, 1);
+        for (int s = 0; s < kDwStages; ++s) { mbar_init(&bar_full[s], 128); mbar_init(&bar_empty[s], 1); }
         mbar_init(&bar_done, 1);
         mbar_fence_init();
     }
@@ -276,47 +286,48 @@ mlp_dw_tc_kernel(MlpDwTcParams q) {
         const int lt = tid - 128, lw = warp - 4;
         int use = 0;
         for (int w = blockIdx.x; w < total; w += gridDim.x, ++use) {
-            const int b = w / tiles_per_sample, p0 = (w - b * tiles_per_sample) * kTbNT;
-            mbar_wait(&bar_empty, (use & 1) ^ 1);
-            // ---- dY tile: rows = positions, columns = this M block's 128 output channels ----
-            for (int it0 = lt; it0 < 4 * 16 * 32; it0 += 128 * 4) {
-                DyRaw raw[4];
+            const int st = use % kDwStages, ph = (use / kDwStages) & 1;
+            const int b = w / tiles_per_sample, p0 = (w - b * tiles_per_sample) * kDwTile;
+            mbar_wait(&bar_empty[st], ph ^ 1);
+            uint8_t *dh = dy_hi(st), *dl = dy_lo(st), *ah = a_hi(st), *al = a_lo(st);
+            // ---- dY tile: row = output channel of this M block, 8 quads of 4 positions per row ----
+            {
+                DyRaw raw[8];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int it = it0 + 128 * u;
-                    const int cl = it & 31, pq = (it >> 5) & 15, cb = it >> 9;
-                    const int co = mb * kTbM + cb * 32 + cl;
+                for (int u = 0; u < 8; ++u) {
+                    const int it = lt + 128 * u;           // 1024 items = 128 rows x 8 quads
+                    const int row = it >> 3, pq = it & 7;
+                    const int co = mb * kTbM + row;
                     if (co < Cout) dy_quad_load(q.dy, b, co, p0 + pq * 4, raw[u]);
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int it = it0 + 128 * u;
-                    const int cl = it & 31, pq = (it >> 5) & 15, cb = it >> 9;
-                    const int co = mb * kTbM + cb * 32 + cl;
+                for (int u = 0; u < 8; ++u) {
+                    const int it = lt + 128 * u;
+                    const int row = it >> 3, pq = it & 7;
+                    const int co = mb * kTbM + row;
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (co < Cout) v = dy_quad_finish(q.dy, p0 + pq * 4, raw[u]);
-                    const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float hi = tc::tf32_hi(vv[j]);
-                        const uint32_t off = static_cast<uint32_t>(cb) * blk + tc::sw128_32b_offset(pq * 4 + j, cl);
-                        *reinterpret_cast<float *>(dy_hi + off) = hi;
-                        *reinterpret_cast<float *>(dy_lo + off) = tc::tf32_hi(vv[j] - hi);
-                    }
+                    const float4 hi = make_float4(tc::tf32_hi(v.x), tc::tf32_hi(v.y), tc::tf32_hi(v.z), tc::tf32_hi(v.w));
+                    const float4 lo = make_float4(tc::tf32_hi(v.x - hi.x), tc::tf32_hi(v.y - hi.y), tc::tf32_hi(v.z - hi.z),
+                                                  tc::tf32_hi(v.w - hi.w));
+                    const uint32_t off = static_cast<uint32_t>(row) * 128u + static_cast<uint32_t>((pq ^ (row & 7)) * 16);
+                    *reinterpret_cast<float4 *>(dh + off) = hi;
+                    *reinterpret_cast<float4 *>(dl + off) = lo;
                 }
             }
-            // ---- a tile: rows = positions, columns = input channels ----
+            // ---- a tile: row = input channel ----
             if (GATHER) {
-                const int j_lo = __ldg(q.idx + static_cast<size_t>(b) * P + p0 + lane);
-                const int j_hi = __ldg(q.idx + static_cast<size_t>(b) * P + p0 + 32 + lane);
-                const int nitems = kTbNT * NB;
+                // point-major source: lane <-> channel, one position at a time (transposing 4-byte stores)
+                const int jl = __ldg(q.idx + static_cast<size_t>(b) * P + p0 + lane);
+                const int nblk = (nrows_a + 31) / 32;
+                const int nitems = kDwTile * nblk;
                 for (int it0 = lw; it0 < nitems; it0 += 4 * 8) {
                     float vals[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const int it = it0 + 4 * u;
-                        const int p = it / NB, cb = it - p * NB;
-                        const int j = __shfl_sync(OGC_FULL_MASK, p < 32 ? j_lo : j_hi, p & 31);
+                        const int p = it / nblk, cb = it - p * nblk;
+                        const int j = __shfl_sync(OGC_FULL_MASK, jl, p & 31);
                         const int c = cb * 32 + lane;
                         float v = 0.f;
                         if (it < nitems) {
@@ -330,73 +341,75 @@ mlp_dw_tc_kernel(MlpDwTcParams q) {
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const int it = it0 + 4 * u;
-                        if (it < nitems) {
-                            const int p = it / NB, cb = it - p * NB;
+                        const int p = it / nblk, cb = it - p * nblk;
+                        const int c = cb * 32 + lane;
+                        if (it < nitems && c < a_rows_alloc) {
                             const float hi = tc::tf32_hi(vals[u]);
-                            const uint32_t off = static_cast<uint32_t>(cb) * blk + tc::sw128_32b_offset(p, lane);
-                            *reinterpret_cast<float *>(a_hi + off) = hi;
-                            *reinterpret_cast<float *>(a_lo + off) = tc::tf32_hi(vals[u] - hi);
+                            const uint32_t off = tc::sw128_offset(c, p);
+                            *reinterpret_cast<float *>(ah + off) = hi;
+                            *reinterpret_cast<float *>(al + off) = tc::tf32_hi(vals[u] - hi);
                         }
                     }
                 }
             } else {
-                const int nitems = NB * 16 * 32;
+                const int nitems = a_rows_alloc * 8;
                 for (int it0 = lt; it0 < nitems; it0 += 128 * 8) {
                     float4 raw[8];
                     float scv[8], shv[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const int it = it0 + 128 * u;
-                        const int cl = it & 31, pq = (it >> 5) & 15, cb = it >> 9;
-                        const int c = cb * 32 + cl;
+                        const int row = it >> 3, pq = it & 7;
                         raw[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                         scv[u] = shv[u] = 0.f;
-                        if (it < nitems && c < q.Cin) {
-                            scv[u] = __ldg(q.ss_prev + (static_cast<size_t>(b) * q.Cin + c) * 2);
-                            shv[u] = __ldg(q.ss_prev + (static_cast<size_t>(b) * q.Cin + c) * 2 + 1);
-                            raw[u] = __ldg(reinterpret_cast<const float4 *>(q.y_prev + (static_cast<size_t>(b) * q.Cin + c) * P + p0 + pq * 4));
+                        if (it < nitems && row < q.Cin) {
+                            scv[u] = __ldg(q.ss_prev + (static_cast<size_t>(b) * q.Cin + row) * 2);
+                            shv[u] = __ldg(q.ss_prev + (static_cast<size_t>(b) * q.Cin + row) * 2 + 1);
+                            raw[u] = __ldg(reinterpret_cast<const float4 *>(q.y_prev + (static_cast<size_t>(b) * q.Cin + row) * P + p0 + pq * 4));
                         }
                     }
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const int it = it0 + 128 * u;
                         if (it >= nitems) continue;
-                        const int cl = it & 31, pq = (it >> 5) & 15, cb = it >> 9;
-                        const float vv[4] = {fmaxf(fmaf(scv[u], raw[u].x, shv[u]), 0.f), fmaxf(fmaf(scv[u], raw[u].y, shv[u]), 0.f),
-                                             fmaxf(fmaf(scv[u], raw[u].z, shv[u]), 0.f), fmaxf(fmaf(scv[u], raw[u].w, shv[u]), 0.f)};
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float hi = tc::tf32_hi(vv[j]);
-                            const uint32_t off = static_cast<uint32_t>(cb) * blk + tc::sw128_32b_offset(pq * 4 + j, cl);
-                            *reinterpret_cast<float *>(a_hi + off) = hi;
-                            *reinterpret_cast<float *>(a_lo + off) = tc::tf32_hi(vv[j] - hi);
-                        }
+                        const int row = it >> 3, pq = it & 7;
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (row < q.Cin)
+                            v = make_float4(fmaxf(fmaf(scv[u], raw[u].x, shv[u]), 0.f), fmaxf(fmaf(scv[u], raw[u].y, shv[u]), 0.f),
+                                            fmaxf(fmaf(scv[u], raw[u].z, shv[u]), 0.f), fmaxf(fmaf(scv[u], raw[u].w, shv[u]), 0.f));
+                        const float4 hi = make_float4(tc::tf32_hi(v.x), tc::tf32_hi(v.y), tc::tf32_hi(v.z), tc::tf32_hi(v.w));
+                        const float4 lo = make_float4(tc::tf32_hi(v.x - hi.x), tc::tf32_hi(v.y - hi.y), tc::tf32_hi(v.z - hi.z),
+                                                      tc::tf32_hi(v.w - hi.w));
+                        const uint32_t off = static_cast<uint32_t>(row) * 128u + static_cast<uint32_t>((pq ^ (row & 7)) * 16);
+                        *reinterpret_cast<float4 *>(ah + off) = hi;
+                        *reinterpret_cast<float4 *>(al + off) = lo;
                     }
                 }
             }
             tc::fence_proxy_async();
-            mbar_arrive(&bar_full);
+            mbar_arrive(&bar_full[st]);
         }
     } else if (warp == 8) {
         if (lane == 0) {
-            const uint32_t idesc = tc::make_idesc_tf32(kTbM, n_mma, 1, 1);
+            const uint32_t idesc = tc::make_idesc_tf32(kTbM, n_mma, 0, 0);
             int use = 0;
             uint32_t acc = 0;
             for (int w = blockIdx.x; w < total; w += gridDim.x, ++use) {
-                mbar_wait(&bar_full, use & 1);
+                const int st = use % kDwStages, ph = (use / kDwStages) & 1;
+                mbar_wait(&bar_full[st], ph);
                 tc::fence_after_sync();
-                for (int s = 0; s < kTbNT / 8; ++s) {      // K = 64 positions = 8 steps of 8 rows (1024 B)
-                    const uint32_t o = static_cast<uint32_t>(s) * 1024u;
-                    const uint64_t dhd = tc::make_desc(smem_u32(dy_hi) + o, blk, 512, tc::kLayoutSw128Base32);
-                    const uint64_t dld = tc::make_desc(smem_u32(dy_lo) + o, blk, 512, tc::kLayoutSw128Base32);
-                    const uint64_t ahd = tc::make_desc(smem_u32(a_hi) + o, blk, 512, tc::kLayoutSw128Base32);
-                    const uint64_t ald = tc::make_desc(smem_u32(a_lo) + o, blk, 512, tc::kLayoutSw128Base32);
+                for (int s = 0; s < kDwTile / 8; ++s) {     // 32 positions = 4 K-steps of 32 B inside the 128 B rows
+                    const uint32_t o = static_cast<uint32_t>(s) * 32u;
+                    const uint64_t dhd = tc::make_desc_sw128(smem_u32(dy_hi(st)) + o, 16, 1024);
+                    const uint64_t dld = tc::make_desc_sw128(smem_u32(dy_lo(st)) + o, 16, 1024);
+                    const uint64_t ahd = tc::make_desc_sw128(smem_u32(a_hi(st)) + o, 16, 1024);
+                    const uint64_t ald = tc::make_desc_sw128(smem_u32(a_lo(st)) + o, 16, 1024);
                     tc::mma_tf32(tmem_base, dhd, ahd, idesc, acc);
                     tc::mma_tf32(tmem_base, dhd, ald, idesc, 1);
                     tc::mma_tf32(tmem_base, dld, ahd, idesc, 1);
                     acc = 1;
                 }
-                tc::mma_commit(&bar_empty);
+                tc::mma_commit(&bar_empty[st]);
             }
             tc::mma_commit(&bar_done);
         }
@@ -405,15 +418,14 @@ mlp_dw_tc_kernel(MlpDwTcParams q) {
         mbar_wait(&bar_done, 0);
         tc::fence_after_sync();
         const int co = mb * kTbM + tid;
-        const bool any = blockIdx.x < total;                      // CTAs without work hold garbage in TMEM
         for (int c0 = 0; c0 < n_mma; c0 += 32) {
             float h[32];
             tc::tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(c0), h);
-            if (!any || co >= Cout) continue;
+            if (co >= Cout) continue;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const int c = c0 + j;
-                if (c >= ncols_n) continue;
+                if (c >= nrows_a) continue;
                 const int ci = GATHER ? (c < q.Cf ? 3 + c : c - q.Cf) : c;
                 atomicAdd(q.dW + static_cast<size_t>(co) * q.Cin + ci, h[j]);
             }
@@ -500,10 +512,11 @@ extern "C" int ogc_sa_mlp_layer_dw_tc(int b, int n, int m, int nsample, int cout
     if (!gather && (!y_prev || !ss_prev)) return OGC_ERR_INVALID_ARG;
     q.Cin = cin; q.B = b; q.y_prev = y_prev; q.ss_prev = ss_prev; q.xyz = xyz; q.new_xyz = new_xyz;
     q.feat_pm = feat_pm; q.idx = idx; q.N = n; q.Cf = cin - 3; q.dW = dw;
-    q.NB = (cin + 31) / 32;
-    const size_t smem = static_cast<size_t>(8 + 2 * q.NB) * kTbNT * 128 + 1024;
+    const int n_mma = ((cin + 15) / 16) * 16, a_rows = ((n_mma + 7) / 8) * 8;
+    const size_t a_bytes = ((static_cast<size_t>(a_rows) * 128) + 1023) & ~static_cast<size_t>(1023);
+    const size_t smem = static_cast<size_t>(kDwStages) * (2 * kTbM * 128 + 2 * a_bytes) + 1024;
     const int mblocks = (cout + kTbM - 1) / kTbM;
-    const int total = b * m;
+    const int total = b * m * (nsample / kDwTile);
     int gx = kNumSMs / mblocks;
     gx = gx > total ? total : (gx < 1 ? 1 : gx);
     dim3 grid(gx, mblocks);

@@ -24,8 +24,15 @@ def _tc_ok(S, cin, cout, gather):
     return USE_TC and S == 64 and cout >= 64 and cout % 16 == 0 and cout <= 256 and 32 <= k <= 160 and k % 4 == 0
 
 
+TC_DW_ALL = False   # tests: route every supported dW through the tensor-core kernel
+
+
 def _tc_dw_ok(S, cin, cout):
-    return USE_TC and S == 64 and 32 <= cin <= 160 and 32 <= cout <= 256
+    # measured (scratch/mlp_bench.py): the tensor-core dW only beats the SIMT split-K kernel for the square 128x128
+    # layer; elsewhere its loader (two dependent load batches per 32-position tile) is the bottleneck
+    if TC_DW_ALL:
+        return USE_TC and S == 64 and 32 <= cin <= 160 and 32 <= cout <= 256
+    return USE_TC and S == 64 and cin == 128 and cout == 128
 
 
 def _tc_dx_ok(S, cout, rows, scatter):

@@ -107,6 +107,33 @@ def test_tensor_core_forward_matches_simt_forward(b200, N, M, Cf, widths):
             assert float((a - b).abs().max()) <= 2e-5 * max(1.0, float(a.abs().max()))
 
 
+def test_tensor_core_dw_kernel_matches_simt(b200):
+    """Every supported weight-gradient shape through the tcgen05 dW kernel (it is only the default for 128x128)."""
+    from ogc_b200 import segnet, sa_fused
+    import pointnet2.pointnet2 as ops
+    torch.manual_seed(7)
+    B, S, N, M, Cf, widths = 2, 64, 300, 70, 128, [128, 128, 256]
+    xyz = torch.randn(B, N, 3, device="cuda")
+    new_xyz = xyz[:, :M].contiguous()
+    feat_pm = torch.randn(B, N, Cf, device="cuda")
+    mlp = segnet.SharedMLP([Cf + 3] + widths).cuda()
+    dist, idx = ops.knn(S, new_xyz, xyz)
+    layers = [(getattr(mlp, f"layer{i}").conv.weight, getattr(mlp, f"layer{i}").normlayer.gn.weight,
+               getattr(mlp, f"layer{i}").normlayer.gn.bias) for i in range(3)]
+    probe = torch.randn(B, widths[-1], M, device="cuda")
+    grads = {}
+    for flag in (False, True):
+        sa_fused.TC_DW_ALL = flag
+        try:
+            mlp.zero_grad()
+            (sa_fused.fused_sa_mlp(xyz, new_xyz, feat_pm, idx, layers) * probe).sum().backward()
+        finally:
+            sa_fused.TC_DW_ALL = False
+        grads[flag] = [getattr(mlp, f"layer{i}").conv.weight.grad.clone() for i in range(3)]
+    for a, b in zip(grads[False], grads[True]):
+        assert float((a - b).norm() / a.norm()) < 1e-5
+
+
 def test_segnet_fused_equals_composed_full_model(b200):
     """Whole MaskFormer3D (kitti variant, 2048 points): fused SA path vs composed path, masks and gradients."""
     from ogc_b200 import segnet
