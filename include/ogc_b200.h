@@ -273,7 +273,8 @@ OGC_API int ogc_lsap_maximize_host(int n, const double *score, int *col4row);
 
 /* RankLoss (losses/seg_loss_unsup.py:300-314): out (b) = nuclear norm of each (n,k) mask, via the fp64 Gram
  * matrix and a Jacobi eigen-solve on the device (no cuSOLVER SVD, no host sync). */
-OGC_API int ogc_mask_nuclear_norm(int b, int n, int k, const float *mask, float *out, void *stream);
+OGC_API int ogc_mask_nuclear_norm(int b, int n, int k, const float *mask, float *out, double *gram_ws,
+                                  void *stream);   /* gram_ws: caller scratch, b*32*32 doubles */
 
 /* ogc_adam_step with the step counter and learning rate in device memory (state[0] = t, state[1] = lr), so a
  * CUDA-graph-captured training step can be replayed: t advances on the device, lr is refreshed by a host->device
@@ -297,6 +298,13 @@ OGC_API int ogc_sa_mlp_layer_dw_tc(int b, int n, int m, int nsample, int cout, i
                                    const float *y, const float *coef, const float *y_prev, const float *ss_prev,
                                    const float *xyz, const float *new_xyz, const float *feat_pm, const int *idx,
                                    float *dw, void *stream);
+
+/* ogc_knn_sqrt restricted to candidates with distance <= max_dist: exact AFTER the radius clipping the callers
+ * apply (QueryAndGroup pointnet2/pointnet2.py:284-286, KnnLoss losses/seg_loss_unsup.py:121-122), far cheaper in
+ * sparse clouds.  Slots without a candidate inside the bound hold (+inf, 0).  Requires each query's nearest
+ * neighbour to lie inside the bound (queries drawn from `known`). */
+OGC_API int ogc_knn_bounded(int b, int n, int m, int k, float max_dist, const float *unknown, const float *known,
+                            float *dist, int *idx, void *stream);
 
 #ifdef __cplusplus
 }

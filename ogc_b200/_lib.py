@@ -22,6 +22,7 @@ SIGNATURES = {
     "ogc_gather_points_grad": [_I, _I, _I, _I, _P, _P, _P, _P],
     "ogc_knn": [_I, _I, _I, _I, _P, _P, _P, _P, _P],
     "ogc_knn_sqrt": [_I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "ogc_knn_bounded": [_I, _I, _I, _I, _F, _P, _P, _P, _P, _P],
     "ogc_three_nn": [_I, _I, _I, _P, _P, _P, _P, _P],
     "ogc_three_interpolate": [_I, _I, _I, _I, _P, _P, _P, _P, _P],
     "ogc_three_interpolate_grad": [_I, _I, _I, _I, _P, _P, _P, _P, _P],
@@ -49,7 +50,7 @@ SIGNATURES = {
     "ogc_sa_mlp_layer_dw_tc": [_I] * 7 + [_P, _P, _I, _I] + [_P] * 11,
     "ogc_mask_match": [_I, _I, _P, _P, _P, _P],
     "ogc_lsap_maximize_host": [_I, _P, _P],
-    "ogc_mask_nuclear_norm": [_I, _I, _I, _P, _P, _P],
+    "ogc_mask_nuclear_norm": [_I, _I, _I, _P, _P, _P, _P],
     "ogc_adam_step_dev": [_LL, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _P, _P],
 }
 

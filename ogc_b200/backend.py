@@ -114,6 +114,20 @@ class B200Backend:
         self.launches += 1
         return d, idx
 
+    def knn_bounded(self, k, unknown, known, max_dist):
+        """k-NN among candidates within max_dist (dist = sqrt, +inf / idx 0 for unfilled slots); see the header."""
+        _chk_f32(unknown, "unknown")
+        _chk_f32(known, "known")
+        B, n, _ = unknown.shape
+        m = known.shape[1]
+        d = torch.empty(B, n, k, dtype=torch.float32, device=unknown.device)
+        idx = torch.empty(B, n, k, dtype=torch.int32, device=unknown.device)
+        with TIMER.span("knn", B * (12 * (n + m) + 8 * n * k)):
+            _lib.check(self.lib.ogc_knn_bounded(B, n, m, k, float(max_dist), _ptr(unknown), _ptr(known), _ptr(d),
+                                                _ptr(idx), _stream()), "ogc_knn_bounded")
+        self.launches += 1
+        return d, idx
+
     def three_nn(self, unknown, known):
         _chk_f32(unknown, "unknown")
         _chk_f32(known, "known")
@@ -302,9 +316,11 @@ class B200Backend:
         _chk_f32(mask, "mask")
         B, N, K = mask.shape
         out = torch.empty(B, dtype=torch.float32, device=mask.device)
+        ws = torch.empty(B * 1024, dtype=torch.float64, device=mask.device)
         with TIMER.span("mask_nuclear_norm", B * N * K * 4):
-            _lib.check(self.lib.ogc_mask_nuclear_norm(B, N, K, _ptr(mask), _ptr(out), _stream()), "ogc_mask_nuclear_norm")
-        self.launches += 1
+            _lib.check(self.lib.ogc_mask_nuclear_norm(B, N, K, _ptr(mask), _ptr(out), _ptr(ws), _stream()),
+                       "ogc_mask_nuclear_norm")
+        self.launches += 2
         return out
 
 

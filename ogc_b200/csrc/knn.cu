@@ -29,12 +29,14 @@ template <int KR>
 struct TopK {
     float d[KR];
     int i[KR];
-    float tau;  // distance of element k-1 (warp-uniform)
+    float tau;   // admission threshold: min(distance of element k-1, tau0) (warp-uniform)
+    float tau0;  // caller's bound on useful squared distances (+inf = exact k-NN)
 
-    __device__ __forceinline__ void init() {
+    __device__ __forceinline__ void init(float bound) {
 #pragma unroll
         for (int r = 0; r < KR; ++r) { d[r] = __int_as_float(0x7f800000); i[r] = 0; }
-        tau = __int_as_float(0x7f800000);
+        tau0 = bound;
+        tau = bound;
     }
 
     // Warp-uniform call: insert (cd, ci); precondition cd < tau.
@@ -64,13 +66,13 @@ struct TopK {
         float t = d[0];
 #pragma unroll
         for (int r = 1; r < KR; ++r) t = (kr == r) ? d[r] : t;
-        tau = __shfl_sync(OGC_FULL_MASK, t, kl);
+        tau = fminf(__shfl_sync(OGC_FULL_MASK, t, kl), tau0);
     }
 };
 
 template <int KR, bool SQRT_OUT>
 __global__ void __launch_bounds__(kKnnThreads)
-knn_warp_kernel(int n, int m, int k, int rounds, const float *__restrict__ unknown,
+knn_warp_kernel(int n, int m, int k, int rounds, float tau0, const float *__restrict__ unknown,
                 const float *__restrict__ known, float *__restrict__ dist_out, int *__restrict__ idx_out) {
     extern __shared__ __align__(16) float knn_smem[];
     __shared__ __align__(8) uint64_t bar;
@@ -103,7 +105,7 @@ knn_warp_kernel(int n, int m, int k, int rounds, const float *__restrict__ unkno
             uz = __ldg(unknown + q * 3 + 2);
         }
         TopK<KR> top;
-        top.init();
+        top.init(tau0);
 
         for (int t = 0; t < ntiles; ++t) {
             const int t0 = t * kKnnTilePoints;
@@ -153,8 +155,8 @@ knn_warp_kernel(int n, int m, int k, int rounds, const float *__restrict__ unkno
 }
 
 template <int KR, bool SQ>
-static cudaError_t launch_knn(int b, int n, int m, int k, const float *unknown, const float *known, float *dist,
-                              int *idx, cudaStream_t st) {
+static cudaError_t launch_knn(int b, int n, int m, int k, float tau0, const float *unknown, const float *known,
+                              float *dist, int *idx, cudaStream_t st) {
     const int tile_pts = m < kKnnTilePoints ? m : kKnnTilePoints;
     const size_t smem = (static_cast<size_t>(tile_pts) * 3 + 4) * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(knn_warp_kernel<KR, SQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -166,12 +168,12 @@ static cudaError_t launch_knn(int b, int n, int m, int k, const float *unknown, 
     rounds = rounds < 1 ? 1 : (rounds > 8 ? 8 : rounds);
     const int qpc = rounds * kKnnWarps;
     dim3 grid((n + qpc - 1) / qpc, b);
-    knn_warp_kernel<KR, SQ><<<grid, kKnnThreads, smem, st>>>(n, m, k, rounds, unknown, known, dist, idx);
+    knn_warp_kernel<KR, SQ><<<grid, kKnnThreads, smem, st>>>(n, m, k, rounds, tau0, unknown, known, dist, idx);
     return cudaGetLastError();
 }
 
 template <bool SQ>
-static int knn_dispatch(int b, int n, int m, int k, const float *unknown, const float *known, float *dist,
+static int knn_dispatch(int b, int n, int m, int k, float tau0, const float *unknown, const float *known, float *dist,
                         int *idx, void *stream) {
     if (b < 0 || n < 0 || m < 0 || k < 1 || k > 224) return OGC_ERR_INVALID_ARG;
     if (b == 0 || n == 0) return OGC_OK;
@@ -179,10 +181,10 @@ static int knn_dispatch(int b, int n, int m, int k, const float *unknown, const 
     if (b > 65535) return OGC_ERR_UNSUPPORTED;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e;
-    if (k <= 32) e = launch_knn<1, SQ>(b, n, m, k, unknown, known, dist, idx, st);
-    else if (k <= 64) e = launch_knn<2, SQ>(b, n, m, k, unknown, known, dist, idx, st);
-    else if (k <= 128) e = launch_knn<4, SQ>(b, n, m, k, unknown, known, dist, idx, st);
-    else e = launch_knn<7, SQ>(b, n, m, k, unknown, known, dist, idx, st);
+    if (k <= 32) e = launch_knn<1, SQ>(b, n, m, k, tau0, unknown, known, dist, idx, st);
+    else if (k <= 64) e = launch_knn<2, SQ>(b, n, m, k, tau0, unknown, known, dist, idx, st);
+    else if (k <= 128) e = launch_knn<4, SQ>(b, n, m, k, tau0, unknown, known, dist, idx, st);
+    else e = launch_knn<7, SQ>(b, n, m, k, tau0, unknown, known, dist, idx, st);
     return e == cudaSuccess ? OGC_OK : static_cast<int>(e);
 }
 
@@ -190,15 +192,30 @@ static int knn_dispatch(int b, int n, int m, int k, const float *unknown, const 
 
 extern "C" int ogc_knn(int b, int n, int m, int k, const float *unknown, const float *known, float *dist2,
                        int *idx, void *stream) {
-    return ogc::knn_dispatch<false>(b, n, m, k, unknown, known, dist2, idx, stream);
+    return ogc::knn_dispatch<false>(b, n, m, k, __builtin_inff(), unknown, known, dist2, idx, stream);
 }
 
 extern "C" int ogc_knn_sqrt(int b, int n, int m, int k, const float *unknown, const float *known, float *dist,
                             int *idx, void *stream) {
-    return ogc::knn_dispatch<true>(b, n, m, k, unknown, known, dist, idx, stream);
+    return ogc::knn_dispatch<true>(b, n, m, k, __builtin_inff(), unknown, known, dist, idx, stream);
 }
 
 extern "C" int ogc_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2,
                             int *idx, void *stream) {
-    return ogc::knn_dispatch<false>(b, n, m, 3, unknown, known, dist2, idx, stream);
+    return ogc::knn_dispatch<false>(b, n, m, 3, __builtin_inff(), unknown, known, dist2, idx, stream);
+}
+
+// k-NN restricted to candidates with distance <= max_dist (sqrt'ed output like ogc_knn_sqrt).  For the call sites
+// that discard farther neighbours anyway -- QueryAndGroup / KnnLoss replace every neighbour with dist > radius by
+// the nearest one (pointnet2/pointnet2.py:284-286, losses/seg_loss_unsup.py:121-122) -- the result AFTER that
+// clipping is identical to the exact k-NN, while far candidates never enter the running top-k (most insertions of
+// the exact search in sparse outdoor clouds).  Slots with no candidate inside the bound hold (+inf, 0).
+// Only valid when every query's nearest neighbour lies inside the bound (queries that are members of `known`).
+extern "C" int ogc_knn_bounded(int b, int n, int m, int k, float max_dist, const float *unknown, const float *known,
+                               float *dist, int *idx, void *stream) {
+    if (!(max_dist >= 0.f)) return OGC_ERR_INVALID_ARG;
+    // admit d2 < tau0 with tau0 just above max_dist^2, so every candidate with sqrtf(d2) <= max_dist is kept
+    const float r2 = max_dist * max_dist;
+    const float tau0 = r2 * 1.00001f + 1e-30f;
+    return ogc::knn_dispatch<true>(b, n, m, k, tau0, unknown, known, dist, idx, stream);
 }

@@ -436,13 +436,53 @@ __global__ void mask_match_kernel(int B, int K, const int *__restrict__ inter, i
 
 // Nuclear norm of the (N,K) soft mask of every sample: sum of singular values = sum sqrt(eig(M^T M)).
 // Replaces RankLoss's `mask.norm(p='nuc', dim=(1,2))` (losses/seg_loss_unsup.py:313: a batched (N,K) SVD through
-// cuSOLVER with a host sync, computed every step for a logged-only number).  Gram matrix accumulated in fp64
-// (warp per (i,j) pair), eigenvalues by cyclic Jacobi on one thread.  One CTA per sample.
+// cuSOLVER with a host sync, computed every step for a logged-only number).
+//   gram_kernel : grid (chunks, B); each thread owns points n = tid, tid+256, ... of its chunk, reads the K-float
+//                 row once and accumulates the K(K+1)/2 products (fp32 per thread, fp64 across threads/CTAs)
+//   nuclear_from_gram_kernel : one thread per sample, cyclic Jacobi eigenvalues in fp64
+constexpr int kGramMaxK = 16;     // register-resident pair accumulators; larger K uses the generic pair loop
+
+template <int K>
 __global__ void __launch_bounds__(256)
-nuclear_norm_kernel(int n, int K, const float *__restrict__ mask, float *__restrict__ out) {
-    __shared__ double G[kMaxSlots][kMaxSlots];
+gram_kernel(int n, const float *__restrict__ mask, double *__restrict__ gram) {
+    constexpr int NP = K * (K + 1) / 2;
+    __shared__ double sg[NP];
+    const int b = blockIdx.y;
+    const float *m = mask + static_cast<size_t>(b) * n * K;
+    for (int i = threadIdx.x; i < NP; i += blockDim.x) sg[i] = 0.0;
+    __syncthreads();
+    float acc[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) acc[i] = 0.f;
+    const int per = (n + gridDim.x - 1) / gridDim.x;
+    const int lo = blockIdx.x * per, hi = min(n, lo + per);
+    for (int p = lo + threadIdx.x; p < hi; p += blockDim.x) {
+        float r[K];
+#pragma unroll
+        for (int c = 0; c < K; ++c) r[c] = __ldg(m + static_cast<size_t>(p) * K + c);
+        int q = 0;
+#pragma unroll
+        for (int i = 0; i < K; ++i)
+#pragma unroll
+            for (int j = i; j < K; ++j) { acc[q] = fmaf(r[i], r[j], acc[q]); ++q; }
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        float v = acc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(OGC_FULL_MASK, v, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&sg[i], static_cast<double>(v));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NP; i += blockDim.x) atomicAdd(gram + static_cast<size_t>(b) * kMaxSlots * kMaxSlots + i, sg[i]);
+}
+
+// generic K (<= 32): warp per (i,j) pair
+__global__ void __launch_bounds__(256)
+gram_pairs_kernel(int n, int K, const float *__restrict__ mask, double *__restrict__ gram) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    const float *m = mask + static_cast<size_t>(blockIdx.x) * n * K;
+    const int b = blockIdx.y;
+    const float *m = mask + static_cast<size_t>(b) * n * K;
     const int npairs = K * (K + 1) / 2;
     for (int pr = warp; pr < npairs; pr += nwarp) {
         int i = 0, rem = pr;
@@ -453,10 +493,22 @@ nuclear_norm_kernel(int n, int K, const float *__restrict__ mask, float *__restr
             acc += static_cast<double>(__ldg(m + static_cast<size_t>(p) * K + i)) * static_cast<double>(__ldg(m + static_cast<size_t>(p) * K + j));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(OGC_FULL_MASK, acc, o);
-        if (lane == 0) { G[i][j] = acc; G[j][i] = acc; }
+        if (lane == 0) gram[static_cast<size_t>(b) * kMaxSlots * kMaxSlots + pr] = acc;
     }
-    __syncthreads();
-    if (threadIdx.x != 0) return;
+}
+
+// gram: per sample, the K(K+1)/2 upper-triangle entries in row-major pair order
+__global__ void nuclear_from_gram_kernel(int B, int K, const double *__restrict__ gram, float *__restrict__ out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double G[kMaxSlots][kMaxSlots];
+    int q = 0;
+    for (int i = 0; i < K; ++i)
+        for (int j = i; j < K; ++j) {
+            const double v = gram[static_cast<size_t>(b) * kMaxSlots * kMaxSlots + q++];
+            G[i][j] = v;
+            G[j][i] = v;
+        }
     for (int sweep = 0; sweep < 60; ++sweep) {
         double off = 0.0, diag = 0.0;
         for (int i = 0; i < K; ++i) {
@@ -465,26 +517,26 @@ nuclear_norm_kernel(int n, int K, const float *__restrict__ mask, float *__restr
         }
         if (off <= 1e-18 * diag || off == 0.0) break;
         for (int p = 0; p < K - 1; ++p)
-            for (int q = p + 1; q < K; ++q) {
-                if (G[p][q] == 0.0) continue;
-                const double theta = (G[q][q] - G[p][p]) / (2.0 * G[p][q]);
+            for (int r2 = p + 1; r2 < K; ++r2) {
+                if (G[p][r2] == 0.0) continue;
+                const double theta = (G[r2][r2] - G[p][p]) / (2.0 * G[p][r2]);
                 const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
                 const double c = 1.0 / sqrt(t * t + 1.0), s_ = t * c;
                 for (int r = 0; r < K; ++r) {
-                    const double gp = G[r][p], gq = G[r][q];
+                    const double gp = G[r][p], gq = G[r][r2];
                     G[r][p] = c * gp - s_ * gq;
-                    G[r][q] = s_ * gp + c * gq;
+                    G[r][r2] = s_ * gp + c * gq;
                 }
                 for (int r = 0; r < K; ++r) {
-                    const double gp = G[p][r], gq = G[q][r];
+                    const double gp = G[p][r], gq = G[r2][r];
                     G[p][r] = c * gp - s_ * gq;
-                    G[q][r] = s_ * gp + c * gq;
+                    G[r2][r] = s_ * gp + c * gq;
                 }
             }
     }
     double sum = 0.0;
     for (int i = 0; i < K; ++i) sum += sqrt(G[i][i] > 0.0 ? G[i][i] : 0.0);
-    out[blockIdx.x] = static_cast<float>(sum);
+    out[b] = static_cast<float>(sum);
 }
 
 }  // namespace ogc
@@ -581,11 +633,25 @@ extern "C" int ogc_lsap_maximize_host(int n, const double *score, int *col4row) 
     return OGC_OK;
 }
 
-extern "C" int ogc_mask_nuclear_norm(int b, int n, int k, const float *mask, float *out, void *stream) {
+extern "C" int ogc_mask_nuclear_norm(int b, int n, int k, const float *mask, float *out, double *gram_ws, void *stream) {
     using namespace ogc;
     if (b < 0 || n <= 0 || k < 1 || k > kMaxSlots) return OGC_ERR_INVALID_ARG;
     if (b == 0) return OGC_OK;
-    if (!mask || !out) return OGC_ERR_INVALID_ARG;
-    nuclear_norm_kernel<<<b, 256, 0, static_cast<cudaStream_t>(stream)>>>(n, k, mask, out);
+    if (!mask || !out || !gram_ws) return OGC_ERR_INVALID_ARG;
+    if (b > 65535) return OGC_ERR_UNSUPPORTED;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(gram_ws, 0, static_cast<size_t>(b) * kMaxSlots * kMaxSlots * sizeof(double), st);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    const int chunks = n >= 4096 ? 8 : 1;
+    dim3 grid(chunks, b);
+    switch (k) {
+#define OGC_GRAM_CASE(KK) case KK: gram_kernel<KK><<<grid, 256, 0, st>>>(n, mask, gram_ws); break;
+        OGC_GRAM_CASE(1) OGC_GRAM_CASE(2) OGC_GRAM_CASE(3) OGC_GRAM_CASE(4) OGC_GRAM_CASE(5) OGC_GRAM_CASE(6)
+        OGC_GRAM_CASE(7) OGC_GRAM_CASE(8) OGC_GRAM_CASE(9) OGC_GRAM_CASE(10) OGC_GRAM_CASE(11) OGC_GRAM_CASE(12)
+        OGC_GRAM_CASE(13) OGC_GRAM_CASE(14) OGC_GRAM_CASE(15) OGC_GRAM_CASE(16)
+#undef OGC_GRAM_CASE
+        default: gram_pairs_kernel<<<dim3(1, b), 256, 0, st>>>(n, k, mask, gram_ws); break;
+    }
+    nuclear_from_gram_kernel<<<(b + 31) / 32, 32, 0, st>>>(b, k, gram_ws, out);
     OGC_RETURN_LAUNCH_STATUS();
 }

@@ -130,7 +130,8 @@ class _NeighborL1Fn(Function):
         total = None
         for kind, k, radius, coef in specs:
             if kind == "knn":
-                dist, idx = be.knn(k, pc, pc, sqrt=True)
+                # neighbours beyond `radius` are replaced by the nearest one anyway (:121-122): bound the search
+                dist, idx = (be.knn_bounded(k, pc, pc, radius) if radius is not None else be.knn(k, pc, pc, sqrt=True))
                 loss_pt = be.neighbor_l1(mask, idx, dist if radius is not None else None, radius, coef, grad)
             else:
                 idx = be.ball_query(radius, k, pc, pc)

@@ -138,7 +138,13 @@ class SetAbstraction(nn.Module):
         knn_cache = {}
         for radius, nsample, mlp in zip(self.radii, self.nsamples, self.mlps):
             if nsample not in knn_cache or REFERENCE_FAITHFUL:   # identical k-NN for every scale with the same k
-                knn_cache[nsample] = ops.knn(nsample, new_xyz, xyz)
+                same_k = [r for r, ns in zip(self.radii, self.nsamples) if ns == nsample]
+                if fused and all(r is not None for r in same_k):
+                    # every scale replaces neighbours beyond its radius by the nearest one: nothing farther than the
+                    # largest radius can survive, so the search is bounded (centres are members of xyz)
+                    knn_cache[nsample] = _backend_mod.get_backend().knn_bounded(nsample, new_xyz, xyz, max(same_k))
+                else:
+                    knn_cache[nsample] = ops.knn(nsample, new_xyz, xyz)
             dist, idx = knn_cache[nsample]
             idx = ops.clip_neighbours_by_radius(dist, idx, radius)
             if fused:

@@ -213,3 +213,16 @@ def test_operator_layer_autograd_on_gpu(oracle):
     assert torch.equal(got[1], ref[1])
     torch.testing.assert_close(got[2], ref[2], rtol=1e-6, atol=1e-6)
     torch.testing.assert_close(got[4], ref[4], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("n,k,r,kind", [(2048, 32, 1.0, "scene"), (4096, 64, 2.0, "scene"), (1500, 16, 0.3, "normal"), (700, 8, 1e-3, "int")])
+def test_knn_bounded_equals_exact_knn_after_radius_clip(b200, n, k, r, kind):
+    """ogc_knn_bounded: identical to the exact k-NN once neighbours beyond the radius are replaced by the nearest
+    one (what QueryAndGroup / KnnLoss do with the result)."""
+    import pointnet2.pointnet2 as ops
+    pc = clouds(n + k, 2, n, kind).cuda()
+    dist, idx = b200.knn(k, pc, pc, sqrt=True)
+    bd, bidx = b200.knn_bounded(k, pc, pc, r)
+    assert torch.equal(ops.clip_neighbours_by_radius(dist, idx, r), ops.clip_neighbours_by_radius(bd, bidx, r))
+    inside = dist <= r
+    assert torch.equal(bd[inside], dist[inside]) and (torch.isinf(bd) | (bd == dist))[~inside].all()
