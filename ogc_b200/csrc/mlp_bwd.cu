@@ -333,6 +333,82 @@ mlp_dw_kernel(MlpDwParams q) {
     }
 }
 
+// dW of a gathered layer with a narrow input (SA level 1: 3 centred + 3 raw coordinates, C_in = 6).  The generic
+// split-K kernel wastes its 16x16 thread grid on a 32x6 output; here a warp owns CPW output channels, its lanes
+// stream the positions with coalesced 16-byte loads of dz / y, the gathered input tile sits in shared memory and
+// the CPW x CIN partial sums stay in registers across all tiles of the CTA (one reduction at the very end).
+template <int CIN, int CPW>
+__global__ void __launch_bounds__(256)
+mlp_dw_small_kernel(MlpDwParams q) {
+    constexpr int TP = 256;                       // positions per tile: 64 quads, two per lane
+    __shared__ __align__(16) float a0[CIN][TP];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int P = q.dy.P, Cout = q.dy.C;
+    const int tiles_per_sample = (P + TP - 1) / TP;
+    const int total = q.B * tiles_per_sample;
+    float acc[CPW][CIN];
+#pragma unroll
+    for (int i = 0; i < CPW; ++i)
+#pragma unroll
+        for (int j = 0; j < CIN; ++j) acc[i][j] = 0.f;
+
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int b = w / tiles_per_sample, p_base = (w - b * tiles_per_sample) * TP;
+        __syncthreads();
+        {
+            const int gp = p_base + tid;
+            float v[CIN];
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) v[c] = 0.f;
+            if (gp < P) {
+                const int j = __ldg(q.idx + static_cast<size_t>(b) * P + gp);
+                const int m = gp / q.dy.S;
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    v[c] = __ldg(q.xyz + (static_cast<size_t>(b) * q.N + j) * 3 + c) - __ldg(q.new_xyz + (static_cast<size_t>(b) * q.dy.M + m) * 3 + c);
+#pragma unroll
+                for (int c = 3; c < CIN; ++c) v[c] = __ldg(q.feat_pm + (static_cast<size_t>(b) * q.N + j) * q.Cf + c - 3);
+            }
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) a0[c][tid] = v[c];
+        }
+        __syncthreads();
+        DyRaw raw[CPW][2];
+#pragma unroll
+        for (int i = 0; i < CPW; ++i)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int co = warp * CPW + i;
+                if (co < Cout) dy_quad_load(q.dy, b, co, p_base + (lane + 32 * h) * 4, raw[i][h]);
+            }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float4 av[CIN];
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) av[c] = *reinterpret_cast<const float4 *>(&a0[c][(lane + 32 * h) * 4]);
+#pragma unroll
+            for (int i = 0; i < CPW; ++i) {
+                const int co = warp * CPW + i;
+                if (co >= Cout) continue;
+                const float4 d = dy_quad_finish(q.dy, p_base + (lane + 32 * h) * 4, raw[i][h]);
+#pragma unroll
+                for (int c = 0; c < CIN; ++c)
+                    acc[i][c] = fmaf(d.x, av[c].x, fmaf(d.y, av[c].y, fmaf(d.z, av[c].z, fmaf(d.w, av[c].w, acc[i][c]))));
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < CPW; ++i)
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) {
+            float v = acc[i][c];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(OGC_FULL_MASK, v, o);
+            const int co = warp * CPW + i;
+            if (lane == 0 && co < Cout) atomicAdd(q.dW + static_cast<size_t>(co) * CIN + c, v);
+        }
+}
+
 template <int R_T, int P_T>
 static cudaError_t launch_dx(const MlpDxParams &q, int B, bool scatter, cudaStream_t st) {
     constexpr int KC = 64;
@@ -456,6 +532,13 @@ extern "C" int ogc_sa_mlp_layer_dw(int b, int n, int m, int nsample, int cout, i
     q.feat_pm = feat_pm; q.idx = idx; q.N = n; q.Cf = cin - 3; q.dW = dw;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e;
+    if (gather && cin == 6 && (cout == 32 || cout == 64) && (nsample % 4) == 0) {
+        const int total = b * ((m * nsample + 255) / 256);
+        const int gx = total < kNumSMs * 4 ? total : kNumSMs * 4;
+        if (cout == 32) mlp_dw_small_kernel<6, 4><<<gx, 256, 0, st>>>(q);
+        else mlp_dw_small_kernel<6, 8><<<gx, 256, 0, st>>>(q);
+        OGC_RETURN_LAUNCH_STATUS();
+    }
     if (cout <= 32) e = dispatch_dw_nc<2>(q, gather, st);
     else if (cout <= 64) e = dispatch_dw_nc<4>(q, gather, st);
     else e = dispatch_dw_nc<8>(q, gather, st);

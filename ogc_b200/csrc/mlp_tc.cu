@@ -24,7 +24,10 @@
 
 namespace ogc {
 
-constexpr int kTcThreads = 288;
+constexpr int kTcLoaderWarps = 8;
+constexpr int kTcLoaders = kTcLoaderWarps * 32;
+constexpr int kTcMmaWarp = 4 + kTcLoaderWarps;
+constexpr int kTcThreads = (kTcMmaWarp + 1) * 32;
 constexpr int kTcNT = 64;          // positions per tile == nsample
 constexpr int kTcM = 128;          // output channels per CTA (one M block)
 
@@ -54,9 +57,9 @@ mlp_fwd_tc_kernel(MlpTcParams q) {
     const uint32_t w_bytes = static_cast<uint32_t>(KB) * kTcM * 128u, a_bytes = static_cast<uint32_t>(KB) * kTcNT * 128u;
     uint8_t *w_hi = smem, *w_lo = w_hi + w_bytes, *a_hi = w_lo + w_bytes, *a_lo = a_hi + a_bytes;
 
-    if (warp == 8) tc::tmem_alloc(&tmem_base_s, 128);
+    if (warp == kTcMmaWarp) tc::tmem_alloc(&tmem_base_s, 128);
     if (tid == 0) {
-        mbar_init(&bar_full, 128);
+        mbar_init(&bar_full, kTcLoaders);
         mbar_init(&bar_empty, 1);
         mbar_init(&bar_tfull[0], 1); mbar_init(&bar_tfull[1], 1);
         mbar_init(&bar_tempty[0], 128); mbar_init(&bar_tempty[1], 128);
@@ -79,9 +82,9 @@ mlp_fwd_tc_kernel(MlpTcParams q) {
     tc::fence_after_sync();
     const uint32_t tmem_base = tmem_base_s;
 
-    if (warp >= 4 && warp < 8) {
+    if (warp >= 4 && warp < kTcMmaWarp) {
         // ================================ loader ================================
-        const int lt = tid - 128;           // 0..127
+        const int lt = tid - 128;           // 0..kTcLoaders-1
         const int lw = warp - 4;
         int use = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++use) {
@@ -96,11 +99,11 @@ mlp_fwd_tc_kernel(MlpTcParams q) {
                 // one warp per (position, column block): 32 lanes = 32 consecutive feature channels of one point
                 // row (coalesced 128 B); 8 independent row reads in flight per lane before any is consumed
                 const int nitems = kTcNT * KB;
-                for (int it0 = lw; it0 < nitems; it0 += 4 * 8) {
+                for (int it0 = lw; it0 < nitems; it0 += kTcLoaderWarps * 8) {
                     float vals[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
-                        const int it = it0 + 4 * u;
+                        const int it = it0 + kTcLoaderWarps * u;
                         const int p = it / KB, kb = it - p * KB;
                         const int j = __shfl_sync(OGC_FULL_MASK, p < 32 ? j_lo : j_hi, p & 31);
                         const int c = kb * 32 + lane;
@@ -108,7 +111,7 @@ mlp_fwd_tc_kernel(MlpTcParams q) {
                     }
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
-                        const int it = it0 + 4 * u;
+                        const int it = it0 + kTcLoaderWarps * u;
                         if (it < nitems) {
                             const int p = it / KB, kb = it - p * KB;
                             const float hi = tc::tf32_hi(vals[u]);
@@ -131,12 +134,12 @@ mlp_fwd_tc_kernel(MlpTcParams q) {
                 // 32 channels of one block for one quad -> conflict-free swizzled row writes.  8 independent 16 B
                 // loads in flight per thread before any is consumed (the loader is latency-, not issue-bound).
                 const int nitems = KB * 16 * 32;
-                for (int it0 = lt; it0 < nitems; it0 += 128 * 8) {
+                for (int it0 = lt; it0 < nitems; it0 += kTcLoaders * 8) {
                     float4 raw[8];
                     float scv[8], shv[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
-                        const int it = it0 + 128 * u;
+                        const int it = it0 + kTcLoaders * u;
                         const int cl = it & 31, pq = (it >> 5) & 15, kb = it >> 9;
                         const int c = kb * 32 + cl;
                         raw[u] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -149,7 +152,7 @@ mlp_fwd_tc_kernel(MlpTcParams q) {
                     }
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
-                        const int it = it0 + 128 * u;
+                        const int it = it0 + kTcLoaders * u;
                         if (it >= nitems) continue;
                         const int cl = it & 31, pq = (it >> 5) & 15, kb = it >> 9;
                         const float vv[4] = {fmaxf(fmaf(scv[u], raw[u].x, shv[u]), 0.f), fmaxf(fmaf(scv[u], raw[u].y, shv[u]), 0.f),
@@ -167,7 +170,7 @@ mlp_fwd_tc_kernel(MlpTcParams q) {
             tc::fence_proxy_async();
             mbar_arrive(&bar_full);
         }
-    } else if (warp == 8) {
+    } else if (warp == kTcMmaWarp) {
         // ================================ MMA issuer ================================
         if (lane == 0) {
             const uint32_t idesc = tc::make_idesc_tf32(kTcM, kTcNT, 0, 0);
@@ -264,7 +267,7 @@ mlp_fwd_tc_kernel(MlpTcParams q) {
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 8) tc::tmem_dealloc(tmem_base, 128);
+    if (warp == kTcMmaWarp) tc::tmem_dealloc(tmem_base, 128);
 }
 
 }  // namespace ogc

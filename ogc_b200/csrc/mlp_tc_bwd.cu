@@ -16,7 +16,10 @@
 
 namespace ogc {
 
-constexpr int kTbThreads = 288;
+constexpr int kTbLoaderWarps = 8;
+constexpr int kTbLoaders = kTbLoaderWarps * 32;
+constexpr int kTbMmaWarp = 4 + kTbLoaderWarps;
+constexpr int kTbThreads = (kTbMmaWarp + 1) * 32;
 constexpr int kTbNT = 64;     // positions per tile
 constexpr int kTbM = 128;
 
@@ -54,9 +57,9 @@ mlp_dx_tc_kernel(MlpDxTcParams q) {
     const uint32_t w_bytes = static_cast<uint32_t>(KB) * kTbM * 128u, a_bytes = static_cast<uint32_t>(KB) * kTbNT * 128u;
     uint8_t *w_hi = smem, *w_lo = w_hi + w_bytes, *a_hi = w_lo + w_bytes, *a_lo = a_hi + a_bytes;
 
-    if (warp == 8) tc::tmem_alloc(&tmem_base_s, 128);
+    if (warp == kTbMmaWarp) tc::tmem_alloc(&tmem_base_s, 128);
     if (tid == 0) {
-        mbar_init(&bar_full, 128);
+        mbar_init(&bar_full, kTbLoaders);
         mbar_init(&bar_empty, 1);
         mbar_init(&bar_tfull[0], 1); mbar_init(&bar_tfull[1], 1);
         mbar_init(&bar_tempty[0], 128); mbar_init(&bar_tempty[1], 128);
@@ -78,7 +81,7 @@ mlp_dx_tc_kernel(MlpDxTcParams q) {
     tc::fence_after_sync();
     const uint32_t tmem_base = tmem_base_s;
 
-    if (warp >= 4 && warp < 8) {
+    if (warp >= 4 && warp < kTbMmaWarp) {
         // ================================ loader: dY tile, rows = positions, K = channels ================
         const int lt = tid - 128;
         int use = 0;
@@ -86,18 +89,18 @@ mlp_dx_tc_kernel(MlpDxTcParams q) {
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++use) {
             const int p0 = t * kTbNT;
             mbar_wait(&bar_empty, (use & 1) ^ 1);
-            for (int it0 = lt; it0 < nitems; it0 += 128 * 4) {
+            for (int it0 = lt; it0 < nitems; it0 += kTbLoaders * 4) {
                 DyRaw raw[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int it = it0 + 128 * u;
+                    const int it = it0 + kTbLoaders * u;
                     const int cl = it & 31, pq = (it >> 5) & 15, kb = it >> 9;
                     const int c = kb * 32 + cl;
                     if (it < nitems && c < q.kn) dy_quad_load(q.dy, b, q.k0 + c, p0 + pq * 4, raw[u]);
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int it = it0 + 128 * u;
+                    const int it = it0 + kTbLoaders * u;
                     if (it >= nitems) continue;
                     const int cl = it & 31, pq = (it >> 5) & 15, kb = it >> 9;
                     const int c = kb * 32 + cl;
@@ -116,7 +119,7 @@ mlp_dx_tc_kernel(MlpDxTcParams q) {
             tc::fence_proxy_async();
             mbar_arrive(&bar_full);
         }
-    } else if (warp == 8) {
+    } else if (warp == kTbMmaWarp) {
         if (lane == 0) {
             const uint32_t idesc = tc::make_idesc_tf32(kTbM, kTbNT, 0, 0);
             int use = 0;
@@ -227,7 +230,7 @@ mlp_dx_tc_kernel(MlpDxTcParams q) {
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 8) tc::tmem_dealloc(tmem_base, 128);
+    if (warp == kTbMmaWarp) tc::tmem_dealloc(tmem_base, 128);
 }
 
 // ------------------------------------------------------------------------------------------------ dW
@@ -271,9 +274,9 @@ mlp_dw_tc_kernel(MlpDwTcParams q) {
     auto a_hi = [&](int s) { return smem + s * stage_bytes + 2 * dy_bytes; };
     auto a_lo = [&](int s) { return smem + s * stage_bytes + 2 * dy_bytes + ((a_bytes + 1023u) & ~1023u); };
 
-    if (warp == 8) tc::tmem_alloc(&tmem_base_s, 256);
+    if (warp == kTbMmaWarp) tc::tmem_alloc(&tmem_base_s, 256);
     if (tid == 0) {
-        for (int s = 0; s < kDwStages; ++s) { mbar_init(&bar_full[s], 128); mbar_init(&bar_empty[s], 1); }
+        for (int s = 0; s < kDwStages; ++s) { mbar_init(&bar_full[s], kTbLoaders); mbar_init(&bar_empty[s], 1); }
         mbar_init(&bar_done, 1);
         mbar_fence_init();
     }
@@ -282,7 +285,7 @@ mlp_dw_tc_kernel(MlpDwTcParams q) {
     tc::fence_after_sync();
     const uint32_t tmem_base = tmem_base_s;
 
-    if (warp >= 4 && warp < 8) {
+    if (warp >= 4 && warp < kTbMmaWarp) {
         const int lt = tid - 128, lw = warp - 4;
         int use = 0;
         for (int w = blockIdx.x; w < total; w += gridDim.x, ++use) {
@@ -292,17 +295,18 @@ mlp_dw_tc_kernel(MlpDwTcParams q) {
             uint8_t *dh = dy_hi(st), *dl = dy_lo(st), *ah = a_hi(st), *al = a_lo(st);
             // ---- dY tile: row = output channel of this M block, 8 quads of 4 positions per row ----
             {
-                DyRaw raw[8];
+                constexpr int DU = 1024 / kTbLoaders;        // 1024 items = 128 rows x 8 quads
+                DyRaw raw[DU];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int it = lt + 128 * u;           // 1024 items = 128 rows x 8 quads
+                for (int u = 0; u < DU; ++u) {
+                    const int it = lt + kTbLoaders * u;
                     const int row = it >> 3, pq = it & 7;
                     const int co = mb * kTbM + row;
                     if (co < Cout) dy_quad_load(q.dy, b, co, p0 + pq * 4, raw[u]);
                 }
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int it = lt + 128 * u;
+                for (int u = 0; u < DU; ++u) {
+                    const int it = lt + kTbLoaders * u;
                     const int row = it >> 3, pq = it & 7;
                     const int co = mb * kTbM + row;
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -321,11 +325,11 @@ mlp_dw_tc_kernel(MlpDwTcParams q) {
                 const int jl = __ldg(q.idx + static_cast<size_t>(b) * P + p0 + lane);
                 const int nblk = (nrows_a + 31) / 32;
                 const int nitems = kDwTile * nblk;
-                for (int it0 = lw; it0 < nitems; it0 += 4 * 8) {
+                for (int it0 = lw; it0 < nitems; it0 += kTbLoaderWarps * 8) {
                     float vals[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
-                        const int it = it0 + 4 * u;
+                        const int it = it0 + kTbLoaderWarps * u;
                         const int p = it / nblk, cb = it - p * nblk;
                         const int j = __shfl_sync(OGC_FULL_MASK, jl, p & 31);
                         const int c = cb * 32 + lane;
@@ -340,7 +344,7 @@ mlp_dw_tc_kernel(MlpDwTcParams q) {
                     }
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
-                        const int it = it0 + 4 * u;
+                        const int it = it0 + kTbLoaderWarps * u;
                         const int p = it / nblk, cb = it - p * nblk;
                         const int c = cb * 32 + lane;
                         if (it < nitems && c < a_rows_alloc) {
@@ -353,12 +357,12 @@ mlp_dw_tc_kernel(MlpDwTcParams q) {
                 }
             } else {
                 const int nitems = a_rows_alloc * 8;
-                for (int it0 = lt; it0 < nitems; it0 += 128 * 8) {
+                for (int it0 = lt; it0 < nitems; it0 += kTbLoaders * 8) {
                     float4 raw[8];
                     float scv[8], shv[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
-                        const int it = it0 + 128 * u;
+                        const int it = it0 + kTbLoaders * u;
                         const int row = it >> 3, pq = it & 7;
                         raw[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                         scv[u] = shv[u] = 0.f;
@@ -370,7 +374,7 @@ mlp_dw_tc_kernel(MlpDwTcParams q) {
                     }
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
-                        const int it = it0 + 128 * u;
+                        const int it = it0 + kTbLoaders * u;
                         if (it >= nitems) continue;
                         const int row = it >> 3, pq = it & 7;
                         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -389,7 +393,7 @@ mlp_dw_tc_kernel(MlpDwTcParams q) {
             tc::fence_proxy_async();
             mbar_arrive(&bar_full[st]);
         }
-    } else if (warp == 8) {
+    } else if (warp == kTbMmaWarp) {
         if (lane == 0) {
             const uint32_t idesc = tc::make_idesc_tf32(kTbM, n_mma, 0, 0);
             int use = 0;
@@ -433,7 +437,7 @@ mlp_dw_tc_kernel(MlpDwTcParams q) {
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 8) tc::tmem_dealloc(tmem_base, 256);
+    if (warp == kTbMmaWarp) tc::tmem_dealloc(tmem_base, 256);
 }
 
 }  // namespace ogc

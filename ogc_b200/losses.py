@@ -358,8 +358,14 @@ class UnsupervisedOGCLoss(nn.Module):
             terms.append(w(self.w_invariance, self.start_step_invariance) * l_inv)
             logged["invariance"] = l_inv
         with torch.no_grad():
-            logged["entropy"] = scale * sum(self.entropy_loss(m) for m in masks)
-            logged["rank"] = scale * sum(self.rank_loss(m) for m in masks)
+            if _use_fused(*masks) and len({m.shape for m in masks}) == 1:
+                # logged-only terms: one launch over all views (sum of per-view means = n_view * mean over all)
+                allm = torch.cat([m.detach() for m in masks], dim=0)
+                logged["entropy"] = scale * n_view * self.entropy_loss(allm)
+                logged["rank"] = scale * n_view * self.rank_loss(allm)
+            else:
+                logged["entropy"] = scale * sum(self.entropy_loss(m) for m in masks)
+                logged["rank"] = scale * sum(self.rank_loss(m) for m in masks)
         loss = sum(terms)
         logged["sum"] = loss
         # one device->host transfer for every logged scalar (the reference calls .item() six times)
