@@ -306,6 +306,14 @@ OGC_API int ogc_sa_mlp_layer_dw_tc(int b, int n, int m, int nsample, int cout, i
 OGC_API int ogc_knn_bounded(int b, int n, int m, int k, float max_dist, const float *unknown, const float *known,
                             float *dist, int *idx, void *stream);
 
+/* One correspondence step of object_aware_icp (oa_icp.py:64-75), without any N x N tensor:
+ *   flow_out[m] = sum_n softmax_n(-|pc1[m]+flow[m] - pc2[n]| / temperature) c[m,n] pc2[n]
+ *                 / max(sum_n softmax_n(.) c[m,n], 1e-10)  -  pc1[m],      c = mask1 mask2^T (oa_icp.py:57)
+ * pc1, flow (b,n1,3); pc2 (b,n2,3); mask1 (b,n1,k); mask2 (b,n2,k) already permuted to mask1's slot order; k <= 16. */
+OGC_API int ogc_icp_correspond(int b, int n1, int n2, int k, float temperature, const float *pc1, const float *flow,
+                               const float *pc2, const float *mask1, const float *mask2, float *flow_out,
+                               void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -301,6 +301,18 @@ class B200Backend:
         self.launches += 1
         return loss_pt, g1, g2
 
+    def icp_correspond(self, pc1, flow, pc2, mask1, mask2, temperature):
+        for t, nme in ((pc1, "pc1"), (flow, "flow"), (pc2, "pc2"), (mask1, "mask1"), (mask2, "mask2")):
+            _chk_f32(t, nme)
+        B, N1, K = mask1.shape
+        N2 = pc2.shape[1]
+        out = torch.empty(B, N1, 3, dtype=torch.float32, device=pc1.device)
+        with TIMER.span("icp_correspond", B * (N1 * (36 + 4 * K) + N2 * (12 + 4 * K))):
+            _lib.check(self.lib.ogc_icp_correspond(B, N1, N2, K, float(temperature), _ptr(pc1), _ptr(flow), _ptr(pc2),
+                                                   _ptr(mask1), _ptr(mask2), _ptr(out), _stream()), "ogc_icp_correspond")
+        self.launches += 1
+        return out
+
     def mask_match(self, inter):
         """inter (B,K,K) int32 -> (perm12, perm21) (B,K) int32, Hungarian on the device (no host sync)."""
         _chk_i32(inter, "inter")

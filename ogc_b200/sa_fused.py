@@ -28,11 +28,12 @@ TC_DW_ALL = False   # tests: route every supported dW through the tensor-core ke
 
 
 def _tc_dw_ok(S, cin, cout):
-    # measured (scratch/mlp_bench.py): the tensor-core dW only beats the SIMT split-K kernel for the square 128x128
-    # layer; elsewhere its loader (two dependent load batches per 32-position tile) is the bottleneck
+    # measured (scratch/mlp_bench.py, 8 loader warps): the tensor-core dW beats the SIMT split-K kernel for the
+    # wide-input layers (128 -> 128: 0.38 vs 0.79 ms, 128 -> 256: 1.21 vs 1.61, 131 -> 128: 0.84 vs 1.00); for
+    # narrower inputs its per-tile loader latency dominates and the SIMT kernel stays the default
     if TC_DW_ALL:
         return USE_TC and S == 64 and 32 <= cin <= 160 and 32 <= cout <= 256
-    return USE_TC and S == 64 and cin == 128 and cout == 128
+    return USE_TC and S == 64 and 128 <= cin <= 160 and 32 <= cout <= 256
 
 
 def _tc_dx_ok(S, cout, rows, scatter):

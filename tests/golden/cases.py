@@ -37,6 +37,19 @@ CASES = {
 }
 
 
+FLOW_LOSS = {   # config/flow/ogcdr/ogcdr_unsup.yaml:37-52 with 3 unrolled iterations
+    "weights": [0.75, 0.25], "iters_w": [0.5, 0.3, 0.3],
+    "chamfer_loss_params": {"loss_norm": 2},
+    "smooth_loss_params": {"w_knn": 3.0, "w_ball_q": 1.0,
+                           "knn_loss_params": {"k": 4, "radius": 0.05, "loss_norm": 1},
+                           "ball_q_loss_params": {"k": 8, "radius": 0.1, "loss_norm": 1}},
+}
+CASES["flownet_ogcdr_512"] = {"kind": "flownet", "npoint": 512, "B": 2, "seed": 15, "iters": 3, "loss_cfg": FLOW_LOSS,
+                              "grad_params": ["encoder_loc.sa1.mlp_convs.0.weight", "gru.convq.mlp_convs.0.weight",
+                                              "flow_regressor.fc.weight", "global_corr_layer.epsilon"]}
+CASES["oa_icp"] = {"kind": "oa_icp", "B": 2, "N": 768, "K": 6, "seed": 14, "scale": 8.0, "icp_iter": 4}
+
+
 def make_inputs(case):
     rng = np.random.default_rng(case["seed"])
     f32 = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float32))
@@ -44,6 +57,38 @@ def make_inputs(case):
         pc = f32(rng.uniform(-1, 1, size=(case["B"], case["n_point"], 3)) * case["scale"])
         probe = f32(rng.normal(size=(case["B"], case["n_point"], case["n_slot"])))
         return {"pc": pc, "probe": probe}
+    if case["kind"] == "flownet":
+        B, N = case["B"], case["npoint"]
+        pc1 = rng.uniform(-0.5, 0.5, size=(B, N, 3))
+        ang = 0.05
+        Rz = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]])
+        pc2 = np.stack([(pc1[b] @ Rz.T + np.array([0.03, -0.02, 0.01]))[rng.permutation(N)] for b in range(B)])
+        pc2 = pc2 + rng.normal(size=pc2.shape) * 0.002
+        return {"pc1": f32(pc1), "pc2": f32(pc2)}
+    if case["kind"] == "oa_icp":
+        B, N, K = case["B"], case["N"], case["K"]
+        pc1 = rng.uniform(-1, 1, size=(B, N, 3)) * case["scale"]
+        seg = np.clip(((pc1[..., 0] / case["scale"] + 1) / 2 * K).astype(int), 0, K - 1)
+        true_flow = np.zeros_like(pc1)
+        for k in range(K):
+            ang = rng.uniform(-0.08, 0.08)
+            Rz = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]])
+            t = rng.uniform(-0.3, 0.3, size=3)
+            sel = seg == k
+            true_flow[sel] = pc1[sel] @ Rz.T + t - pc1[sel]
+        pc2 = np.stack([(pc1[b] + true_flow[b])[rng.permutation(N)] for b in range(B)])
+        pc2 = pc2 + rng.normal(size=pc2.shape) * 0.01
+        flow0 = true_flow + rng.normal(size=pc1.shape) * 0.15
+        def soft(segm, noise):
+            lg = rng.normal(size=(B, N, K)) * noise
+            lg[np.arange(B)[:, None], np.arange(N)[None, :], segm] += 3.0
+            e = np.exp(lg - lg.max(-1, keepdims=True))
+            return e / e.sum(-1, keepdims=True)
+        d = ((pc2[:, :, None, :] - (pc1 + true_flow)[:, None, :, :]) ** 2).sum(-1)
+        seg2 = np.take_along_axis(seg, d.argmin(-1), 1)
+        perm_slots = rng.permutation(K)
+        mask2 = soft(seg2, 0.5)[..., perm_slots]          # frame 2 uses another slot order
+        return {"pc1": f32(pc1), "pc2": f32(pc2), "flow": f32(flow0), "mask1": f32(soft(seg, 0.5)), "mask2": f32(mask2)}
     V = 4 if case["aug"] else 2
     B, N, K = case["B"], case["N"], case["K"]
     pcs, flows, logits = [], [], []
@@ -76,6 +121,21 @@ def build_my_segnet(case):
             if n.endswith("gn.weight") or (("norm" in n) and n.endswith("weight")):
                 p.add_(0.2 * torch.randn(p.shape, generator=g))
             elif n.endswith("gn.bias") or (("norm" in n) and n.endswith("bias")):
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+    net.train()
+    return net
+
+
+def build_my_flownet(case):
+    from ogc_b200.flownet import FlowStep3D
+    torch.manual_seed(10)
+    net = FlowStep3D(npoint=case["npoint"], loc_flow_nn=8, loc_flow_rad=0.05)
+    g = torch.Generator().manual_seed(case["seed"])
+    with torch.no_grad():
+        for n, p in net.named_parameters():
+            if "mlp_bns" in n and n.endswith("weight"):
+                p.add_(0.2 * torch.randn(p.shape, generator=g))
+            elif "mlp_bns" in n and n.endswith("bias"):
                 p.add_(0.1 * torch.randn(p.shape, generator=g))
     net.train()
     return net

@@ -71,6 +71,52 @@ def main():
                 (inp["pcs"][0] + inp["flows"][0]).unsqueeze(1).repeat(1, case["K"], 1, 1).reshape(-1, case["N"], 3),
                 masks[0].detach().transpose(1, 2).reshape(-1, case["N"]))
             out["kabsch_R"], out["kabsch_t"] = R.numpy(), t.numpy()
+        elif case["kind"] == "flownet":
+            from tests.golden.cases import build_my_flownet
+            from losses import flow_loss_unsup as ref_floss
+            mine = build_my_flownet(case)
+            ref_mod = importlib.import_module("models.flownet_ogcdr")
+            ref = ref_mod.FlowStep3D(npoint=case["npoint"], use_instance_norm=False, loc_flow_nn=8, loc_flow_rad=0.05)
+            ref.load_state_dict(mine.state_dict())
+            ref.train()
+            preds = ref(inp["pc1"], inp["pc2"], inp["pc1"], inp["pc2"], iters=case["iters"])
+            cfg = case["loss_cfg"]
+            crit = ref_floss.UnsupervisedFlowStep3DLoss(ref_floss.ChamferLoss(**cfg["chamfer_loss_params"]),
+                                                        ref_floss.SmoothLoss(**cfg["smooth_loss_params"]),
+                                                        weights=cfg["weights"], iters_w=cfg["iters_w"])
+            loss, d = crit(inp["pc1"], inp["pc2"], preds)
+            loss.backward()
+            for i, pr in enumerate(preds):
+                out["flow%d" % i] = pr.detach().numpy()
+            out["loss"] = np.float32(loss.item())
+            for k, v in d.items():
+                out["dict:" + k] = np.float32(v)
+            for pname in case["grad_params"]:
+                out["grad:" + pname] = dict(ref.named_parameters())[pname].grad.numpy()
+        elif case["kind"] == "oa_icp":
+            # The reference's own oa_icp.object_aware_icp evaluated in FLOAT64 (its fp32 cdist is ill-conditioned:
+            # SURVEY.md 7, hard part 8).  tensorboardX / metrics imports are stubbed; the k-NN index lookup inside
+            # interpolate_mask_by_flow runs in fp32 (the operator layer is fp32-only), everything else in fp64.
+            import types
+            sys.modules.setdefault("tensorboardX", types.SimpleNamespace(SummaryWriter=object))
+            import oa_icp as ref_icp
+            orig_knn, orig_group = ref_loss.knn, ref_loss.grouping_operation
+            ref_loss.knn = lambda k, a, b: tuple(t.double() if t.is_floating_point() else t for t in orig_knn(k, a.float().contiguous(), b.float().contiguous()))
+            ref_loss.grouping_operation = lambda f, i: orig_group(f.float().contiguous(), i).double()
+            orig_match = ref_icp.match_mask_by_iou
+            ref_icp.match_mask_by_iou = lambda a, b: orig_match(a, b).double()
+            torch.set_default_dtype(torch.float64)      # fit_motion_svd_batch builds its identity / zeros with the default dtype
+            try:
+                d = {k: v.double() for k, v in inp.items()}
+                out["flow64"] = ref_icp.object_aware_icp(d["pc1"], d["pc2"], d["flow"], d["mask1"], d["mask2"],
+                                                         icp_iter=case["icp_iter"]).numpy()
+                out["kabsch_flow64"] = ref_icp.weighted_kabsch(d["pc1"], d["flow"], d["mask1"]).numpy()
+            finally:
+                torch.set_default_dtype(torch.float32)
+                ref_icp.match_mask_by_iou = orig_match
+                ref_loss.knn, ref_loss.grouping_operation = orig_knn, orig_group
+            out["flow32"] = ref_icp.object_aware_icp(inp["pc1"], inp["pc2"], inp["flow"], inp["mask1"], inp["mask2"],
+                                                     icp_iter=case["icp_iter"]).numpy()
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
         print(name, {k: getattr(v, "shape", v) for k, v in out.items()})
 

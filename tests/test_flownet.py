@@ -1,0 +1,57 @@
+"""FlowStep3D + unsupervised flow loss (BASELINE.json configs[2]; reference models/flownet_ogcdr.py:146-233,
+losses/flow_loss_unsup.py:7-140).  Golden = the unmodified reference network and loss on CPU with OUR state_dict
+loaded (tests/golden/make_golden.py), so the parameter naming is part of what is checked."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.golden.cases import CASES, build_my_flownet, make_inputs
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = dict(np.load(os.path.join(HERE, "golden", "flownet_ogcdr_512.npz")))
+CASE = CASES["flownet_ogcdr_512"]
+
+
+def run(device):
+    from ogc_b200.flownet import build_flow_loss
+    net = build_my_flownet(CASE).to(device)
+    inp = {k: v.to(device) for k, v in make_inputs(CASE).items()}
+    preds = net(inp["pc1"], inp["pc2"], inp["pc1"], inp["pc2"], iters=CASE["iters"])
+    loss, d = build_flow_loss(CASE["loss_cfg"])(inp["pc1"], inp["pc2"], preds)
+    loss.backward()
+    grads = {n: dict(net.named_parameters())[n].grad.cpu().numpy() for n in CASE["grad_params"]}
+    return [p.detach().cpu().numpy() for p in preds], float(loss.detach()), d, grads
+
+
+def check(preds, loss, d, grads, tol, gtol):
+    for i, p in enumerate(preds):
+        err = float(np.abs(p - G["flow%d" % i]).max())
+        assert err <= tol, f"flow prediction {i}: {err:.2e}"
+    assert abs(loss - float(G["loss"])) <= tol * max(1.0, abs(float(G["loss"])))
+    for k, v in d.items():
+        assert abs(v - float(G["dict:" + k])) <= tol * max(1.0, abs(float(G["dict:" + k]))), k
+    for n, g in grads.items():
+        ref = G["grad:" + n]
+        rel = float(np.linalg.norm(g - ref) / max(np.linalg.norm(ref), 1e-12))
+        assert rel <= gtol, f"grad {n}: rel Frobenius error {rel:.2e}"
+
+
+def test_flownet_state_dict_names_match_reference_layout():
+    names = set(build_my_flownet(CASE).state_dict())
+    for n in CASE["grad_params"] + ["encoder_glob.sa2.mlp_bns.2.running_var", "h0_net.sa2.mlp_convs.0.weight",
+                                    "local_corr_layer.mlp_convs.0.weight", "flow_conv2.mlp_bns.0.num_batches_tracked",
+                                    "gru.convz.mlp_convs.0.weight", "flow0_regressor.fc.bias"]:
+        assert n in names, n
+
+
+def test_flownet_composed_cpu_matches_reference(oracle_ops):
+    check(*run("cpu"), tol=1e-5, gtol=1e-4)
+
+
+@pytest.mark.gpu
+def test_flownet_gpu_matches_reference(b200):
+    # fp32 reassociation (cuDNN/cuBLAS conv, batch-norm reductions) through 3 GRU iterations; a single arg-max /
+    # ReLU flip moves a weight gradient by ~1e-3 of its norm (see tests/test_gpu_fused_sa.py).
+    check(*run("cuda"), tol=1e-4, gtol=5e-3)
