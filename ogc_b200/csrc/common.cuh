@@ -63,6 +63,24 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
         : "memory");
 }
 
+// ---- per-thread async copies global -> shared (SASS: LDGSTS), tracked with commit / wait groups ----
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src_gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *dst_smem, const void *src_gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// wait until at most `pending` (0..3) of this thread's most recent groups are still in flight
+__device__ __forceinline__ void cp_async_wait(int pending) {
+    switch (pending) {
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+    }
+}
+
 // Stage `nfloats` contiguous floats from global memory into shared memory with the TMA bulk-copy
 // engine.  `sm` must be 16-byte aligned with room for nfloats + 4 floats.  The source only needs
 // 4-byte alignment: the (<= 3 float) unaligned head and tail are moved with ordinary loads, the

@@ -1,7 +1,7 @@
 // Fused set-abstraction MLP layer on the 5th-generation tensor cores (tcgen05.mma kind::tf32, 3xTF32 split).
 //
 // Same contract as mlp_fwd_kernel in mlp.cu (one SharedMLP layer: y = W a, GroupNorm statistics, optional
-// max/min over nsample), for the layers where the contraction dominates (C_out >= 64, K a multiple of 32
+// max/min over nsample), for the layers where the contraction dominates (C_out >= 64, K a multiple of 4
 // after taking the three xyz input channels of a gathered layer out of the GEMM).
 //
 //   D[co][p] = sum_k W[co][k] a[k][p]      M = 128 output channels (TMEM lanes), N = 64 positions (one centre,
@@ -9,193 +9,244 @@
 //   fp32-grade accuracy from tf32 tensor cores: x = hi + lo (hi = rna_tf32(x), lo = rna_tf32(x - hi));
 //   D += W_hi a_hi + W_hi a_lo + W_lo a_hi      (error ~3x an fp32 GEMM: tests/test_gpu_tcgen05.py)
 //
-// One persistent CTA per SM, warp-specialised:
+// One persistent CTA per SM, warp-specialised, every stage asynchronous to the next:
+//   W (hi and lo)  lives in TENSOR MEMORY for the CTA's lifetime (2 x K columns next to the accumulators) and is
+//              the MMA's A operand from there: no shared memory, and no shared-memory bandwidth per MMA
+//   warps 4-11 "transformers": (1) cp.async the RAW input of tile u+D (rows of the previous layer's pre-norm
+//              output, or the gathered feature rows + xyz of the tile's 64 neighbours) into a ring of raw stages,
+//              D tiles ahead -- the HBM/L2 latency is covered by copies in flight, not by registers;
+//              (2) turn the raw stage of tile u into the B operand: GroupNorm+ReLU of the previous layer on the
+//              fly, hi/lo split, 128B-swizzled K-major rows, double buffered against the MMAs
+//   warp 12    one thread issues the MMAs (A from TMEM, B from shared memory) and commits to mbarriers
 //   warps 0-3  epilogue: tcgen05.ld their 32 TMEM lanes (= 32 channels) x 64 columns; thread = channel, so
 //              the GroupNorm sums, the max/min/arg over the 64 samples and the xyz contribution of a gathered
-//              layer are plain per-thread loops (no shuffles); stores y channel-major (16 x 16 B per thread)
-//   warps 4-7  loader: build the activation tile (64 positions x K) in the 128B-swizzled K-major layout,
-//              hi and lo copies: gather feature rows through idx (coalesced 128 B row reads), or read the
-//              previous layer's pre-norm output and apply GroupNorm+ReLU on the fly
-//   warp  8    one thread issues the MMAs and commits to mbarriers; owns the TMEM allocation
-// The weight tile (hi+lo, up to 128 KB) stays in shared memory for the CTA's lifetime; TMEM is double
-// buffered (2 x 64 columns) so the epilogue of tile t overlaps the load + MMA of tile t+1.
+//              layer are plain per-thread loops (no shuffles); stores y channel-major (16 x 16 B per thread);
+//              the accumulator is double buffered so this overlaps the next tile's MMAs
+#include <cstdlib>
+
 #include "mlp_common.cuh"
 #include "tcgen05.cuh"
 
 namespace ogc {
 
-constexpr int kTcLoaderWarps = 8;
-constexpr int kTcLoaders = kTcLoaderWarps * 32;
-constexpr int kTcMmaWarp = 4 + kTcLoaderWarps;
+constexpr int kTcXfWarps = 8;                 // transformer warps
+constexpr int kTcXf = kTcXfWarps * 32;
+constexpr int kTcMmaWarp = 4 + kTcXfWarps;
 constexpr int kTcThreads = (kTcMmaWarp + 1) * 32;
 constexpr int kTcNT = 64;          // positions per tile == nsample
 constexpr int kTcM = 128;          // output channels per CTA (one M block)
+constexpr int kTcMaxK = 128;       // contraction length (TMEM: 128 accumulator + 2 * 128 weight columns)
+constexpr int kTcWCol = 2 * kTcNT; // first TMEM column of W_hi
+constexpr int kTcRowPad = 16;      // raw rows are padded by 16 B: 16-byte row reads at a 4-bank skew
+constexpr int kTcXfBar = 2;        // named barrier of the transformer warps
 
 struct MlpTcParams {
     MlpFwdParams f;
     const float *W;       // (Cout, Cin) row-major (NOT transposed)
     int k_off, K;         // tensor-core K range: W columns [k_off, k_off+K); gather: k_off = 3, K = Cf
+    int n_raw, n_op;      // raw ring stages (2..4), operand buffers (1..2)
+    int raw_stage_bytes;
 };
 
 template <bool GATHER, bool LAST>
 __global__ void __launch_bounds__(kTcThreads, 1)
 mlp_fwd_tc_kernel(MlpTcParams q) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_full, bar_empty, bar_tfull[2], bar_tempty[2];
+    __shared__ __align__(8) uint64_t bar_full[2], bar_empty[2], bar_tfull[2], bar_tempty[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ double gs[kGnGroups][2];
     __shared__ float rel[2][kTcNT][4];   // centred xyz of the tile's positions (gather), double buffered
+    __shared__ float2 ss_s[kTcMaxK];     // GroupNorm (scale, shift) of the input channels (dense)
+    __shared__ int idx_s[2][kTcNT];      // neighbour indices of the tile whose copies are issued next (gather)
 
     const MlpFwdParams &f = q.f;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y, mb = blockIdx.z;
-    const int K = q.K, KB = (K + 31) / 32;
+    const int K = q.K, KB = (K + 31) / 32, Kp = KB * 32;
     const int Cout = f.Cout, Cin = f.Cin, P = f.P;
     const int ntiles = P / kTcNT;
+    const int n_my = ntiles > static_cast<int>(blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int n_op = q.n_op, n_raw = q.n_raw, D = n_raw - 1;
 
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const uint32_t w_bytes = static_cast<uint32_t>(KB) * kTcM * 128u, a_bytes = static_cast<uint32_t>(KB) * kTcNT * 128u;
-    uint8_t *w_hi = smem, *w_lo = w_hi + w_bytes, *a_hi = w_lo + w_bytes, *a_lo = a_hi + a_bytes;
+    const uint32_t a_bytes = static_cast<uint32_t>(KB) * kTcNT * 128u;      // one of hi / lo
+    uint8_t *raw_base = smem + static_cast<size_t>(n_op) * 2 * a_bytes;
+    auto op_hi = [&](int ob) { return smem + static_cast<size_t>(ob) * 2 * a_bytes; };
+    auto raw_stage = [&](int u) { return raw_base + static_cast<size_t>(u % n_raw) * q.raw_stage_bytes; };
+    const uint32_t g_pitch = static_cast<uint32_t>(K) * 4u + kTcRowPad;     // gather: row = one neighbour's K features
+    const uint32_t d_pitch = kTcNT * 4u + kTcRowPad;                        // dense: row = one channel's 64 positions
+    const uint32_t xyz_off = kTcNT * g_pitch;                               // gather: 64 x 3 xyz, then the centre
 
-    if (warp == kTcMmaWarp) tc::tmem_alloc(&tmem_base_s, 128);
+    if (warp == kTcMmaWarp) tc::tmem_alloc(&tmem_base_s, 512);
     if (tid == 0) {
-        mbar_init(&bar_full, kTcLoaders);
-        mbar_init(&bar_empty, 1);
-        mbar_init(&bar_tfull[0], 1); mbar_init(&bar_tfull[1], 1);
-        mbar_init(&bar_tempty[0], 128); mbar_init(&bar_tempty[1], 128);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_full[i], kTcXf); mbar_init(&bar_empty[i], 1);
+            mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], 128);
+        }
         mbar_fence_init();
     }
     if (tid < kGnGroups * 2) (&gs[0][0])[tid] = 0.0;
-    // weight tile: rows = this M block's output channels, K-major, hi + lo
-    for (int e = tid; e < kTcM * KB * 32; e += kTcThreads) {
-        const int r = e / (KB * 32), k = e - r * (KB * 32);
-        const int co = mb * kTcM + r;
-        const float v = (co < Cout && k < K) ? __ldg(q.W + static_cast<size_t>(co) * Cin + q.k_off + k) : 0.f;
-        const float hi = tc::tf32_hi(v);
-        const uint32_t off = static_cast<uint32_t>(k >> 5) * (kTcM * 128u) + tc::sw128_offset(r, k & 31);
-        *reinterpret_cast<float *>(w_hi + off) = hi;
-        *reinterpret_cast<float *>(w_lo + off) = tc::tf32_hi(v - hi);
-    }
-    tc::fence_proxy_async();
+    if (!GATHER)
+        for (int c = tid; c < K; c += kTcThreads)
+            ss_s[c] = __ldg(reinterpret_cast<const float2 *>(f.ss_prev) + static_cast<size_t>(b) * Cin + c);
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = tmem_base_s;
 
-    if (warp >= 4 && warp < kTcMmaWarp) {
-        // ================================ loader ================================
-        const int lt = tid - 128;           // 0..kTcLoaders-1
-        const int lw = warp - 4;
-        int use = 0;
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++use) {
-            const int p0 = t * kTcNT;
-            mbar_wait(&bar_empty, (use & 1) ^ 1);          // the MMAs that read the previous tile are done
+    // ---- raw-stage copies of this CTA's u-th tile (transformer threads; no wait) ----
+    const int lt = tid - 128;
+    auto issue = [&](int u) {
+        const int t = blockIdx.x + u * gridDim.x;
+        uint8_t *st = raw_stage(u);
+        if (GATHER) {
+            const int *js = idx_s[u & 1];
+            const int cpr = K >> 2;                       // 16-byte chunks per feature row
+            for (int it = lt; it < kTcNT * cpr; it += kTcXf) {
+                const int p = it / cpr, ch = it - p * cpr;
+                cp_async16(st + p * g_pitch + ch * 16, f.feat_pm + (static_cast<size_t>(b) * f.N + js[p]) * f.Cf + ch * 4);
+            }
+            if (lt < kTcNT * 3) {
+                const int p = lt / 3, c = lt - p * 3;
+                cp_async4(st + xyz_off + lt * 4, f.xyz + (static_cast<size_t>(b) * f.N + js[p]) * 3 + c);
+            } else if (lt < kTcNT * 3 + 3) {
+                const int c = lt - kTcNT * 3;
+                cp_async4(st + xyz_off + lt * 4, f.new_xyz + (static_cast<size_t>(b) * f.M + t) * 3 + c);
+            }
+        } else {
+            const float *src = f.y_prev + static_cast<size_t>(b) * Cin * P + static_cast<size_t>(t) * kTcNT;
+            for (int it = lt; it < K * 16; it += kTcXf) {
+                const int c = it >> 4, ch = it & 15;
+                cp_async16(st + c * d_pitch + ch * 16, src + static_cast<size_t>(c) * P + ch * 4);
+            }
+        }
+    };
+    auto load_idx = [&](int u) {     // neighbour indices of tile u (threads lt < 64), -1 past the end
+        return (lt < kTcNT && u < n_my)
+                   ? __ldg(f.idx + static_cast<size_t>(b) * P + static_cast<size_t>(blockIdx.x + u * gridDim.x) * kTcNT + lt) : 0;
+    };
+
+    if (warp < 4) {
+        // ---- W -> tensor memory: thread = output channel = TMEM lane; columns [kTcWCol, +Kp) hi, then lo ----
+        const int co = mb * kTcM + tid;
+        const float *wrow = q.W + static_cast<size_t>(co < Cout ? co : 0) * Cin + q.k_off;
+        for (int kb = 0; kb < KB; ++kb) {
+            float hi[32], lo[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int k = kb * 32 + j;
+                const float v = (co < Cout && k < K) ? __ldg(wrow + k) : 0.f;
+                hi[j] = tc::tf32_hi(v);
+                lo[j] = tc::tf32_hi(v - hi[j]);
+            }
+            const uint32_t ta = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + kTcWCol + kb * 32;
+            tc::tmem_st32(ta, hi);
+            tc::tmem_st32(ta + Kp, lo);
+        }
+    } else if (warp < kTcMmaWarp) {
+        // ---- prologue: the first D tiles' copies ----
+        for (int d = 0; d < D; ++d) {
             if (GATHER) {
-                // rel[use & 1] was last read by the epilogue of tile use-2, which arrives on bar_tempty AFTER that read
-                mbar_wait(&bar_tempty[use & 1], ((use >> 1) & 1) ^ 1);
-                // the tile's 64 neighbour indices: lane l holds positions l and l + 32
-                const int j_lo = __ldg(f.idx + static_cast<size_t>(b) * P + p0 + lane);
-                const int j_hi = __ldg(f.idx + static_cast<size_t>(b) * P + p0 + 32 + lane);
-                // one warp per (position, column block): 32 lanes = 32 consecutive feature channels of one point
-                // row (coalesced 128 B); 8 independent row reads in flight per lane before any is consumed
-                const int nitems = kTcNT * KB;
-                for (int it0 = lw; it0 < nitems; it0 += kTcLoaderWarps * 8) {
-                    float vals[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int it = it0 + kTcLoaderWarps * u;
-                        const int p = it / KB, kb = it - p * KB;
-                        const int j = __shfl_sync(OGC_FULL_MASK, p < 32 ? j_lo : j_hi, p & 31);
-                        const int c = kb * 32 + lane;
-                        vals[u] = (it < nitems && c < K) ? __ldg(f.feat_pm + (static_cast<size_t>(b) * f.N + j) * f.Cf + c) : 0.f;
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int it = it0 + kTcLoaderWarps * u;
-                        if (it < nitems) {
-                            const int p = it / KB, kb = it - p * KB;
-                            const float hi = tc::tf32_hi(vals[u]);
-                            const uint32_t off = static_cast<uint32_t>(kb) * (kTcNT * 128u) + tc::sw128_offset(p, lane);
-                            *reinterpret_cast<float *>(a_hi + off) = hi;
-                            *reinterpret_cast<float *>(a_lo + off) = tc::tf32_hi(vals[u] - hi);
-                        }
-                    }
-                }
+                const int j = load_idx(d);
+                if (lt < kTcNT) idx_s[d & 1][lt] = j;
+                named_bar_sync(kTcXfBar, kTcXf);
+            }
+            if (d < n_my) issue(d);
+            cp_async_commit();
+        }
+        if (GATHER) {
+            const int j = load_idx(D);
+            named_bar_sync(kTcXfBar, kTcXf);             // issue(D-2) has read the slot
+            if (lt < kTcNT) idx_s[D & 1][lt] = j;
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+
+    if (warp >= 4 && warp < kTcMmaWarp) {
+        // ================================ transformers ================================
+        for (int u = 0; u < n_my; ++u) {
+            const int ob = u % n_op, tb = u & 1;
+            cp_async_wait(D - 1);                          // this thread's copies of tile u have landed
+            named_bar_sync(kTcXfBar, kTcXf);               // ... everyone's; and transform u-1 is finished everywhere
+            if (u + D < n_my) issue(u + D);                // into the stage tile u-1 just vacated
+            cp_async_commit();
+            int jn = 0;
+            if (GATHER) jn = load_idx(u + D + 1);
+            mbar_wait(&bar_empty[ob], ((u / n_op) & 1) ^ 1);            // MMAs of the tile that used this buffer are done
+            const uint8_t *st = raw_stage(u);
+            uint8_t *a_hi = op_hi(ob), *a_lo = a_hi + a_bytes;
+            if (GATHER) {
+                // rel[tb] was last read by the epilogue of tile u-2, which arrives on bar_tempty AFTER that read
+                mbar_wait(&bar_tempty[tb], ((u >> 1) & 1) ^ 1);
                 if (lt < kTcNT) {
-                    const int j = __ldg(f.idx + static_cast<size_t>(b) * P + p0 + lt);
-                    const int m = (p0 + lt) / f.S;
+                    const float *xs = reinterpret_cast<const float *>(st + xyz_off);
 #pragma unroll
-                    for (int c = 0; c < 3; ++c)
-                        rel[use & 1][lt][c] = __ldg(f.xyz + (static_cast<size_t>(b) * f.N + j) * 3 + c) -
-                                              __ldg(f.new_xyz + (static_cast<size_t>(b) * f.M + m) * 3 + c);
+                    for (int c = 0; c < 3; ++c) rel[tb][lt][c] = xs[lt * 3 + c] - xs[kTcNT * 3 + c];
+                }
+                const int qpr = KB * 8;                    // channel quads per operand row (incl. zero padding)
+                for (int it = lt; it < kTcNT * qpr; it += kTcXf) {
+                    const int p = it / qpr, c = (it - p * qpr) * 4;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (c < K) v = *reinterpret_cast<const float4 *>(st + p * g_pitch + c * 4);
+                    const float4 hi = make_float4(tc::tf32_hi(v.x), tc::tf32_hi(v.y), tc::tf32_hi(v.z), tc::tf32_hi(v.w));
+                    const float4 lo = make_float4(tc::tf32_hi(v.x - hi.x), tc::tf32_hi(v.y - hi.y), tc::tf32_hi(v.z - hi.z),
+                                                  tc::tf32_hi(v.w - hi.w));
+                    const uint32_t off = static_cast<uint32_t>(c >> 5) * (kTcNT * 128u) + tc::sw128_offset(p, c & 31);
+                    *reinterpret_cast<float4 *>(a_hi + off) = hi;
+                    *reinterpret_cast<float4 *>(a_lo + off) = lo;
                 }
             } else {
-                // channel-major source: item = (column block, position quad, channel in block); a warp covers the
-                // 32 channels of one block for one quad -> conflict-free swizzled row writes.  8 independent 16 B
-                // loads in flight per thread before any is consumed (the loader is latency-, not issue-bound).
-                const int nitems = KB * 16 * 32;
-                for (int it0 = lt; it0 < nitems; it0 += kTcLoaders * 8) {
-                    float4 raw[8];
-                    float scv[8], shv[8];
+                // raw rows are channels: a thread takes 4 consecutive channels of one position (4 conflict-free
+                // scalar reads, lanes = consecutive positions) and writes one 16-byte chunk of the K-major row
+                for (int it = lt; it < kTcNT * KB * 8; it += kTcXf) {
+                    const int p = it & (kTcNT - 1), c = (it >> 6) * 4;
+                    float v[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (c < K) {
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int it = it0 + kTcLoaders * u;
-                        const int cl = it & 31, pq = (it >> 5) & 15, kb = it >> 9;
-                        const int c = kb * 32 + cl;
-                        raw[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        scv[u] = shv[u] = 0.f;
-                        if (it < nitems && c < K) {
-                            scv[u] = __ldg(f.ss_prev + (static_cast<size_t>(b) * Cin + c) * 2);
-                            shv[u] = __ldg(f.ss_prev + (static_cast<size_t>(b) * Cin + c) * 2 + 1);
-                            raw[u] = __ldg(reinterpret_cast<const float4 *>(f.y_prev + (static_cast<size_t>(b) * Cin + c) * P + p0 + pq * 4));
+                        for (int e = 0; e < 4; ++e) {
+                            const float x = *reinterpret_cast<const float *>(st + (c + e) * d_pitch + p * 4);
+                            const float2 ss = ss_s[c + e];
+                            v[e] = fmaxf(fmaf(ss.x, x, ss.y), 0.f);
                         }
                     }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int it = it0 + kTcLoaders * u;
-                        if (it >= nitems) continue;
-                        const int cl = it & 31, pq = (it >> 5) & 15, kb = it >> 9;
-                        const float vv[4] = {fmaxf(fmaf(scv[u], raw[u].x, shv[u]), 0.f), fmaxf(fmaf(scv[u], raw[u].y, shv[u]), 0.f),
-                                             fmaxf(fmaf(scv[u], raw[u].z, shv[u]), 0.f), fmaxf(fmaf(scv[u], raw[u].w, shv[u]), 0.f)};
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float hi = tc::tf32_hi(vv[j]);
-                            const uint32_t off = static_cast<uint32_t>(kb) * (kTcNT * 128u) + tc::sw128_offset(pq * 4 + j, cl);
-                            *reinterpret_cast<float *>(a_hi + off) = hi;
-                            *reinterpret_cast<float *>(a_lo + off) = tc::tf32_hi(vv[j] - hi);
-                        }
-                    }
+                    const float4 hi = make_float4(tc::tf32_hi(v[0]), tc::tf32_hi(v[1]), tc::tf32_hi(v[2]), tc::tf32_hi(v[3]));
+                    const float4 lo = make_float4(tc::tf32_hi(v[0] - hi.x), tc::tf32_hi(v[1] - hi.y), tc::tf32_hi(v[2] - hi.z),
+                                                  tc::tf32_hi(v[3] - hi.w));
+                    const uint32_t off = static_cast<uint32_t>(c >> 5) * (kTcNT * 128u) + tc::sw128_offset(p, c & 31);
+                    *reinterpret_cast<float4 *>(a_hi + off) = hi;
+                    *reinterpret_cast<float4 *>(a_lo + off) = lo;
                 }
             }
             tc::fence_proxy_async();
-            mbar_arrive(&bar_full);
+            mbar_arrive(&bar_full[ob]);
+            if (GATHER && lt < kTcNT) idx_s[(u + D + 1) & 1][lt] = jn;   // read by issue(u+D+1) after the next barrier
         }
     } else if (warp == kTcMmaWarp) {
         // ================================ MMA issuer ================================
         if (lane == 0) {
             const uint32_t idesc = tc::make_idesc_tf32(kTcM, kTcNT, 0, 0);
-            int use = 0;
-            for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++use) {
-                const int buf = use & 1;
-                mbar_wait(&bar_full, use & 1);
-                mbar_wait(&bar_tempty[buf], ((use >> 1) & 1) ^ 1);
+            for (int u = 0; u < n_my; ++u) {
+                const int ob = u % n_op, tb = u & 1;
+                mbar_wait(&bar_full[ob], (u / n_op) & 1);
+                mbar_wait(&bar_tempty[tb], ((u >> 1) & 1) ^ 1);
                 tc::fence_after_sync();
-                const uint32_t d = tmem_base + static_cast<uint32_t>(buf * kTcNT);
+                const uint32_t d = tmem_base + static_cast<uint32_t>(tb * kTcNT);
+                const uint32_t bh0 = smem_u32(op_hi(ob)), bl0 = bh0 + a_bytes;
                 uint32_t acc = 0;
                 for (int s = 0; s < KB * 4; ++s) {
-                    const uint32_t wo = static_cast<uint32_t>(s >> 2) * (kTcM * 128u) + static_cast<uint32_t>(s & 3) * 32u;
-                    const uint32_t ao = static_cast<uint32_t>(s >> 2) * (kTcNT * 128u) + static_cast<uint32_t>(s & 3) * 32u;
-                    const uint64_t whd = tc::make_desc_sw128(smem_u32(w_hi) + wo, 16, 1024);
-                    const uint64_t wld = tc::make_desc_sw128(smem_u32(w_lo) + wo, 16, 1024);
-                    const uint64_t ahd = tc::make_desc_sw128(smem_u32(a_hi) + ao, 16, 1024);
-                    const uint64_t ald = tc::make_desc_sw128(smem_u32(a_lo) + ao, 16, 1024);
-                    tc::mma_tf32(d, whd, ahd, idesc, acc);
-                    tc::mma_tf32(d, whd, ald, idesc, 1);
-                    tc::mma_tf32(d, wld, ahd, idesc, 1);
+                    const uint32_t bo = static_cast<uint32_t>(s >> 2) * (kTcNT * 128u) + static_cast<uint32_t>(s & 3) * 32u;
+                    const uint64_t bhd = tc::make_desc_sw128(bh0 + bo, 16, 1024);
+                    const uint64_t bld = tc::make_desc_sw128(bl0 + bo, 16, 1024);
+                    const uint32_t wh = tmem_base + kTcWCol + static_cast<uint32_t>(s * 8), wl = wh + Kp;
+                    tc::mma_tf32_ts(d, wh, bhd, idesc, acc);
+                    tc::mma_tf32_ts(d, wh, bld, idesc, 1);
+                    tc::mma_tf32_ts(d, wl, bhd, idesc, 1);
                     acc = 1;
                 }
-                tc::mma_commit(&bar_empty);        // operand tile may be overwritten
-                tc::mma_commit(&bar_tfull[buf]);   // accumulator ready
+                tc::mma_commit(&bar_empty[ob]);    // operand buffer may be overwritten
+                tc::mma_commit(&bar_tfull[tb]);    // accumulator ready
             }
         }
     } else {
@@ -206,11 +257,10 @@ mlp_fwd_tc_kernel(MlpTcParams q) {
         if (GATHER && valid)
             for (int c = 0; c < 3; ++c) wx[c] = __ldg(q.W + static_cast<size_t>(co) * Cin + c);
         double ds = 0.0, dq = 0.0;
-        int use = 0;
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++use) {
-            const int buf = use & 1;
-            const int p0 = t * kTcNT;
-            mbar_wait(&bar_tfull[buf], (use >> 1) & 1);
+        for (int u = 0; u < n_my; ++u) {
+            const int buf = u & 1;
+            const int p0 = (blockIdx.x + u * gridDim.x) * kTcNT;
+            mbar_wait(&bar_tfull[buf], (u >> 1) & 1);
             tc::fence_after_sync();
             float v[kTcNT];
             {
@@ -230,7 +280,7 @@ mlp_fwd_tc_kernel(MlpTcParams q) {
                     v[j] = fmaf(wx[2], rel[buf][j][2], fmaf(wx[1], rel[buf][j][1], fmaf(wx[0], rel[buf][j][0], v[j])));
             }
             tc::fence_before_sync();
-            mbar_arrive(&bar_tempty[buf]);          // TMEM buffer (and rel[buf]) free for tile t+2
+            mbar_arrive(&bar_tempty[buf]);          // TMEM buffer (and rel[buf]) free for tile u+2
             if (valid) {
                 float s = 0.f, sq = 0.f;
 #pragma unroll
@@ -267,14 +317,31 @@ mlp_fwd_tc_kernel(MlpTcParams q) {
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == kTcMmaWarp) tc::tmem_dealloc(tmem_base, 128);
+    if (warp == kTcMmaWarp) tc::tmem_dealloc(tmem_base, 512);
+}
+
+// raw ring / operand buffer counts for a contraction length K (0 = does not fit)
+static inline bool tc_fwd_plan(int K, bool gather, int &n_raw, int &n_op, int &stage, size_t &smem) {
+    const int KB = (K + 31) / 32;
+    const size_t op = static_cast<size_t>(KB) * kTcNT * 128 * 2;
+    stage = gather ? kTcNT * (K * 4 + kTcRowPad) + 1024 : K * (kTcNT * 4 + kTcRowPad);
+    stage = (stage + 127) & ~127;
+    const size_t budget = static_cast<size_t>(kMaxSmemPerCta) - 6 * 1024 - 1024;
+    for (n_op = 2; n_op >= 1; --n_op) {
+        if (op * n_op + 2 * static_cast<size_t>(stage) > budget) continue;
+        n_raw = static_cast<int>((budget - op * n_op) / stage);
+        n_raw = n_raw > 4 ? 4 : n_raw;
+        smem = op * n_op + static_cast<size_t>(n_raw) * stage + 1024;
+        return true;
+    }
+    return false;
 }
 
 }  // namespace ogc
 
 // Tensor-core variant of ogc_sa_mlp_layer_fwd (same meaning of every argument; `w` is W (cout,cin), not W^T).
 // Supported: nsample == 64, cout a multiple of 16 with cout/4 groups aligned, K = (gather ? cin-3 : cin) a
-// multiple of 4 and <= 160.  Returns OGC_ERR_UNSUPPORTED otherwise (callers fall back to the SIMT kernel).
+// multiple of 4 and <= 128.  Returns OGC_ERR_UNSUPPORTED otherwise (callers fall back to the SIMT kernel).
 extern "C" int ogc_sa_mlp_layer_fwd_tc(int b, int n, int m, int nsample, int cin, int cout, int gather, int last,
                                        const float *xyz, const float *new_xyz, const float *feat_pm, const int *idx,
                                        const float *y_prev, const float *ss_prev, const float *w, float *y,
@@ -284,7 +351,8 @@ extern "C" int ogc_sa_mlp_layer_fwd_tc(int b, int n, int m, int nsample, int cin
     if (b < 0 || m <= 0 || nsample <= 0 || cin <= 0 || cout <= 0 || !w || !sums) return OGC_ERR_INVALID_ARG;
     if (b == 0) return OGC_OK;
     const int K = gather ? cin - 3 : cin;
-    if (nsample != kTcNT || cout % 16 != 0 || cout > 256 || K < 8 || K > 160 || b > 65535) return OGC_ERR_UNSUPPORTED;
+    if (nsample != kTcNT || cout % 16 != 0 || cout > 256 || K < 8 || K > kTcMaxK || K % 4 != 0 || b > 65535)
+        return OGC_ERR_UNSUPPORTED;
     if (last && (!ymax || !ymin || !amax || !amin)) return OGC_ERR_INVALID_ARG;
     if (gather && (!xyz || !new_xyz || !idx || !feat_pm)) return OGC_ERR_INVALID_ARG;
     if (!gather && (!y_prev || !ss_prev)) return OGC_ERR_INVALID_ARG;
@@ -293,9 +361,9 @@ extern "C" int ogc_sa_mlp_layer_fwd_tc(int b, int n, int m, int nsample, int cin
     q.f.xyz = xyz; q.f.new_xyz = new_xyz; q.f.feat_pm = feat_pm; q.f.idx = idx; q.f.y_prev = y_prev; q.f.ss_prev = ss_prev;
     q.f.Wt = nullptr; q.f.y = y; q.f.sums = sums; q.f.ymax = ymax; q.f.ymin = ymin; q.f.amax = amax; q.f.amin = amin;
     q.W = w; q.k_off = gather ? 3 : 0; q.K = K;
-    const int KB = (K + 31) / 32;
-    const size_t smem = static_cast<size_t>(KB) * (kTcM + kTcNT) * 128 * 2 + 1024;
-    if (smem > static_cast<size_t>(kMaxSmemPerCta) - 2048) return OGC_ERR_UNSUPPORTED;
+    size_t smem = 0;
+    if (!tc_fwd_plan(K, gather != 0, q.n_raw, q.n_op, q.raw_stage_bytes, smem)) return OGC_ERR_UNSUPPORTED;
+    if (const char *e = getenv("OGC_TC_NRAW")) { const int v = atoi(e); if (v >= 2 && v <= q.n_raw) q.n_raw = v; }
     const int ntiles = m;
     const int mblocks = (cout + kTcM - 1) / kTcM;
     int per_sample = kNumSMs / (b * mblocks);      // one CTA per SM (shared memory): never more CTAs than SMs if avoidable

@@ -37,121 +37,186 @@ struct MlpDxTcParams {
     const int *idx;
     float *dfeat_pm;
     int N, dfeat_stride, dfeat_off;
+    int n_raw, n_op, raw_stage_bytes;
 };
 
+constexpr int kTbMaxK = 128;
+constexpr int kTbWCol = 2 * kTbNT;   // first TMEM column of (W^T)_hi
+constexpr int kTbRowPad = 16;
+constexpr int kTbXfBar = 2;
+
+// Same skeleton as mlp_fwd_tc_kernel (mlp_tc.cu): W^T (hi, lo) stationary in TENSOR MEMORY as the A operand, raw
+// y_l / dz_l rows of tile u+D streamed into a shared-memory ring with cp.async, dY built from them (GroupNorm
+// backward folded into 4 coefficients per channel) as the K-major B operand, accumulator double buffered.
 template <bool SCATTER>
 __global__ void __launch_bounds__(kTbThreads, 1)
 mlp_dx_tc_kernel(MlpDxTcParams q) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_full, bar_empty, bar_tfull[2], bar_tempty[2];
+    __shared__ __align__(8) uint64_t bar_full[2], bar_empty[2], bar_tfull[2], bar_tempty[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ double gs[kGnGroups][2];
+    __shared__ float4 coef_s[kTbMaxK];          // k1, k2, k3r, mean of this launch's K channels
+    __shared__ float2 selgo_s[2][kTbMaxK];      // last layer: (winning position, pooled gradient) per channel of a tile
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y;
-    const int KB = (q.kn + 31) / 32;
+    const int kn = q.kn, KB = (kn + 31) / 32, Kp = KB * 32;
     const int P = q.dy.P;
     const int ntiles = P / kTbNT;
+    const int n_my = ntiles > static_cast<int>(blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int n_op = q.n_op, n_raw = q.n_raw, D = n_raw - 1;
+    const bool synth = q.dy.dz == nullptr;       // dz from (sel, go) instead of a stored tensor
 
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const uint32_t w_bytes = static_cast<uint32_t>(KB) * kTbM * 128u, a_bytes = static_cast<uint32_t>(KB) * kTbNT * 128u;
-    uint8_t *w_hi = smem, *w_lo = w_hi + w_bytes, *a_hi = w_lo + w_bytes, *a_lo = a_hi + a_bytes;
+    const uint32_t a_bytes = static_cast<uint32_t>(KB) * kTbNT * 128u;
+    uint8_t *raw_base = smem + static_cast<size_t>(n_op) * 2 * a_bytes;
+    auto op_hi = [&](int ob) { return smem + static_cast<size_t>(ob) * 2 * a_bytes; };
+    auto raw_stage = [&](int u) { return raw_base + static_cast<size_t>(u % n_raw) * q.raw_stage_bytes; };
+    const uint32_t pitch = kTbNT * 4u + kTbRowPad;
+    const uint32_t dz_off = static_cast<uint32_t>(kn) * pitch;   // dz rows follow the y rows
 
-    if (warp == kTbMmaWarp) tc::tmem_alloc(&tmem_base_s, 128);
+    if (warp == kTbMmaWarp) tc::tmem_alloc(&tmem_base_s, 512);
     if (tid == 0) {
-        mbar_init(&bar_full, kTbLoaders);
-        mbar_init(&bar_empty, 1);
-        mbar_init(&bar_tfull[0], 1); mbar_init(&bar_tfull[1], 1);
-        mbar_init(&bar_tempty[0], 128); mbar_init(&bar_tempty[1], 128);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_full[i], kTbLoaders); mbar_init(&bar_empty[i], 1);
+            mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], 128);
+        }
         mbar_fence_init();
     }
     if (tid < kGnGroups * 2) (&gs[0][0])[tid] = 0.0;
-    // A = W^T: row r = input channel row_off + r, column k = output channel k0 + k
-    for (int e = tid; e < kTbM * KB * 32; e += kTbThreads) {
-        const int k = e / kTbM, r = e - k * kTbM;       // consecutive threads -> consecutive r: coalesced W row reads
-        const float v = (r < q.rows && k < q.kn) ? __ldg(q.W + static_cast<size_t>(q.k0 + k) * q.cin_full + q.row_off + r) : 0.f;
-        const float hi = tc::tf32_hi(v);
-        const uint32_t off = static_cast<uint32_t>(k >> 5) * (kTbM * 128u) + tc::sw128_offset(r, k & 31);
-        *reinterpret_cast<float *>(w_hi + off) = hi;
-        *reinterpret_cast<float *>(w_lo + off) = tc::tf32_hi(v - hi);
-    }
-    tc::fence_proxy_async();
+    for (int c = tid; c < kn; c += kTbThreads)
+        coef_s[c] = __ldg(reinterpret_cast<const float4 *>(q.dy.coef) + static_cast<size_t>(b) * q.dy.C + q.k0 + c);
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = tmem_base_s;
 
+    const int lt = tid - 128;
+    auto issue = [&](int u) {
+        const int t = blockIdx.x + u * gridDim.x;
+        uint8_t *st = raw_stage(u);
+        const size_t base = (static_cast<size_t>(b) * q.dy.C + q.k0) * P + static_cast<size_t>(t) * kTbNT;
+        for (int it = lt; it < kn * 16; it += kTbLoaders) {
+            const int c = it >> 4, ch = it & 15;
+            cp_async16(st + c * pitch + ch * 16, q.dy.y + base + static_cast<size_t>(c) * P + ch * 4);
+            if (!synth) cp_async16(st + dz_off + c * pitch + ch * 16, q.dy.dz + base + static_cast<size_t>(c) * P + ch * 4);
+        }
+    };
+    // last layer: (sel, go) of tile u for channel lt (one centre per tile: m = tile index)
+    auto load_selgo = [&](int u) {
+        float2 r = make_float2(255.f, 0.f);
+        if (synth && lt < kn && u < n_my) {
+            const int m = blockIdx.x + u * gridDim.x;
+            r.x = static_cast<float>(__ldg(q.dy.sel + (static_cast<size_t>(b) * q.dy.C + q.k0 + lt) * q.dy.M + m));
+            r.y = __ldg(q.dy.go + (static_cast<size_t>(b) * q.dy.go_ctotal + q.dy.go_coff + q.k0 + lt) * q.dy.M + m);
+        }
+        return r;
+    };
+
+    if (warp < 4) {
+        // ---- W^T -> tensor memory: thread = row r (input channel row_off + r), column k = output channel k0 + k ----
+        const int r = tid;
+        for (int kb = 0; kb < KB; ++kb) {
+            float hi[32], lo[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int k = kb * 32 + j;
+                const float v = (r < q.rows && k < kn) ? __ldg(q.W + static_cast<size_t>(q.k0 + k) * q.cin_full + q.row_off + r) : 0.f;
+                hi[j] = tc::tf32_hi(v);
+                lo[j] = tc::tf32_hi(v - hi[j]);
+            }
+            const uint32_t ta = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + kTbWCol + kb * 32;
+            tc::tmem_st32(ta, hi);
+            tc::tmem_st32(ta + Kp, lo);
+        }
+    } else if (warp < kTbMmaWarp) {
+        for (int d = 0; d < D; ++d) {
+            if (d < n_my) issue(d);
+            cp_async_commit();
+        }
+        if (synth && lt < kn) selgo_s[0][lt] = load_selgo(0);
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+
     if (warp >= 4 && warp < kTbMmaWarp) {
-        // ================================ loader: dY tile, rows = positions, K = channels ================
-        const int lt = tid - 128;
-        int use = 0;
-        const int nitems = KB * 16 * 32;
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++use) {
-            const int p0 = t * kTbNT;
-            mbar_wait(&bar_empty, (use & 1) ^ 1);
-            for (int it0 = lt; it0 < nitems; it0 += kTbLoaders * 4) {
-                DyRaw raw[4];
+        // ================================ transformers: dY tile, rows = positions, K = channels ================
+        float2 sg_next = load_selgo(1);
+        for (int u = 0; u < n_my; ++u) {
+            const int ob = u % n_op;
+            cp_async_wait(D - 1);
+            named_bar_sync(kTbXfBar, kTbLoaders);          // tile u's raw rows visible; transform u-1 finished everywhere
+            if (u + D < n_my) issue(u + D);
+            cp_async_commit();
+            if (synth) {                                   // slot (u+1)&1 held tile u-1: free now, read after the next barrier
+                if (lt < kn) selgo_s[(u + 1) & 1][lt] = sg_next;
+                sg_next = load_selgo(u + 2);
+            }
+            mbar_wait(&bar_empty[ob], ((u / n_op) & 1) ^ 1);
+            const uint8_t *st = raw_stage(u);
+            uint8_t *a_hi = op_hi(ob), *a_lo = a_hi + a_bytes;
+            const float2 *sg = selgo_s[u & 1];
+            for (int it = lt; it < kTbNT * KB * 8; it += kTbLoaders) {
+                const int p = it & (kTbNT - 1), c = (it >> 6) * 4;
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                if (c < kn) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int it = it0 + kTbLoaders * u;
-                    const int cl = it & 31, pq = (it >> 5) & 15, kb = it >> 9;
-                    const int c = kb * 32 + cl;
-                    if (it < nitems && c < q.kn) dy_quad_load(q.dy, b, q.k0 + c, p0 + pq * 4, raw[u]);
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int it = it0 + kTbLoaders * u;
-                    if (it >= nitems) continue;
-                    const int cl = it & 31, pq = (it >> 5) & 15, kb = it >> 9;
-                    const int c = kb * 32 + cl;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (c < q.kn) v = dy_quad_finish(q.dy, p0 + pq * 4, raw[u]);
-                    const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float hi = tc::tf32_hi(vv[j]);
-                        const uint32_t off = static_cast<uint32_t>(kb) * (kTbNT * 128u) + tc::sw128_offset(pq * 4 + j, cl);
-                        *reinterpret_cast<float *>(a_hi + off) = hi;
-                        *reinterpret_cast<float *>(a_lo + off) = tc::tf32_hi(vv[j] - hi);
+                    for (int e = 0; e < 4; ++e) {
+                        const float4 cf = coef_s[c + e];
+                        const float y = *reinterpret_cast<const float *>(st + (c + e) * pitch + p * 4);
+                        float dz;
+                        if (synth) {
+                            const float2 s2 = sg[c + e];
+                            dz = (static_cast<int>(s2.x) == p) ? s2.y : 0.f;
+                        } else {
+                            dz = *reinterpret_cast<const float *>(st + dz_off + (c + e) * pitch + p * 4);
+                        }
+                        v[e] = fmaf(cf.x, dz, -cf.y) - (y - cf.w) * cf.z;
                     }
                 }
+                const float4 hi = make_float4(tc::tf32_hi(v[0]), tc::tf32_hi(v[1]), tc::tf32_hi(v[2]), tc::tf32_hi(v[3]));
+                const float4 lo = make_float4(tc::tf32_hi(v[0] - hi.x), tc::tf32_hi(v[1] - hi.y), tc::tf32_hi(v[2] - hi.z),
+                                              tc::tf32_hi(v[3] - hi.w));
+                const uint32_t off = static_cast<uint32_t>(c >> 5) * (kTbNT * 128u) + tc::sw128_offset(p, c & 31);
+                *reinterpret_cast<float4 *>(a_hi + off) = hi;
+                *reinterpret_cast<float4 *>(a_lo + off) = lo;
             }
             tc::fence_proxy_async();
-            mbar_arrive(&bar_full);
+            mbar_arrive(&bar_full[ob]);
         }
     } else if (warp == kTbMmaWarp) {
         if (lane == 0) {
             const uint32_t idesc = tc::make_idesc_tf32(kTbM, kTbNT, 0, 0);
-            int use = 0;
-            for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++use) {
-                const int buf = use & 1;
-                mbar_wait(&bar_full, use & 1);
-                mbar_wait(&bar_tempty[buf], ((use >> 1) & 1) ^ 1);
+            for (int u = 0; u < n_my; ++u) {
+                const int ob = u % n_op, tb = u & 1;
+                mbar_wait(&bar_full[ob], (u / n_op) & 1);
+                mbar_wait(&bar_tempty[tb], ((u >> 1) & 1) ^ 1);
                 tc::fence_after_sync();
-                const uint32_t d = tmem_base + static_cast<uint32_t>(buf * kTbNT);
+                const uint32_t d = tmem_base + static_cast<uint32_t>(tb * kTbNT);
+                const uint32_t bh0 = smem_u32(op_hi(ob)), bl0 = bh0 + a_bytes;
                 uint32_t acc = 0;
                 for (int s = 0; s < KB * 4; ++s) {
-                    const uint32_t wo = static_cast<uint32_t>(s >> 2) * (kTbM * 128u) + static_cast<uint32_t>(s & 3) * 32u;
-                    const uint32_t ao = static_cast<uint32_t>(s >> 2) * (kTbNT * 128u) + static_cast<uint32_t>(s & 3) * 32u;
-                    const uint64_t whd = tc::make_desc_sw128(smem_u32(w_hi) + wo, 16, 1024);
-                    const uint64_t wld = tc::make_desc_sw128(smem_u32(w_lo) + wo, 16, 1024);
-                    const uint64_t ahd = tc::make_desc_sw128(smem_u32(a_hi) + ao, 16, 1024);
-                    const uint64_t ald = tc::make_desc_sw128(smem_u32(a_lo) + ao, 16, 1024);
-                    tc::mma_tf32(d, whd, ahd, idesc, acc);
-                    tc::mma_tf32(d, whd, ald, idesc, 1);
-                    tc::mma_tf32(d, wld, ahd, idesc, 1);
+                    const uint32_t bo = static_cast<uint32_t>(s >> 2) * (kTbNT * 128u) + static_cast<uint32_t>(s & 3) * 32u;
+                    const uint64_t bhd = tc::make_desc_sw128(bh0 + bo, 16, 1024);
+                    const uint64_t bld = tc::make_desc_sw128(bl0 + bo, 16, 1024);
+                    const uint32_t wh = tmem_base + kTbWCol + static_cast<uint32_t>(s * 8), wl = wh + Kp;
+                    tc::mma_tf32_ts(d, wh, bhd, idesc, acc);
+                    tc::mma_tf32_ts(d, wh, bld, idesc, 1);
+                    tc::mma_tf32_ts(d, wl, bhd, idesc, 1);
                     acc = 1;
                 }
-                tc::mma_commit(&bar_empty);
-                tc::mma_commit(&bar_tfull[buf]);
+                tc::mma_commit(&bar_empty[ob]);
+                tc::mma_commit(&bar_tfull[tb]);
             }
         }
     } else {
         // ================================ epilogue: thread = input channel r ============================
         const int r = tid;
         const bool valid = r < q.rows;
+        const bool mask = !SCATTER && q.final;
         float sc = 0.f, sh = 0.f, mu = 0.f, rs = 0.f;
-        if (!SCATTER && q.final && valid) {
+        if (mask && valid) {
             const int g = r / (q.rows / kGnGroups);
             sc = __ldg(q.ss_prev + (static_cast<size_t>(b) * q.rows + r) * 2);
             sh = __ldg(q.ss_prev + (static_cast<size_t>(b) * q.rows + r) * 2 + 1);
@@ -159,11 +224,22 @@ mlp_dx_tc_kernel(MlpDxTcParams q) {
             rs = __ldg(q.mean_rstd_prev + (b * kGnGroups + g) * 2 + 1);
         }
         double dsum = 0.0, dsumy = 0.0;
-        int use = 0;
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++use) {
-            const int buf = use & 1;
-            const int p0 = t * kTbNT;
-            mbar_wait(&bar_tfull[buf], (use >> 1) & 1);
+        for (int u = 0; u < n_my; ++u) {
+            const int buf = u & 1;
+            const int p0 = (blockIdx.x + u * gridDim.x) * kTbNT;
+            // issue this tile's y_prev row reads (ReLU mask) BEFORE waiting for the accumulator
+            float4 y4[kTbNT / 4];
+            if (mask && valid) {
+                const float4 *yp = reinterpret_cast<const float4 *>(q.y_prev + (static_cast<size_t>(b) * q.rows + r) * P + p0);
+#pragma unroll
+                for (int j = 0; j < kTbNT / 4; ++j) y4[j] = __ldg(yp + j);
+            }
+            int j_lo = 0, j_hi = 0;                      // scatter: lane l holds the neighbour index of positions l, l + 32
+            if (SCATTER) {
+                j_lo = __ldg(q.idx + static_cast<size_t>(b) * P + p0 + lane);
+                j_hi = __ldg(q.idx + static_cast<size_t>(b) * P + p0 + 32 + lane);
+            }
+            mbar_wait(&bar_tfull[buf], (u >> 1) & 1);
             tc::fence_after_sync();
             float v[kTbNT];
             {
@@ -180,8 +256,9 @@ mlp_dx_tc_kernel(MlpDxTcParams q) {
             mbar_arrive(&bar_tempty[buf]);
             if (SCATTER) {
                 // 32 lanes = 32 consecutive feature channels of the same point: one coalesced red per position
+#pragma unroll
                 for (int j = 0; j < kTbNT; ++j) {
-                    const int pt = __ldg(q.idx + static_cast<size_t>(b) * P + p0 + j);
+                    const int pt = __shfl_sync(OGC_FULL_MASK, j < 32 ? j_lo : j_hi, j & 31);
                     if (valid) atomicAdd(q.dfeat_pm + (static_cast<size_t>(b) * q.N + pt) * q.dfeat_stride + q.dfeat_off + r, v[j]);
                 }
                 continue;
@@ -196,12 +273,10 @@ mlp_dx_tc_kernel(MlpDxTcParams q) {
                 }
             }
             if (q.final) {
-                const float4 *yp = reinterpret_cast<const float4 *>(q.y_prev + (static_cast<size_t>(b) * q.rows + r) * P + p0);
                 float s = 0.f, sy = 0.f;
 #pragma unroll
                 for (int j = 0; j < kTbNT / 4; ++j) {
-                    const float4 y4 = __ldg(yp + j);
-                    const float yy[4] = {y4.x, y4.y, y4.z, y4.w};
+                    const float yy[4] = {y4[j].x, y4[j].y, y4[j].z, y4[j].w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const float g = fmaf(sc, yy[e], sh) > 0.f ? v[4 * j + e] : 0.f;
@@ -216,7 +291,7 @@ mlp_dx_tc_kernel(MlpDxTcParams q) {
 #pragma unroll
             for (int j = 0; j < kTbNT / 4; ++j) dp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
-        if (!SCATTER && q.final && valid) {
+        if (mask && valid) {
             atomicAdd(q.dbeta_prev + r, static_cast<float>(dsum));
             atomicAdd(q.dgamma_prev + r, static_cast<float>(dsumy));
             const int g = r / (q.rows / kGnGroups);
@@ -225,12 +300,28 @@ mlp_dx_tc_kernel(MlpDxTcParams q) {
             atomicAdd(&gs[g][1], gm * dsumy);
         }
         named_bar_sync(1, 128);
-        if (!SCATTER && q.final && tid < kGnGroups * 2)
+        if (mask && tid < kGnGroups * 2)
             atomicAdd(q.ab_prev + static_cast<size_t>(b) * kGnGroups * 2 + tid, (&gs[0][0])[tid]);
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == kTbMmaWarp) tc::tmem_dealloc(tmem_base, 128);
+    if (warp == kTbMmaWarp) tc::tmem_dealloc(tmem_base, 512);
+}
+
+static inline bool tc_dx_plan(int kn, bool synth, int &n_raw, int &n_op, int &stage, size_t &smem) {
+    const int KB = (kn + 31) / 32;
+    const size_t op = static_cast<size_t>(KB) * kTbNT * 128 * 2;
+    stage = kn * (kTbNT * 4 + kTbRowPad) * (synth ? 1 : 2);
+    stage = (stage + 127) & ~127;
+    const size_t budget = static_cast<size_t>(kMaxSmemPerCta) - 8 * 1024 - 1024;
+    for (n_op = 2; n_op >= 1; --n_op) {
+        if (op * n_op + 2 * static_cast<size_t>(stage) > budget) continue;
+        n_raw = static_cast<int>((budget - op * n_op) / stage);
+        n_raw = n_raw > 4 ? 4 : n_raw;
+        smem = op * n_op + static_cast<size_t>(n_raw) * stage + 1024;
+        return true;
+    }
+    return false;
 }
 
 // ------------------------------------------------------------------------------------------------ dW
@@ -481,8 +572,8 @@ extern "C" int ogc_sa_mlp_layer_dx_tc(int b, int n, int m, int nsample, int cout
         q.kn = cout - k0 < kTbM ? cout - k0 : kTbM;
         q.add_partial = k0 > 0;
         q.final = k0 + kTbM >= cout;
-        const int KB = (q.kn + 31) / 32;
-        const size_t smem = static_cast<size_t>(KB) * (kTbM + kTbNT) * 128 * 2 + 1024;
+        size_t smem = 0;
+        if (!tc_dx_plan(q.kn, dz == nullptr, q.n_raw, q.n_op, q.raw_stage_bytes, smem)) return OGC_ERR_UNSUPPORTED;
         cudaError_t e;
         if (scatter) {
             e = cudaFuncSetAttribute(mlp_dx_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));

@@ -8,6 +8,8 @@ namespace ogc {
 
 // mode 0: A (128,K) row-major, B (N,K) row-major (both K-major operands):   D = A B^T
 // mode 1: A (K,128) row-major, B (K,N) row-major (both MN-major operands):  D = A^T B
+// mode 2: as mode 0, but A is first written to TENSOR MEMORY (tcgen05.st, lane = row, column = k; hi then lo) and the
+//         MMAs read it from there (the .ts form used by the fused MLP kernels for the stationary weight operand)
 __global__ void __launch_bounds__(128)
 tc_probe_kernel(int mode, int N, int K, int split3, const float *__restrict__ A, const float *__restrict__ B,
                 float *__restrict__ D) {
@@ -22,16 +24,17 @@ tc_probe_kernel(int mode, int N, int K, int split3, const float *__restrict__ A,
     uint8_t *a_hi = smem, *b_hi = a_hi + a_bytes, *a_lo = b_hi + b_bytes, *b_lo = a_lo + a_bytes;
 
     uint32_t ncols = 32;
-    while (ncols < static_cast<uint32_t>(N)) ncols <<= 1;
+    while (ncols < static_cast<uint32_t>(N) + (mode == 2 ? 2u * K : 0u)) ncols <<= 1;
+    const uint32_t a_col = static_cast<uint32_t>(N);      // TMEM column of A_hi (mode 2); A_lo follows at +K
     if (warp == 0) tc::tmem_alloc(&tmem_base_s, ncols);
     if (tid == 0) {
         mbar_init(&bar, 1);
         mbar_fence_init();
     }
     // ---- fill the operand tiles ----
-    if (mode == 0) {
+    if (mode == 0 || mode == 2) {
         // column blocks over K: block kb = [rows][32], rows = M (A) or N (B)
-        for (int e = tid; e < M * K; e += blockDim.x) {
+        for (int e = tid; e < M * K && mode == 0; e += blockDim.x) {
             const int r = e / K, k = e - r * K;
             const float v = A[e], hi = split3 ? tc::tf32_hi(v) : v;
             const uint32_t off = static_cast<uint32_t>(k >> 5) * (M * 128u) + tc::sw128_offset(r, k & 31);
@@ -67,8 +70,43 @@ tc_probe_kernel(int mode, int N, int K, int split3, const float *__restrict__ A,
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = tmem_base_s;
+    if (mode == 2) {
+        // thread = row of A: 32 columns per store
+        for (int k0 = 0; k0 < K; k0 += 32) {
+            float hi[32], lo[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float v = A[tid * K + k0 + j];
+                hi[j] = split3 ? tc::tf32_hi(v) : v;
+                lo[j] = tc::tf32_hi(v - hi[j]);
+            }
+            const uint32_t ta = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + a_col + static_cast<uint32_t>(k0);
+            tc::tmem_st32(ta, hi);
+            if (split3) tc::tmem_st32(ta + static_cast<uint32_t>(K), lo);
+        }
+        tc::fence_before_sync();
+        __syncthreads();
+        tc::fence_after_sync();
+    }
 
-    if (tid == 0) {
+    if (tid == 0 && mode == 2) {
+        const uint32_t idesc = tc::make_idesc_tf32(M, N, 0, 0);
+        uint32_t acc = 0;
+        for (int s = 0; s < K / 8; ++s) {
+            const uint32_t b_off = static_cast<uint32_t>(s >> 2) * (N * 128u) + static_cast<uint32_t>(s & 3) * 32u;
+            const uint64_t bh = tc::make_desc_sw128(smem_u32(b_hi) + b_off, 16, 1024);
+            const uint64_t bl = tc::make_desc_sw128(smem_u32(b_lo) + b_off, 16, 1024);
+            const uint32_t ah = tmem_base + a_col + static_cast<uint32_t>(s * 8), al = ah + static_cast<uint32_t>(K);
+            tc::mma_tf32_ts(tmem_base, ah, bh, idesc, acc);
+            if (split3) {
+                tc::mma_tf32_ts(tmem_base, ah, bl, idesc, 1);
+                tc::mma_tf32_ts(tmem_base, al, bh, idesc, 1);
+            }
+            acc = 1;
+        }
+        tc::mma_commit(&bar);
+    }
+    if (tid == 0 && mode != 2) {
         const uint32_t idesc = tc::make_idesc_tf32(M, N, mode, mode);
         const int ksteps = K / 8;
         uint32_t acc = 0;
@@ -115,6 +153,7 @@ extern "C" int ogc_tc_probe_gemm(int mode, int n, int k, int split3, const float
                                  void *stream) {
     using namespace ogc;
     if (n < 32 || n > 256 || n % 32 != 0 || k < 32 || k % 32 != 0 || !a || !b || !d) return OGC_ERR_INVALID_ARG;
+    if (mode == 2 && n + 2 * k > 512) return OGC_ERR_UNSUPPORTED;
     const size_t smem = static_cast<size_t>(split3 ? 2 : 1) * (128 + n) * k * 4 + 1024;
     if (smem > static_cast<size_t>(kMaxSmemPerCta)) return OGC_ERR_UNSUPPORTED;
     cudaError_t e = cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));

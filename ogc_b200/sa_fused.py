@@ -21,7 +21,7 @@ USE_TC = True   # tcgen05 3xTF32 kernels for the layers they cover (tests flip i
 
 def _tc_ok(S, cin, cout, gather):
     k = cin - 3 if gather else cin
-    return USE_TC and S == 64 and cout >= 64 and cout % 16 == 0 and cout <= 256 and 32 <= k <= 160 and k % 4 == 0
+    return USE_TC and S == 64 and cout >= 64 and cout % 16 == 0 and cout <= 256 and 32 <= k <= 128 and k % 4 == 0
 
 
 TC_DW_ALL = False   # tests: route every supported dW through the tensor-core kernel

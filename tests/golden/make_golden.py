@@ -92,7 +92,19 @@ def main():
             for k, v in d.items():
                 out["dict:" + k] = np.float32(v)
             for pname in case["grad_params"]:
-                out["grad:" + pname] = dict(ref.named_parameters())[pname].grad.numpy()
+                out["grad:" + pname] = dict(ref.named_parameters())[pname].grad.numpy().copy()
+            # the same with 2 unrolled iterations: the GPU parity case (iteration 3 re-runs kNN on a cloud warped by
+            # iteration 2's output and amplifies 1e-5 differences to 1e-2 -- seen between two fp32 CPU runs)
+            ref.zero_grad()
+            preds = ref(inp["pc1"], inp["pc2"], inp["pc1"], inp["pc2"], iters=2)
+            crit.iters_w = cfg["iters_w"][:2]
+            loss, d = crit(inp["pc1"], inp["pc2"], preds)
+            loss.backward()
+            out["i2:loss"] = np.float32(loss.item())
+            for k, v in d.items():
+                out["i2:dict:" + k] = np.float32(v)
+            for pname in case["grad_params"]:
+                out["i2:grad:" + pname] = dict(ref.named_parameters())[pname].grad.numpy().copy()
         elif case["kind"] == "oa_icp":
             # The reference's own oa_icp.object_aware_icp evaluated in FLOAT64 (its fp32 cdist is ill-conditioned:
             # SURVEY.md 7, hard part 8).  tensorboardX / metrics imports are stubbed; the k-NN index lookup inside

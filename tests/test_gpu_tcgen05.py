@@ -53,3 +53,17 @@ def test_3xtf32_is_fp32_grade(mode):
     assert e1 > 1e-3          # single-pass TF32 is NOT accurate enough for the 1e-4 logit parity ...
     print(f'single-pass {e1:.2e}  3xTF32 {e3:.2e}  fp32 {e32:.2e}')
     assert e3 < 4 * e32 + 1e-6   # ... the 3-pass split is at the level of an fp32 GEMM (measured: 2.6-3.1x cuBLAS sgemm's error)
+
+
+@pytest.mark.parametrize("n,k", [(32, 32), (64, 128), (64, 96), (128, 64)])
+def test_a_operand_from_tensor_memory(n, k):
+    """The .ts form: A written to TMEM with tcgen05.st (lane = row, column = k), B K-major in shared memory."""
+    torch.manual_seed(n + 7 * k)
+    a = torch.randint(-8, 9, (128, k), device="cuda").float()
+    b = torch.randint(-8, 9, (n, k), device="cuda").float()
+    assert torch.equal(run(2, n, k, 0, a, b), a @ b.t())
+    a, b = torch.randn(128, k, device="cuda"), torch.randn(n, k, device="cuda")
+    ref = a.double() @ b.double().t()
+    e3 = float((run(2, n, k, 1, a, b).double() - ref).abs().max())
+    e32 = float(((a @ b.t()).double() - ref).abs().max())
+    assert e3 < 4 * e32 + 1e-6, (e3, e32)
