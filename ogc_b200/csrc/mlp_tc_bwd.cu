@@ -333,178 +333,273 @@ struct MlpDwTcParams {
     const int *idx;
     int N, Cf;
     float *dW;                    // (Cout, Cin) accumulated with red.add
+    int n_raw, raw_stage_bytes;
 };
 
 constexpr int kDwTile = 32;       // positions per pipeline stage = one 128-byte row of every operand
-constexpr int kDwStages = 2;
+constexpr int kDwPitch = kDwTile * 4 + 16;   // raw row pitch (16-byte reads of consecutive rows at a 4-bank skew)
+constexpr int kDwAccCols = 192;   // accumulator: up to 160 columns; dY operand buffers follow
+constexpr int kDwMaxCin = 160;
 
-// K = positions.  Both operands K-major with rows = channels: a row is 32 consecutive positions of one channel,
-// i.e. 128 contiguous bytes of the channel-major tensors -> float4 loads, 16-byte swizzled stores, no transposition
-// (only the gathered a_0 of layer 1 is built point by point).  a-tile row order: dense: ci; gather: [feat, xyz].
+// K = positions.  Per stage (32 positions of one sample):
+//   raw ring (cp.async, D stages ahead): y_l and dz_l rows of this M block's channels, and the layer's input -- the
+//       previous layer's pre-norm rows, or the gathered feature rows + xyz of the stage's 32 neighbours
+//   A = dY (128 channels x 32 positions, hi and lo): thread = channel builds its row from the raw rows and its four
+//       GroupNorm-backward coefficients and writes it straight to TENSOR MEMORY (tcgen05.st) -- no shared memory
+//   B = a  (C_in rows x 32 positions, K-major 128 B rows, hi and lo) in shared memory, double buffered
+//   ONE accumulator (128 x C_in) per CTA in TMEM over all its stages, read out once and red.add'ed into dW.
+// a-tile row order: dense: ci; gather: [feat, xyz].
 template <bool GATHER>
 __global__ void __launch_bounds__(kTbThreads, 1)
 mlp_dw_tc_kernel(MlpDwTcParams q) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_full[kDwStages], bar_empty[kDwStages], bar_done;
+    __shared__ __align__(8) uint64_t bar_full[2], bar_empty[2], bar_done;
     __shared__ uint32_t tmem_base_s;
+    __shared__ float2 ss_s[2][kDwMaxCin];      // GroupNorm (scale, shift) of the input channels for the stage's sample
+    __shared__ int idx_s[2][kDwTile];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int mb = blockIdx.y;
     const int P = q.dy.P, Cout = q.dy.C;
     const int tiles_per_sample = P / kDwTile;
     const int total = q.B * tiles_per_sample;
+    const int n_my = total > static_cast<int>(blockIdx.x) ? (total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int nrows_a = GATHER ? q.Cf + 3 : q.Cin;              // valid rows of the a tile
     const int n_mma = ((nrows_a + 15) / 16) * 16;                // MMA N (rows of B), <= 160
     const int a_rows_alloc = ((n_mma + 7) / 8) * 8;
+    const int m_rows = min(kTbM, Cout - mb * kTbM);              // valid channels of this M block
+    const int n_raw = q.n_raw, D = n_raw - 1;
+    const bool synth = q.dy.dz == nullptr;
 
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const uint32_t dy_bytes = kTbM * 128u, a_bytes = static_cast<uint32_t>(a_rows_alloc) * 128u;
-    const uint32_t stage_bytes = 2 * dy_bytes + 2 * ((a_bytes + 1023u) & ~1023u);
-    auto dy_hi = [&](int s) { return smem + s * stage_bytes; };
-    auto dy_lo = [&](int s) { return smem + s * stage_bytes + dy_bytes; };
-    auto a_hi = [&](int s) { return smem + s * stage_bytes + 2 * dy_bytes; };
-    auto a_lo = [&](int s) { return smem + s * stage_bytes + 2 * dy_bytes + ((a_bytes + 1023u) & ~1023u); };
+    const uint32_t a_bytes = (static_cast<uint32_t>(a_rows_alloc) * 128u + 1023u) & ~1023u;
+    auto a_hi = [&](int ob) { return smem + static_cast<size_t>(ob) * 2 * a_bytes; };
+    uint8_t *raw_base = smem + 4 * static_cast<size_t>(a_bytes);
+    auto raw_stage = [&](int u) { return raw_base + static_cast<size_t>(u % n_raw) * q.raw_stage_bytes; };
+    const uint32_t dz_off = static_cast<uint32_t>(m_rows) * kDwPitch;
+    const uint32_t in_off = dz_off * (synth ? 1u : 2u);                      // input rows follow y (and dz)
+    const uint32_t g_pitch = static_cast<uint32_t>(q.Cf) * 4u + 16u;         // gather: one neighbour's features
+    const uint32_t xyz_off = in_off + kDwTile * g_pitch;
 
-    if (warp == kTbMmaWarp) tc::tmem_alloc(&tmem_base_s, 256);
+    if (warp == kTbMmaWarp) tc::tmem_alloc(&tmem_base_s, 512);
     if (tid == 0) {
-        for (int s = 0; s < kDwStages; ++s) { mbar_init(&bar_full[s], kTbLoaders); mbar_init(&bar_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&bar_full[s], kTbLoaders); mbar_init(&bar_empty[s], 1); }
         mbar_init(&bar_done, 1);
         mbar_fence_init();
     }
+    for (uint32_t e = tid * 16u; e < 4 * a_bytes; e += kTbThreads * 16u)     // padding rows stay zero for the CTA's lifetime
+        *reinterpret_cast<float4 *>(smem + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+    tc::fence_proxy_async();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = tmem_base_s;
 
+    const int lt = tid - 128;
+    auto stage_of = [&](int u, int &b, int &p0) {
+        const int w = blockIdx.x + u * gridDim.x;
+        b = w / tiles_per_sample;
+        p0 = (w - b * tiles_per_sample) * kDwTile;
+    };
+    auto issue = [&](int u) {
+        int b, p0;
+        stage_of(u, b, p0);
+        uint8_t *st = raw_stage(u);
+        const size_t ybase = (static_cast<size_t>(b) * Cout + mb * kTbM) * P + p0;
+        for (int it = lt; it < m_rows * 8; it += kTbLoaders) {
+            const int c = it >> 3, ch = it & 7;
+            cp_async16(st + c * kDwPitch + ch * 16, q.dy.y + ybase + static_cast<size_t>(c) * P + ch * 4);
+            if (!synth) cp_async16(st + dz_off + c * kDwPitch + ch * 16, q.dy.dz + ybase + static_cast<size_t>(c) * P + ch * 4);
+        }
+        if (GATHER) {
+            const int *js = idx_s[u & 1];
+            const int cpr = q.Cf >> 2;
+            for (int it = lt; it < kDwTile * cpr; it += kTbLoaders) {
+                const int p = it / cpr, ch = it - p * cpr;
+                cp_async16(st + in_off + p * g_pitch + ch * 16, q.feat_pm + (static_cast<size_t>(b) * q.N + js[p]) * q.Cf + ch * 4);
+            }
+            if (lt < kDwTile * 3) {
+                const int p = lt / 3, c = lt - p * 3;
+                cp_async4(st + xyz_off + lt * 4, q.xyz + (static_cast<size_t>(b) * q.N + js[p]) * 3 + c);
+            } else if (lt < kDwTile * 3 + 3) {
+                const int c = lt - kDwTile * 3;
+                cp_async4(st + xyz_off + lt * 4, q.new_xyz + (static_cast<size_t>(b) * q.dy.M + p0 / q.dy.S) * 3 + c);
+            }
+        } else {
+            const size_t abase = static_cast<size_t>(b) * q.Cin * P + p0;
+            for (int it = lt; it < q.Cin * 8; it += kTbLoaders) {
+                const int c = it >> 3, ch = it & 7;
+                cp_async16(st + in_off + c * kDwPitch + ch * 16, q.y_prev + abase + static_cast<size_t>(c) * P + ch * 4);
+            }
+        }
+    };
+    auto load_idx = [&](int u) {
+        int b, p0;
+        stage_of(u, b, p0);
+        return (GATHER && lt < kDwTile && u < n_my) ? __ldg(q.idx + static_cast<size_t>(b) * P + p0 + lt) : 0;
+    };
+    auto load_ss = [&](int u) {      // thread lt < Cin: (scale, shift) of input channel lt for stage u's sample
+        int b, p0;
+        stage_of(u, b, p0);
+        return (!GATHER && lt < q.Cin && u < n_my) ? __ldg(reinterpret_cast<const float2 *>(q.ss_prev) + static_cast<size_t>(b) * q.Cin + lt)
+                                                  : make_float2(0.f, 0.f);
+    };
+    // this thread's dY row: channel co (TMEM lane), 16 of the stage's 32 positions
+    const int lq = warp & 3;                                     // TMEM lane quarter this warp may access
+    const int chalf = (warp - 4) >> 2;                           // 0: positions 0-15, 1: positions 16-31
+    const int row = lq * 32 + lane, co = mb * kTbM + row;
+    auto load_coef = [&](int u) {
+        int b, p0;
+        stage_of(u, b, p0);
+        return (co < Cout && u < n_my) ? __ldg(reinterpret_cast<const float4 *>(q.dy.coef) + static_cast<size_t>(b) * Cout + co)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    auto load_selgo = [&](int u) {
+        float2 r = make_float2(255.f, 0.f);
+        if (synth && co < Cout && u < n_my) {
+            int b, p0;
+            stage_of(u, b, p0);
+            const int m = p0 / q.dy.S;
+            r.x = static_cast<float>(__ldg(q.dy.sel + (static_cast<size_t>(b) * Cout + co) * q.dy.M + m));
+            r.y = __ldg(q.dy.go + (static_cast<size_t>(b) * q.dy.go_ctotal + q.dy.go_coff + co) * q.dy.M + m);
+        }
+        return r;
+    };
+
     if (warp >= 4 && warp < kTbMmaWarp) {
-        const int lt = tid - 128, lw = warp - 4;
-        int use = 0;
-        for (int w = blockIdx.x; w < total; w += gridDim.x, ++use) {
-            const int st = use % kDwStages, ph = (use / kDwStages) & 1;
-            const int b = w / tiles_per_sample, p0 = (w - b * tiles_per_sample) * kDwTile;
-            mbar_wait(&bar_empty[st], ph ^ 1);
-            uint8_t *dh = dy_hi(st), *dl = dy_lo(st), *ah = a_hi(st), *al = a_lo(st);
-            // ---- dY tile: row = output channel of this M block, 8 quads of 4 positions per row ----
+        // ================================ transformers ================================
+        for (int d = 0; d < D; ++d) {
+            if (GATHER) {
+                const int j = load_idx(d);
+                if (lt < kDwTile) idx_s[d & 1][lt] = j;
+                named_bar_sync(kTbXfBar, kTbLoaders);
+            }
+            if (d < n_my) issue(d);
+            cp_async_commit();
+        }
+        if (GATHER) {
+            const int j = load_idx(D);
+            named_bar_sync(kTbXfBar, kTbLoaders);
+            if (lt < kDwTile) idx_s[D & 1][lt] = j;
+        } else if (lt < q.Cin) {
+            ss_s[0][lt] = load_ss(0);
+        }
+        float4 cf = load_coef(0);
+        float2 sg = load_selgo(0);
+        for (int u = 0; u < n_my; ++u) {
+            const int ob = u & 1;
+            cp_async_wait(D - 1);
+            named_bar_sync(kTbXfBar, kTbLoaders);          // stage u landed everywhere; transform u-1 finished everywhere
+            if (u + D < n_my) issue(u + D);
+            cp_async_commit();
+            const int jn = load_idx(u + D + 1);
+            const float2 ssn = load_ss(u + 1);
+            const float4 cfn = load_coef(u + 1);
+            const float2 sgn = load_selgo(u + 1);
+            mbar_wait(&bar_empty[ob], ((u >> 1) & 1) ^ 1);  // the MMAs that read operand buffers `ob` are done
+            const uint8_t *st = raw_stage(u);
+            int b, p0;
+            stage_of(u, b, p0);
+            // ---- dY row -> tensor memory ----
             {
-                constexpr int DU = 1024 / kTbLoaders;        // 1024 items = 128 rows x 8 quads
-                DyRaw raw[DU];
+                float hi[16], lo[16];
+                if (row < m_rows) {
+                    const float4 *yr = reinterpret_cast<const float4 *>(st + row * kDwPitch + chalf * 64);
+                    const float4 *zr = reinterpret_cast<const float4 *>(st + dz_off + row * kDwPitch + chalf * 64);
+                    const int s0 = p0 % q.dy.S + chalf * 16;        // position of column 0 inside its centre's group
 #pragma unroll
-                for (int u = 0; u < DU; ++u) {
-                    const int it = lt + kTbLoaders * u;
-                    const int row = it >> 3, pq = it & 7;
-                    const int co = mb * kTbM + row;
-                    if (co < Cout) dy_quad_load(q.dy, b, co, p0 + pq * 4, raw[u]);
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 y4 = yr[i];
+                        float4 z4;
+                        if (synth) {
+                            const int sl = static_cast<int>(sg.x) - s0 - 4 * i;
+                            z4 = make_float4(sl == 0 ? sg.y : 0.f, sl == 1 ? sg.y : 0.f, sl == 2 ? sg.y : 0.f, sl == 3 ? sg.y : 0.f);
+                        } else {
+                            z4 = zr[i];
+                        }
+                        const float yy[4] = {y4.x, y4.y, y4.z, y4.w}, zz[4] = {z4.x, z4.y, z4.z, z4.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float v = fmaf(cf.x, zz[e], -cf.y) - (yy[e] - cf.w) * cf.z;
+                            hi[4 * i + e] = tc::tf32_hi(v);
+                            lo[4 * i + e] = tc::tf32_hi(v - hi[4 * i + e]);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) hi[i] = lo[i] = 0.f;
                 }
+                const uint32_t ta = tmem_base + (static_cast<uint32_t>(lq * 32) << 16) + kDwAccCols + ob * 64 + chalf * 16;
+                tc::tmem_st16(ta, hi);
+                tc::tmem_st16(ta + 32, lo);
+            }
+            // ---- a tile: row = input channel, 128 B = the stage's 32 positions ----
+            uint8_t *ah = a_hi(ob), *al = ah + a_bytes;
+            if (GATHER) {
+                for (int it = lt; it < q.Cf * 8; it += kTbLoaders) {
+                    const int pq = it / q.Cf, c = it - pq * q.Cf;
+                    float v[4];
 #pragma unroll
-                for (int u = 0; u < DU; ++u) {
-                    const int it = lt + kTbLoaders * u;
-                    const int row = it >> 3, pq = it & 7;
-                    const int co = mb * kTbM + row;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (co < Cout) v = dy_quad_finish(q.dy, p0 + pq * 4, raw[u]);
+                    for (int e = 0; e < 4; ++e) v[e] = *reinterpret_cast<const float *>(st + in_off + (pq * 4 + e) * g_pitch + c * 4);
+                    const float4 hi = make_float4(tc::tf32_hi(v[0]), tc::tf32_hi(v[1]), tc::tf32_hi(v[2]), tc::tf32_hi(v[3]));
+                    const float4 lo = make_float4(tc::tf32_hi(v[0] - hi.x), tc::tf32_hi(v[1] - hi.y), tc::tf32_hi(v[2] - hi.z),
+                                                  tc::tf32_hi(v[3] - hi.w));
+                    const uint32_t off = static_cast<uint32_t>(c) * 128u + static_cast<uint32_t>((pq ^ (c & 7)) * 16);
+                    *reinterpret_cast<float4 *>(ah + off) = hi;
+                    *reinterpret_cast<float4 *>(al + off) = lo;
+                }
+                if (lt < kDwTile * 3) {
+                    const int c = lt >> 5, p = lt & 31;
+                    const float *xs = reinterpret_cast<const float *>(st + xyz_off);
+                    const float v = xs[p * 3 + c] - xs[kDwTile * 3 + c];
+                    const float hi = tc::tf32_hi(v);
+                    const uint32_t off = tc::sw128_offset(q.Cf + c, p);
+                    *reinterpret_cast<float *>(ah + off) = hi;
+                    *reinterpret_cast<float *>(al + off) = tc::tf32_hi(v - hi);
+                }
+            } else {
+                const float2 *ss = ss_s[u & 1];
+                for (int it = lt; it < q.Cin * 8; it += kTbLoaders) {
+                    const int r = it >> 3, pq = it & 7;
+                    const float4 x = *reinterpret_cast<const float4 *>(st + in_off + r * kDwPitch + pq * 16);
+                    const float2 s2 = ss[r];
+                    const float4 v = make_float4(fmaxf(fmaf(s2.x, x.x, s2.y), 0.f), fmaxf(fmaf(s2.x, x.y, s2.y), 0.f),
+                                                 fmaxf(fmaf(s2.x, x.z, s2.y), 0.f), fmaxf(fmaf(s2.x, x.w, s2.y), 0.f));
                     const float4 hi = make_float4(tc::tf32_hi(v.x), tc::tf32_hi(v.y), tc::tf32_hi(v.z), tc::tf32_hi(v.w));
                     const float4 lo = make_float4(tc::tf32_hi(v.x - hi.x), tc::tf32_hi(v.y - hi.y), tc::tf32_hi(v.z - hi.z),
                                                   tc::tf32_hi(v.w - hi.w));
-                    const uint32_t off = static_cast<uint32_t>(row) * 128u + static_cast<uint32_t>((pq ^ (row & 7)) * 16);
-                    *reinterpret_cast<float4 *>(dh + off) = hi;
-                    *reinterpret_cast<float4 *>(dl + off) = lo;
-                }
-            }
-            // ---- a tile: row = input channel ----
-            if (GATHER) {
-                // point-major source: lane <-> channel, one position at a time (transposing 4-byte stores)
-                const int jl = __ldg(q.idx + static_cast<size_t>(b) * P + p0 + lane);
-                const int nblk = (nrows_a + 31) / 32;
-                const int nitems = kDwTile * nblk;
-                for (int it0 = lw; it0 < nitems; it0 += kTbLoaderWarps * 8) {
-                    float vals[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int it = it0 + kTbLoaderWarps * u;
-                        const int p = it / nblk, cb = it - p * nblk;
-                        const int j = __shfl_sync(OGC_FULL_MASK, jl, p & 31);
-                        const int c = cb * 32 + lane;
-                        float v = 0.f;
-                        if (it < nitems) {
-                            if (c < q.Cf) v = __ldg(q.feat_pm + (static_cast<size_t>(b) * q.N + j) * q.Cf + c);
-                            else if (c < q.Cf + 3)
-                                v = __ldg(q.xyz + (static_cast<size_t>(b) * q.N + j) * 3 + (c - q.Cf)) -
-                                    __ldg(q.new_xyz + (static_cast<size_t>(b) * q.dy.M + (p0 + p) / q.dy.S) * 3 + (c - q.Cf));
-                        }
-                        vals[u] = v;
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int it = it0 + kTbLoaderWarps * u;
-                        const int p = it / nblk, cb = it - p * nblk;
-                        const int c = cb * 32 + lane;
-                        if (it < nitems && c < a_rows_alloc) {
-                            const float hi = tc::tf32_hi(vals[u]);
-                            const uint32_t off = tc::sw128_offset(c, p);
-                            *reinterpret_cast<float *>(ah + off) = hi;
-                            *reinterpret_cast<float *>(al + off) = tc::tf32_hi(vals[u] - hi);
-                        }
-                    }
-                }
-            } else {
-                const int nitems = a_rows_alloc * 8;
-                for (int it0 = lt; it0 < nitems; it0 += kTbLoaders * 8) {
-                    float4 raw[8];
-                    float scv[8], shv[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int it = it0 + kTbLoaders * u;
-                        const int row = it >> 3, pq = it & 7;
-                        raw[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        scv[u] = shv[u] = 0.f;
-                        if (it < nitems && row < q.Cin) {
-                            scv[u] = __ldg(q.ss_prev + (static_cast<size_t>(b) * q.Cin + row) * 2);
-                            shv[u] = __ldg(q.ss_prev + (static_cast<size_t>(b) * q.Cin + row) * 2 + 1);
-                            raw[u] = __ldg(reinterpret_cast<const float4 *>(q.y_prev + (static_cast<size_t>(b) * q.Cin + row) * P + p0 + pq * 4));
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int it = it0 + kTbLoaders * u;
-                        if (it >= nitems) continue;
-                        const int row = it >> 3, pq = it & 7;
-                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (row < q.Cin)
-                            v = make_float4(fmaxf(fmaf(scv[u], raw[u].x, shv[u]), 0.f), fmaxf(fmaf(scv[u], raw[u].y, shv[u]), 0.f),
-                                            fmaxf(fmaf(scv[u], raw[u].z, shv[u]), 0.f), fmaxf(fmaf(scv[u], raw[u].w, shv[u]), 0.f));
-                        const float4 hi = make_float4(tc::tf32_hi(v.x), tc::tf32_hi(v.y), tc::tf32_hi(v.z), tc::tf32_hi(v.w));
-                        const float4 lo = make_float4(tc::tf32_hi(v.x - hi.x), tc::tf32_hi(v.y - hi.y), tc::tf32_hi(v.z - hi.z),
-                                                      tc::tf32_hi(v.w - hi.w));
-                        const uint32_t off = static_cast<uint32_t>(row) * 128u + static_cast<uint32_t>((pq ^ (row & 7)) * 16);
-                        *reinterpret_cast<float4 *>(ah + off) = hi;
-                        *reinterpret_cast<float4 *>(al + off) = lo;
-                    }
+                    const uint32_t off = static_cast<uint32_t>(r) * 128u + static_cast<uint32_t>((pq ^ (r & 7)) * 16);
+                    *reinterpret_cast<float4 *>(ah + off) = hi;
+                    *reinterpret_cast<float4 *>(al + off) = lo;
                 }
             }
             tc::fence_proxy_async();
-            mbar_arrive(&bar_full[st]);
+            tc::fence_before_sync();
+            mbar_arrive(&bar_full[ob]);
+            if (GATHER) { if (lt < kDwTile) idx_s[(u + D + 1) & 1][lt] = jn; }
+            else if (lt < q.Cin) ss_s[(u + 1) & 1][lt] = ssn;     // read after the next barrier
+            cf = cfn;
+            sg = sgn;
         }
     } else if (warp == kTbMmaWarp) {
         if (lane == 0) {
             const uint32_t idesc = tc::make_idesc_tf32(kTbM, n_mma, 0, 0);
-            int use = 0;
             uint32_t acc = 0;
-            for (int w = blockIdx.x; w < total; w += gridDim.x, ++use) {
-                const int st = use % kDwStages, ph = (use / kDwStages) & 1;
-                mbar_wait(&bar_full[st], ph);
+            for (int u = 0; u < n_my; ++u) {
+                const int ob = u & 1;
+                mbar_wait(&bar_full[ob], (u >> 1) & 1);
                 tc::fence_after_sync();
-                for (int s = 0; s < kDwTile / 8; ++s) {     // 32 positions = 4 K-steps of 32 B inside the 128 B rows
-                    const uint32_t o = static_cast<uint32_t>(s) * 32u;
-                    const uint64_t dhd = tc::make_desc_sw128(smem_u32(dy_hi(st)) + o, 16, 1024);
-                    const uint64_t dld = tc::make_desc_sw128(smem_u32(dy_lo(st)) + o, 16, 1024);
-                    const uint64_t ahd = tc::make_desc_sw128(smem_u32(a_hi(st)) + o, 16, 1024);
-                    const uint64_t ald = tc::make_desc_sw128(smem_u32(a_lo(st)) + o, 16, 1024);
-                    tc::mma_tf32(tmem_base, dhd, ahd, idesc, acc);
-                    tc::mma_tf32(tmem_base, dhd, ald, idesc, 1);
-                    tc::mma_tf32(tmem_base, dld, ahd, idesc, 1);
+                const uint32_t ah0 = smem_u32(a_hi(ob)), al0 = ah0 + a_bytes;
+                const uint32_t dh0 = tmem_base + kDwAccCols + ob * 64, dl0 = dh0 + 32;
+                for (int s = 0; s < kDwTile / 8; ++s) {     // 32 positions = 4 K-steps: 32 B of every a row, 8 dY columns
+                    const uint64_t ahd = tc::make_desc_sw128(ah0 + s * 32, 16, 1024);
+                    const uint64_t ald = tc::make_desc_sw128(al0 + s * 32, 16, 1024);
+                    tc::mma_tf32_ts(tmem_base, dh0 + s * 8, ahd, idesc, acc);
+                    tc::mma_tf32_ts(tmem_base, dh0 + s * 8, ald, idesc, 1);
+                    tc::mma_tf32_ts(tmem_base, dl0 + s * 8, ahd, idesc, 1);
                     acc = 1;
                 }
-                tc::mma_commit(&bar_empty[st]);
+                tc::mma_commit(&bar_empty[ob]);
             }
             tc::mma_commit(&bar_done);
         }
@@ -512,23 +607,41 @@ mlp_dw_tc_kernel(MlpDwTcParams q) {
         // epilogue: wait for every MMA of this CTA, then lane = output channel adds its row of dW
         mbar_wait(&bar_done, 0);
         tc::fence_after_sync();
-        const int co = mb * kTbM + tid;
-        for (int c0 = 0; c0 < n_mma; c0 += 32) {
-            float h[32];
-            tc::tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(c0), h);
-            if (co >= Cout) continue;
+        const int eco = mb * kTbM + tid;
+        if (n_my > 0) {
+            for (int c0 = 0; c0 < n_mma; c0 += 32) {
+                float h[32];
+                tc::tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(c0), h);
+                if (eco >= Cout) continue;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int c = c0 + j;
-                if (c >= nrows_a) continue;
-                const int ci = GATHER ? (c < q.Cf ? 3 + c : c - q.Cf) : c;
-                atomicAdd(q.dW + static_cast<size_t>(co) * q.Cin + ci, h[j]);
+                for (int j = 0; j < 32; ++j) {
+                    const int c = c0 + j;
+                    if (c >= nrows_a) continue;
+                    const int ci = GATHER ? (c < q.Cf ? 3 + c : c - q.Cf) : c;
+                    atomicAdd(q.dW + static_cast<size_t>(eco) * q.Cin + ci, h[j]);
+                }
             }
         }
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == kTbMmaWarp) tc::tmem_dealloc(tmem_base, 256);
+    if (warp == kTbMmaWarp) tc::tmem_dealloc(tmem_base, 512);
+}
+
+static inline bool tc_dw_plan(int cout, int cin, bool gather, bool synth, int &n_raw, int &stage, size_t &smem) {
+    const int nrows_a = cin;                              // gather: Cf + 3 == cin
+    const int n_mma = ((nrows_a + 15) / 16) * 16, a_rows = ((n_mma + 7) / 8) * 8;
+    const size_t a_bytes = (static_cast<size_t>(a_rows) * 128 + 1023) & ~static_cast<size_t>(1023);
+    const int m_rows = cout < kTbM ? cout : kTbM;
+    stage = m_rows * kDwPitch * (synth ? 1 : 2);
+    stage += gather ? kDwTile * ((cin - 3) * 4 + 16) + 512 : cin * kDwPitch;
+    stage = (stage + 127) & ~127;
+    const size_t budget = static_cast<size_t>(kMaxSmemPerCta) - 8 * 1024 - 1024;
+    if (4 * a_bytes + 2 * static_cast<size_t>(stage) > budget) return false;
+    n_raw = static_cast<int>((budget - 4 * a_bytes) / stage);
+    n_raw = n_raw > 4 ? 4 : n_raw;
+    smem = 4 * a_bytes + static_cast<size_t>(n_raw) * stage + 1024;
+    return true;
 }
 
 }  // namespace ogc
@@ -607,9 +720,9 @@ extern "C" int ogc_sa_mlp_layer_dw_tc(int b, int n, int m, int nsample, int cout
     if (!gather && (!y_prev || !ss_prev)) return OGC_ERR_INVALID_ARG;
     q.Cin = cin; q.B = b; q.y_prev = y_prev; q.ss_prev = ss_prev; q.xyz = xyz; q.new_xyz = new_xyz;
     q.feat_pm = feat_pm; q.idx = idx; q.N = n; q.Cf = cin - 3; q.dW = dw;
-    const int n_mma = ((cin + 15) / 16) * 16, a_rows = ((n_mma + 7) / 8) * 8;
-    const size_t a_bytes = ((static_cast<size_t>(a_rows) * 128) + 1023) & ~static_cast<size_t>(1023);
-    const size_t smem = static_cast<size_t>(kDwStages) * (2 * kTbM * 128 + 2 * a_bytes) + 1024;
+    size_t smem = 0;
+    if (gather && (cin - 3) % 4 != 0) return OGC_ERR_UNSUPPORTED;
+    if (!tc_dw_plan(cout, cin, gather != 0, dz == nullptr, q.n_raw, q.raw_stage_bytes, smem)) return OGC_ERR_UNSUPPORTED;
     const int mblocks = (cout + kTbM - 1) / kTbM;
     const int total = b * m * (nsample / kDwTile);
     int gx = kNumSMs / mblocks;

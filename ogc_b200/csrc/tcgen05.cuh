@@ -133,6 +133,20 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) 
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// 16 registers per thread -> 32 lanes x 16 consecutive columns; followed by wait::st
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    uint32_t r[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(v[i]);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 // round-to-nearest TF32 of x (the low 13 mantissa bits cleared): the "hi" part of the 3xTF32 split
 __device__ __forceinline__ float tf32_hi(float x) {
     uint32_t r;

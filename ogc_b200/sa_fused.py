@@ -28,12 +28,12 @@ TC_DW_ALL = False   # tests: route every supported dW through the tensor-core ke
 
 
 def _tc_dw_ok(S, cin, cout):
-    # measured (scratch/mlp_bench.py, 8 loader warps): the tensor-core dW beats the SIMT split-K kernel for the
-    # wide-input layers (128 -> 128: 0.38 vs 0.79 ms, 128 -> 256: 1.21 vs 1.61, 131 -> 128: 0.84 vs 1.00); for
-    # narrower inputs its per-tile loader latency dominates and the SIMT kernel stays the default
+    # measured (scratch/mlp_bench.py, dY operand through tensor memory + cp.async ring): the tensor-core dW wins from
+    # 64 input channels up (64 -> 64: 0.39 vs 0.56 ms SIMT, 99 -> 64: 0.58 vs 1.12, 128 -> 256: 0.71 vs 1.61); for the
+    # 32-channel layers of SA level 1 it is on par with or behind the SIMT split-K kernel (0.67-0.90 vs 0.62-0.93)
     if TC_DW_ALL:
-        return USE_TC and S == 64 and 32 <= cin <= 160 and 32 <= cout <= 256
-    return USE_TC and S == 64 and 128 <= cin <= 160 and 32 <= cout <= 256
+        return USE_TC and S == 64 and 32 <= cin <= 160 and 32 <= cout <= 256 and (cin % 4 == 0 or (cin - 3) % 4 == 0)
+    return USE_TC and S == 64 and 64 <= cin <= 160 and 32 <= cout <= 256 and (cin % 4 == 0 or (cin - 3) % 4 == 0)
 
 
 def _tc_dx_ok(S, cout, rows, scatter):
