@@ -31,6 +31,36 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// ---- explicit shared-state-space accesses on 32-bit addresses (smem_u32): one LDS/STS with an immediate offset
+// instead of a generic LD/ST with 64-bit address arithmetic when the compiler cannot prove the address space ----
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float2 lds_v2(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float4 lds_v4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sts_v4(uint32_t a, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void cp_async16_s(uint32_t dst_smem, const void *src_gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4_s(uint32_t dst_smem, const void *src_gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_smem), "l"(src_gmem) : "memory");
+}
+
 // ---- mbarrier + 1-D bulk async copy (TMA engine, SASS: UBLKCP) -------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -71,13 +101,17 @@ __device__ __forceinline__ void cp_async4(void *dst_smem, const void *src_gmem) 
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-// wait until at most `pending` (0..3) of this thread's most recent groups are still in flight
+// wait until at most `pending` (0..7) of this thread's most recent groups are still in flight
 __device__ __forceinline__ void cp_async_wait(int pending) {
     switch (pending) {
         case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
         case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
         case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
-        default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+        case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+        case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
     }
 }
 

@@ -56,7 +56,7 @@ mlp_fwd_tc_kernel(MlpTcParams q) {
     __shared__ uint32_t tmem_base_s;
     __shared__ double gs[kGnGroups][2];
     __shared__ float rel[2][kTcNT][4];   // centred xyz of the tile's positions (gather), double buffered
-    __shared__ float2 ss_s[kTcMaxK];     // GroupNorm (scale, shift) of the input channels (dense)
+    __shared__ __align__(16) float2 ss_s[kTcMaxK];     // GroupNorm (scale, shift) of the input channels (dense)
     __shared__ int idx_s[2][kTcNT];      // neighbour indices of the tile whose copies are issued next (gather)
 
     const MlpFwdParams &f = q.f;
@@ -96,29 +96,30 @@ mlp_fwd_tc_kernel(MlpTcParams q) {
 
     // ---- raw-stage copies of this CTA's u-th tile (transformer threads; no wait) ----
     const int lt = tid - 128;
+    const uint32_t raw_u32 = smem_u32(raw_base);
     auto issue = [&](int u) {
         const int t = blockIdx.x + u * gridDim.x;
-        uint8_t *st = raw_stage(u);
+        const uint32_t st = raw_u32 + static_cast<uint32_t>(u % n_raw) * q.raw_stage_bytes;
         if (GATHER) {
             const int *js = idx_s[u & 1];
-            const int cpr = K >> 2;                       // 16-byte chunks per feature row
-            for (int it = lt; it < kTcNT * cpr; it += kTcXf) {
-                const int p = it / cpr, ch = it - p * cpr;
-                cp_async16(st + p * g_pitch + ch * 16, f.feat_pm + (static_cast<size_t>(b) * f.N + js[p]) * f.Cf + ch * 4);
+            // lane = 16-byte chunk of a feature row (<= 32 chunks), warp = neighbour: coalesced row reads
+            if (lane < (K >> 2)) {
+                for (int p = warp - 4; p < kTcNT; p += kTcXfWarps)
+                    cp_async16_s(st + p * g_pitch + lane * 16, f.feat_pm + (static_cast<size_t>(b) * f.N + js[p]) * f.Cf + lane * 4);
             }
             if (lt < kTcNT * 3) {
                 const int p = lt / 3, c = lt - p * 3;
-                cp_async4(st + xyz_off + lt * 4, f.xyz + (static_cast<size_t>(b) * f.N + js[p]) * 3 + c);
+                cp_async4_s(st + xyz_off + lt * 4, f.xyz + (static_cast<size_t>(b) * f.N + js[p]) * 3 + c);
             } else if (lt < kTcNT * 3 + 3) {
                 const int c = lt - kTcNT * 3;
-                cp_async4(st + xyz_off + lt * 4, f.new_xyz + (static_cast<size_t>(b) * f.M + t) * 3 + c);
+                cp_async4_s(st + xyz_off + lt * 4, f.new_xyz + (static_cast<size_t>(b) * f.M + t) * 3 + c);
             }
         } else {
-            const float *src = f.y_prev + static_cast<size_t>(b) * Cin * P + static_cast<size_t>(t) * kTcNT;
-            for (int it = lt; it < K * 16; it += kTcXf) {
-                const int c = it >> 4, ch = it & 15;
-                cp_async16(st + c * d_pitch + ch * 16, src + static_cast<size_t>(c) * P + ch * 4);
-            }
+            // thread = (row mod 16, chunk): 16 lanes copy one channel's 256 B, rows advance by 16 per step
+            const float *src = f.y_prev + static_cast<size_t>(b) * Cin * P + static_cast<size_t>(t) * kTcNT + (lt & 15) * 4;
+            const uint32_t dst = st + (lt & 15) * 16;
+            for (int c = lt >> 4; c < K; c += kTcXf / 16)
+                cp_async16_s(dst + c * d_pitch, src + static_cast<size_t>(c) * P);
         }
     };
     auto load_idx = [&](int u) {     // neighbour indices of tile u (threads lt < 64), -1 past the end
@@ -175,48 +176,56 @@ mlp_fwd_tc_kernel(MlpTcParams q) {
             int jn = 0;
             if (GATHER) jn = load_idx(u + D + 1);
             mbar_wait(&bar_empty[ob], ((u / n_op) & 1) ^ 1);            // MMAs of the tile that used this buffer are done
-            const uint8_t *st = raw_stage(u);
-            uint8_t *a_hi = op_hi(ob), *a_lo = a_hi + a_bytes;
+            const uint32_t st = raw_u32 + static_cast<uint32_t>(u % n_raw) * q.raw_stage_bytes;
+            const uint32_t a_hi = smem_u32(op_hi(ob)), a_lo = a_hi + a_bytes;
             if (GATHER) {
                 // rel[tb] was last read by the epilogue of tile u-2, which arrives on bar_tempty AFTER that read
                 mbar_wait(&bar_tempty[tb], ((u >> 1) & 1) ^ 1);
                 if (lt < kTcNT) {
-                    const float *xs = reinterpret_cast<const float *>(st + xyz_off);
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) rel[tb][lt][c] = xs[lt * 3 + c] - xs[kTcNT * 3 + c];
+                    for (int c = 0; c < 3; ++c)
+                        rel[tb][lt][c] = lds_f32(st + xyz_off + (lt * 3 + c) * 4) - lds_f32(st + xyz_off + (kTcNT * 3 + c) * 4);
                 }
-                const int qpr = KB * 8;                    // channel quads per operand row (incl. zero padding)
-                for (int it = lt; it < kTcNT * qpr; it += kTcXf) {
-                    const int p = it / qpr, c = (it - p * qpr) * 4;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (c < K) v = *reinterpret_cast<const float4 *>(st + p * g_pitch + c * 4);
-                    const float4 hi = make_float4(tc::tf32_hi(v.x), tc::tf32_hi(v.y), tc::tf32_hi(v.z), tc::tf32_hi(v.w));
-                    const float4 lo = make_float4(tc::tf32_hi(v.x - hi.x), tc::tf32_hi(v.y - hi.y), tc::tf32_hi(v.z - hi.z),
-                                                  tc::tf32_hi(v.w - hi.w));
-                    const uint32_t off = static_cast<uint32_t>(c >> 5) * (kTcNT * 128u) + tc::sw128_offset(p, c & 31);
-                    *reinterpret_cast<float4 *>(a_hi + off) = hi;
-                    *reinterpret_cast<float4 *>(a_lo + off) = lo;
+                // lane = channel quad (a 16-byte chunk of both the raw row and the operand row), warp = position mod 8:
+                // every address is a per-thread constant plus a multiple of the loop counter
+                const int cq = lane, pw = warp - 4;
+                const uint32_t rd = st + pw * g_pitch + cq * 16;
+                const uint32_t wr = static_cast<uint32_t>(cq >> 3) * (kTcNT * 128u) + pw * 128u + (((cq & 7) ^ (pw & 7)) * 16u);
+                if (cq < KB * 8) {
+#pragma unroll 4
+                    for (int i = 0; i < kTcNT / kTcXfWarps; ++i) {
+                        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (cq * 4 < K) x = lds_v4(rd + i * (kTcXfWarps * g_pitch));
+                        const float v[4] = {x.x, x.y, x.z, x.w};
+                        float4 hi, lo;
+                        tc::tf32_split4(v, hi, lo);
+                        sts_v4(a_hi + wr + i * (kTcXfWarps * 128u), hi);
+                        sts_v4(a_lo + wr + i * (kTcXfWarps * 128u), lo);
+                    }
                 }
             } else {
-                // raw rows are channels: a thread takes 4 consecutive channels of one position (4 conflict-free
-                // scalar reads, lanes = consecutive positions) and writes one 16-byte chunk of the K-major row
-                for (int it = lt; it < kTcNT * KB * 8; it += kTcXf) {
-                    const int p = it & (kTcNT - 1), c = (it >> 6) * 4;
+                // raw rows are channels: thread = (position, channel quad mod 4); 4 conflict-free scalar reads (lanes =
+                // consecutive positions) -> GroupNorm + ReLU -> one 16-byte chunk of the K-major operand row; the
+                // thread's position is fixed, its channel quad advances by 4 (16 channels) per step
+                const int p = lt & (kTcNT - 1), c0 = (lt >> 6) * 4;
+                const uint32_t rd = st + c0 * d_pitch + p * 4;
+                const uint32_t ssa = smem_u32(ss_s) + c0 * 8;
+                const uint32_t wr0 = p * 128u + ((((c0 >> 2)) ^ (p & 7)) * 16u), wr1 = p * 128u + ((((c0 >> 2) + 4) ^ (p & 7)) * 16u);
+#pragma unroll 2
+                for (int i = 0; i < KB * 2; ++i) {
                     float v[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (c < K) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float x = *reinterpret_cast<const float *>(st + (c + e) * d_pitch + p * 4);
-                            const float2 ss = ss_s[c + e];
-                            v[e] = fmaxf(fmaf(ss.x, x, ss.y), 0.f);
-                        }
+                    if (c0 + 16 * i < K) {
+                        const float4 s01 = lds_v4(ssa + i * 128), s23 = lds_v4(ssa + i * 128 + 16);
+                        v[0] = fmaxf(fmaf(s01.x, lds_f32(rd + i * (16 * d_pitch)), s01.y), 0.f);
+                        v[1] = fmaxf(fmaf(s01.z, lds_f32(rd + i * (16 * d_pitch) + d_pitch), s01.w), 0.f);
+                        v[2] = fmaxf(fmaf(s23.x, lds_f32(rd + i * (16 * d_pitch) + 2 * d_pitch), s23.y), 0.f);
+                        v[3] = fmaxf(fmaf(s23.z, lds_f32(rd + i * (16 * d_pitch) + 3 * d_pitch), s23.w), 0.f);
                     }
-                    const float4 hi = make_float4(tc::tf32_hi(v[0]), tc::tf32_hi(v[1]), tc::tf32_hi(v[2]), tc::tf32_hi(v[3]));
-                    const float4 lo = make_float4(tc::tf32_hi(v[0] - hi.x), tc::tf32_hi(v[1] - hi.y), tc::tf32_hi(v[2] - hi.z),
-                                                  tc::tf32_hi(v[3] - hi.w));
-                    const uint32_t off = static_cast<uint32_t>(c >> 5) * (kTcNT * 128u) + tc::sw128_offset(p, c & 31);
-                    *reinterpret_cast<float4 *>(a_hi + off) = hi;
-                    *reinterpret_cast<float4 *>(a_lo + off) = lo;
+                    float4 hi, lo;
+                    tc::tf32_split4(v, hi, lo);
+                    const uint32_t off = static_cast<uint32_t>(i >> 1) * (kTcNT * 128u) + ((i & 1) ? wr1 : wr0);
+                    sts_v4(a_hi + off, hi);
+                    sts_v4(a_lo + off, lo);
                 }
             }
             tc::fence_proxy_async();

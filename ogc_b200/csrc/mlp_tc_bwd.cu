@@ -55,8 +55,8 @@ mlp_dx_tc_kernel(MlpDxTcParams q) {
     __shared__ __align__(8) uint64_t bar_full[2], bar_empty[2], bar_tfull[2], bar_tempty[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ double gs[kGnGroups][2];
-    __shared__ float4 coef_s[kTbMaxK];          // k1, k2, k3r, mean of this launch's K channels
-    __shared__ float2 selgo_s[2][kTbMaxK];      // last layer: (winning position, pooled gradient) per channel of a tile
+    __shared__ __align__(16) float4 coef_s[kTbMaxK];          // k1, k2, k3r, mean of this launch's K channels
+    __shared__ __align__(16) float2 selgo_s[2][kTbMaxK];      // last layer: (winning position, pooled gradient) per channel of a tile
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y;
@@ -92,14 +92,15 @@ mlp_dx_tc_kernel(MlpDxTcParams q) {
     const uint32_t tmem_base = tmem_base_s;
 
     const int lt = tid - 128;
+    const uint32_t raw_u32 = smem_u32(raw_base);
     auto issue = [&](int u) {
         const int t = blockIdx.x + u * gridDim.x;
-        uint8_t *st = raw_stage(u);
-        const size_t base = (static_cast<size_t>(b) * q.dy.C + q.k0) * P + static_cast<size_t>(t) * kTbNT;
-        for (int it = lt; it < kn * 16; it += kTbLoaders) {
-            const int c = it >> 4, ch = it & 15;
-            cp_async16(st + c * pitch + ch * 16, q.dy.y + base + static_cast<size_t>(c) * P + ch * 4);
-            if (!synth) cp_async16(st + dz_off + c * pitch + ch * 16, q.dy.dz + base + static_cast<size_t>(c) * P + ch * 4);
+        const uint32_t dst = raw_u32 + static_cast<uint32_t>(u % n_raw) * q.raw_stage_bytes + (lt & 15) * 16;
+        const size_t base = (static_cast<size_t>(b) * q.dy.C + q.k0) * P + static_cast<size_t>(t) * kTbNT + (lt & 15) * 4;
+        // 16 lanes copy one channel's 256 B; rows advance by 16 per step
+        for (int c = lt >> 4; c < kn; c += kTbLoaders / 16) {
+            cp_async16_s(dst + c * pitch, q.dy.y + base + static_cast<size_t>(c) * P);
+            if (!synth) cp_async16_s(dst + dz_off + c * pitch, q.dy.dz + base + static_cast<size_t>(c) * P);
         }
     };
     // last layer: (sel, go) of tile u for channel lt (one centre per tile: m = tile index)
@@ -154,33 +155,37 @@ mlp_dx_tc_kernel(MlpDxTcParams q) {
                 sg_next = load_selgo(u + 2);
             }
             mbar_wait(&bar_empty[ob], ((u / n_op) & 1) ^ 1);
-            const uint8_t *st = raw_stage(u);
-            uint8_t *a_hi = op_hi(ob), *a_lo = a_hi + a_bytes;
-            const float2 *sg = selgo_s[u & 1];
-            for (int it = lt; it < kTbNT * KB * 8; it += kTbLoaders) {
-                const int p = it & (kTbNT - 1), c = (it >> 6) * 4;
+            const uint32_t st = raw_u32 + static_cast<uint32_t>(u % n_raw) * q.raw_stage_bytes;
+            const uint32_t a_hi = smem_u32(op_hi(ob)), a_lo = a_hi + a_bytes;
+            // thread = (position, channel quad mod 4): fixed position, the channel quad advances by 4 (16 channels) per
+            // step; every address is a per-thread constant plus a multiple of the loop counter
+            const int p = lt & (kTbNT - 1), c0 = (lt >> 6) * 4;
+            const uint32_t rd = st + c0 * pitch + p * 4;
+            const uint32_t cfa = smem_u32(coef_s) + c0 * 16, sga = smem_u32(selgo_s[u & 1]) + c0 * 8;
+            const uint32_t wr0 = p * 128u + ((((c0 >> 2)) ^ (p & 7)) * 16u), wr1 = p * 128u + ((((c0 >> 2) + 4) ^ (p & 7)) * 16u);
+#pragma unroll 2
+            for (int i = 0; i < KB * 2; ++i) {
                 float v[4] = {0.f, 0.f, 0.f, 0.f};
-                if (c < kn) {
+                if (c0 + 16 * i < kn) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const float4 cf = coef_s[c + e];
-                        const float y = *reinterpret_cast<const float *>(st + (c + e) * pitch + p * 4);
+                        const float4 cf = lds_v4(cfa + i * 256 + e * 16);
+                        const float y = lds_f32(rd + i * (16 * pitch) + e * pitch);
                         float dz;
                         if (synth) {
-                            const float2 s2 = sg[c + e];
+                            const float2 s2 = lds_v2(sga + i * 128 + e * 8);
                             dz = (static_cast<int>(s2.x) == p) ? s2.y : 0.f;
                         } else {
-                            dz = *reinterpret_cast<const float *>(st + dz_off + (c + e) * pitch + p * 4);
+                            dz = lds_f32(rd + dz_off + i * (16 * pitch) + e * pitch);
                         }
                         v[e] = fmaf(cf.x, dz, -cf.y) - (y - cf.w) * cf.z;
                     }
                 }
-                const float4 hi = make_float4(tc::tf32_hi(v[0]), tc::tf32_hi(v[1]), tc::tf32_hi(v[2]), tc::tf32_hi(v[3]));
-                const float4 lo = make_float4(tc::tf32_hi(v[0] - hi.x), tc::tf32_hi(v[1] - hi.y), tc::tf32_hi(v[2] - hi.z),
-                                              tc::tf32_hi(v[3] - hi.w));
-                const uint32_t off = static_cast<uint32_t>(c >> 5) * (kTbNT * 128u) + tc::sw128_offset(p, c & 31);
-                *reinterpret_cast<float4 *>(a_hi + off) = hi;
-                *reinterpret_cast<float4 *>(a_lo + off) = lo;
+                float4 hi, lo;
+                tc::tf32_split4(v, hi, lo);
+                const uint32_t off = static_cast<uint32_t>(i >> 1) * (kTbNT * 128u) + ((i & 1) ? wr1 : wr0);
+                sts_v4(a_hi + off, hi);
+                sts_v4(a_lo + off, lo);
             }
             tc::fence_proxy_async();
             mbar_arrive(&bar_full[ob]);
@@ -227,69 +232,71 @@ mlp_dx_tc_kernel(MlpDxTcParams q) {
         for (int u = 0; u < n_my; ++u) {
             const int buf = u & 1;
             const int p0 = (blockIdx.x + u * gridDim.x) * kTbNT;
-            // issue this tile's y_prev row reads (ReLU mask) BEFORE waiting for the accumulator
-            float4 y4[kTbNT / 4];
-            if (mask && valid) {
-                const float4 *yp = reinterpret_cast<const float4 *>(q.y_prev + (static_cast<size_t>(b) * q.rows + r) * P + p0);
-#pragma unroll
-                for (int j = 0; j < kTbNT / 4; ++j) y4[j] = __ldg(yp + j);
-            }
+            const uint32_t ta = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(buf * kTbNT);
+            // the tile is finished in two halves of 32 positions; the y_prev row reads (ReLU mask) of the first half are
+            // issued BEFORE waiting for the accumulator, those of the second half fly while the first is processed
+            const float4 *yp = reinterpret_cast<const float4 *>(q.y_prev + (static_cast<size_t>(b) * q.rows + (valid ? r : 0)) * P + p0);
+            float4 *dp = reinterpret_cast<float4 *>(q.dz_prev + (static_cast<size_t>(b) * q.rows + (valid ? r : 0)) * P + p0);
+            float4 ya[8], yb[8];
             int j_lo = 0, j_hi = 0;                      // scatter: lane l holds the neighbour index of positions l, l + 32
             if (SCATTER) {
                 j_lo = __ldg(q.idx + static_cast<size_t>(b) * P + p0 + lane);
                 j_hi = __ldg(q.idx + static_cast<size_t>(b) * P + p0 + 32 + lane);
+            } else if (mask && valid) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) ya[j] = __ldg(yp + j);
             }
             mbar_wait(&bar_tfull[buf], (u >> 1) & 1);
             tc::fence_after_sync();
-            float v[kTbNT];
-            {
-                float h[32];
-                const uint32_t ta = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(buf * kTbNT);
-                tc::tmem_ld32(ta, h);
+            if (mask && valid) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = h[j];
-                tc::tmem_ld32(ta + 32, h);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[32 + j] = h[j];
+                for (int j = 0; j < 8; ++j) yb[j] = __ldg(yp + 8 + j);
             }
-            tc::fence_before_sync();
-            mbar_arrive(&bar_tempty[buf]);
-            if (SCATTER) {
-                // 32 lanes = 32 consecutive feature channels of the same point: one coalesced red per position
 #pragma unroll
-                for (int j = 0; j < kTbNT; ++j) {
-                    const int pt = __shfl_sync(OGC_FULL_MASK, j < 32 ? j_lo : j_hi, j & 31);
-                    if (valid) atomicAdd(q.dfeat_pm + (static_cast<size_t>(b) * q.N + pt) * q.dfeat_stride + q.dfeat_off + r, v[j]);
+            for (int hf = 0; hf < 2; ++hf) {
+                float v[32];
+                tc::tmem_ld32(ta + hf * 32, v);
+                if (hf == 1) {
+                    tc::fence_before_sync();
+                    mbar_arrive(&bar_tempty[buf]);
                 }
-                continue;
-            }
-            if (!valid) continue;
-            float4 *dp = reinterpret_cast<float4 *>(q.dz_prev + (static_cast<size_t>(b) * q.rows + r) * P + p0);
-            if (q.add_partial) {
+                if (SCATTER) {
+                    // 32 lanes = 32 consecutive feature channels of the same point: one coalesced red per position
 #pragma unroll
-                for (int j = 0; j < kTbNT / 4; ++j) {
-                    const float4 o = dp[j];
-                    v[4 * j] += o.x; v[4 * j + 1] += o.y; v[4 * j + 2] += o.z; v[4 * j + 3] += o.w;
+                    for (int j = 0; j < 32; ++j) {
+                        const int pt = __shfl_sync(OGC_FULL_MASK, hf ? j_hi : j_lo, j);
+                        if (valid) atomicAdd(q.dfeat_pm + (static_cast<size_t>(b) * q.N + pt) * q.dfeat_stride + q.dfeat_off + r, v[j]);
+                    }
+                    continue;
                 }
-            }
-            if (q.final) {
-                float s = 0.f, sy = 0.f;
+                if (!valid) continue;
+                if (q.add_partial) {
 #pragma unroll
-                for (int j = 0; j < kTbNT / 4; ++j) {
-                    const float yy[4] = {y4[j].x, y4[j].y, y4[j].z, y4[j].w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float g = fmaf(sc, yy[e], sh) > 0.f ? v[4 * j + e] : 0.f;
-                        v[4 * j + e] = g;
-                        s += g;
-                        sy = fmaf(g, (yy[e] - mu) * rs, sy);
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 o = dp[hf * 8 + j];
+                        v[4 * j] += o.x; v[4 * j + 1] += o.y; v[4 * j + 2] += o.z; v[4 * j + 3] += o.w;
                     }
                 }
-                dsum += static_cast<double>(s);
-                dsumy += static_cast<double>(sy);
-            }
+                if (q.final) {
+                    float s = 0.f, sy = 0.f;
 #pragma unroll
-            for (int j = 0; j < kTbNT / 4; ++j) dp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 y4 = hf ? yb[j] : ya[j];
+                        const float yy[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float g = fmaf(sc, yy[e], sh) > 0.f ? v[4 * j + e] : 0.f;
+                            v[4 * j + e] = g;
+                            s += g;
+                            sy = fmaf(g, (yy[e] - mu) * rs, sy);
+                        }
+                    }
+                    dsum += static_cast<double>(s);
+                    dsumy += static_cast<double>(sy);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dp[hf * 8 + j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
         }
         if (mask && valid) {
             atomicAdd(q.dbeta_prev + r, static_cast<float>(dsum));
@@ -355,7 +362,7 @@ mlp_dw_tc_kernel(MlpDwTcParams q) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[2], bar_empty[2], bar_done;
     __shared__ uint32_t tmem_base_s;
-    __shared__ float2 ss_s[2][kDwMaxCin];      // GroupNorm (scale, shift) of the input channels for the stage's sample
+    __shared__ __align__(16) float2 ss_s[2][kDwMaxCin];      // GroupNorm (scale, shift) of the input channels for the stage's sample
     __shared__ int idx_s[2][kDwTile];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -401,36 +408,34 @@ mlp_dw_tc_kernel(MlpDwTcParams q) {
         b = w / tiles_per_sample;
         p0 = (w - b * tiles_per_sample) * kDwTile;
     };
+    const uint32_t raw_u32 = smem_u32(raw_base);
     auto issue = [&](int u) {
         int b, p0;
         stage_of(u, b, p0);
-        uint8_t *st = raw_stage(u);
-        const size_t ybase = (static_cast<size_t>(b) * Cout + mb * kTbM) * P + p0;
-        for (int it = lt; it < m_rows * 8; it += kTbLoaders) {
-            const int c = it >> 3, ch = it & 7;
-            cp_async16(st + c * kDwPitch + ch * 16, q.dy.y + ybase + static_cast<size_t>(c) * P + ch * 4);
-            if (!synth) cp_async16(st + dz_off + c * kDwPitch + ch * 16, q.dy.dz + ybase + static_cast<size_t>(c) * P + ch * 4);
+        const uint32_t st = raw_u32 + static_cast<uint32_t>(u % n_raw) * q.raw_stage_bytes;
+        const size_t ybase = (static_cast<size_t>(b) * Cout + mb * kTbM) * P + p0 + (lt & 7) * 4;
+        // 8 lanes copy one channel's 128 B; rows advance by 32 per step
+        for (int c = lt >> 3; c < m_rows; c += kTbLoaders / 8) {
+            cp_async16_s(st + c * kDwPitch + (lt & 7) * 16, q.dy.y + ybase + static_cast<size_t>(c) * P);
+            if (!synth) cp_async16_s(st + dz_off + c * kDwPitch + (lt & 7) * 16, q.dy.dz + ybase + static_cast<size_t>(c) * P);
         }
         if (GATHER) {
             const int *js = idx_s[u & 1];
-            const int cpr = q.Cf >> 2;
-            for (int it = lt; it < kDwTile * cpr; it += kTbLoaders) {
-                const int p = it / cpr, ch = it - p * cpr;
-                cp_async16(st + in_off + p * g_pitch + ch * 16, q.feat_pm + (static_cast<size_t>(b) * q.N + js[p]) * q.Cf + ch * 4);
+            if (lane < (q.Cf >> 2)) {
+                for (int p = warp - 4; p < kDwTile; p += kTbLoaderWarps)
+                    cp_async16_s(st + in_off + p * g_pitch + lane * 16, q.feat_pm + (static_cast<size_t>(b) * q.N + js[p]) * q.Cf + lane * 4);
             }
             if (lt < kDwTile * 3) {
                 const int p = lt / 3, c = lt - p * 3;
-                cp_async4(st + xyz_off + lt * 4, q.xyz + (static_cast<size_t>(b) * q.N + js[p]) * 3 + c);
+                cp_async4_s(st + xyz_off + lt * 4, q.xyz + (static_cast<size_t>(b) * q.N + js[p]) * 3 + c);
             } else if (lt < kDwTile * 3 + 3) {
                 const int c = lt - kDwTile * 3;
-                cp_async4(st + xyz_off + lt * 4, q.new_xyz + (static_cast<size_t>(b) * q.dy.M + p0 / q.dy.S) * 3 + c);
+                cp_async4_s(st + xyz_off + lt * 4, q.new_xyz + (static_cast<size_t>(b) * q.dy.M + p0 / q.dy.S) * 3 + c);
             }
         } else {
-            const size_t abase = static_cast<size_t>(b) * q.Cin * P + p0;
-            for (int it = lt; it < q.Cin * 8; it += kTbLoaders) {
-                const int c = it >> 3, ch = it & 7;
-                cp_async16(st + in_off + c * kDwPitch + ch * 16, q.y_prev + abase + static_cast<size_t>(c) * P + ch * 4);
-            }
+            const size_t abase = static_cast<size_t>(b) * q.Cin * P + p0 + (lt & 7) * 4;
+            for (int c = lt >> 3; c < q.Cin; c += kTbLoaders / 8)
+                cp_async16_s(st + in_off + c * kDwPitch + (lt & 7) * 16, q.y_prev + abase + static_cast<size_t>(c) * P);
         }
     };
     auto load_idx = [&](int u) {
@@ -497,33 +502,29 @@ mlp_dw_tc_kernel(MlpDwTcParams q) {
             const float4 cfn = load_coef(u + 1);
             const float2 sgn = load_selgo(u + 1);
             mbar_wait(&bar_empty[ob], ((u >> 1) & 1) ^ 1);  // the MMAs that read operand buffers `ob` are done
-            const uint8_t *st = raw_stage(u);
+            const uint32_t st = raw_u32 + static_cast<uint32_t>(u % n_raw) * q.raw_stage_bytes;
             int b, p0;
             stage_of(u, b, p0);
             // ---- dY row -> tensor memory ----
             {
                 float hi[16], lo[16];
                 if (row < m_rows) {
-                    const float4 *yr = reinterpret_cast<const float4 *>(st + row * kDwPitch + chalf * 64);
-                    const float4 *zr = reinterpret_cast<const float4 *>(st + dz_off + row * kDwPitch + chalf * 64);
+                    const uint32_t yr = st + row * kDwPitch + chalf * 64, zr = yr + dz_off;
                     const int s0 = p0 % q.dy.S + chalf * 16;        // position of column 0 inside its centre's group
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const float4 y4 = yr[i];
+                        const float4 y4 = lds_v4(yr + i * 16);
                         float4 z4;
                         if (synth) {
                             const int sl = static_cast<int>(sg.x) - s0 - 4 * i;
                             z4 = make_float4(sl == 0 ? sg.y : 0.f, sl == 1 ? sg.y : 0.f, sl == 2 ? sg.y : 0.f, sl == 3 ? sg.y : 0.f);
                         } else {
-                            z4 = zr[i];
+                            z4 = lds_v4(zr + i * 16);
                         }
                         const float yy[4] = {y4.x, y4.y, y4.z, y4.w}, zz[4] = {z4.x, z4.y, z4.z, z4.w};
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float v = fmaf(cf.x, zz[e], -cf.y) - (yy[e] - cf.w) * cf.z;
-                            hi[4 * i + e] = tc::tf32_hi(v);
-                            lo[4 * i + e] = tc::tf32_hi(v - hi[4 * i + e]);
-                        }
+                        for (int e = 0; e < 4; ++e)
+                            tc::tf32_split(fmaf(cf.x, zz[e], -cf.y) - (yy[e] - cf.w) * cf.z, hi[4 * i + e], lo[4 * i + e]);
                     }
                 } else {
 #pragma unroll
@@ -534,43 +535,43 @@ mlp_dw_tc_kernel(MlpDwTcParams q) {
                 tc::tmem_st16(ta + 32, lo);
             }
             // ---- a tile: row = input channel, 128 B = the stage's 32 positions ----
-            uint8_t *ah = a_hi(ob), *al = ah + a_bytes;
+            const uint32_t ah = smem_u32(a_hi(ob)), al = ah + a_bytes;
             if (GATHER) {
-                for (int it = lt; it < q.Cf * 8; it += kTbLoaders) {
-                    const int pq = it / q.Cf, c = it - pq * q.Cf;
-                    float v[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) v[e] = *reinterpret_cast<const float *>(st + in_off + (pq * 4 + e) * g_pitch + c * 4);
-                    const float4 hi = make_float4(tc::tf32_hi(v[0]), tc::tf32_hi(v[1]), tc::tf32_hi(v[2]), tc::tf32_hi(v[3]));
-                    const float4 lo = make_float4(tc::tf32_hi(v[0] - hi.x), tc::tf32_hi(v[1] - hi.y), tc::tf32_hi(v[2] - hi.z),
-                                                  tc::tf32_hi(v[3] - hi.w));
+                // lane = channel (mod 32), warp = position quad: 4 scalar reads down the gathered rows, one 16-byte
+                // chunk of the channel's operand row
+                const int pq = warp - 4;
+                for (int c = lane; c < q.Cf; c += 32) {
+                    const uint32_t rd = st + in_off + (pq * 4) * g_pitch + c * 4;
+                    const float v[4] = {lds_f32(rd), lds_f32(rd + g_pitch), lds_f32(rd + 2 * g_pitch), lds_f32(rd + 3 * g_pitch)};
+                    float4 hi, lo;
+                    tc::tf32_split4(v, hi, lo);
                     const uint32_t off = static_cast<uint32_t>(c) * 128u + static_cast<uint32_t>((pq ^ (c & 7)) * 16);
-                    *reinterpret_cast<float4 *>(ah + off) = hi;
-                    *reinterpret_cast<float4 *>(al + off) = lo;
+                    sts_v4(ah + off, hi);
+                    sts_v4(al + off, lo);
                 }
                 if (lt < kDwTile * 3) {
                     const int c = lt >> 5, p = lt & 31;
-                    const float *xs = reinterpret_cast<const float *>(st + xyz_off);
-                    const float v = xs[p * 3 + c] - xs[kDwTile * 3 + c];
-                    const float hi = tc::tf32_hi(v);
+                    const float v = lds_f32(st + xyz_off + (p * 3 + c) * 4) - lds_f32(st + xyz_off + (kDwTile * 3 + c) * 4);
+                    float hi, lo;
+                    tc::tf32_split(v, hi, lo);
                     const uint32_t off = tc::sw128_offset(q.Cf + c, p);
-                    *reinterpret_cast<float *>(ah + off) = hi;
-                    *reinterpret_cast<float *>(al + off) = tc::tf32_hi(v - hi);
+                    sts_f32(ah + off, hi);
+                    sts_f32(al + off, lo);
                 }
             } else {
-                const float2 *ss = ss_s[u & 1];
-                for (int it = lt; it < q.Cin * 8; it += kTbLoaders) {
-                    const int r = it >> 3, pq = it & 7;
-                    const float4 x = *reinterpret_cast<const float4 *>(st + in_off + r * kDwPitch + pq * 16);
-                    const float2 s2 = ss[r];
-                    const float4 v = make_float4(fmaxf(fmaf(s2.x, x.x, s2.y), 0.f), fmaxf(fmaf(s2.x, x.y, s2.y), 0.f),
-                                                 fmaxf(fmaf(s2.x, x.z, s2.y), 0.f), fmaxf(fmaf(s2.x, x.w, s2.y), 0.f));
-                    const float4 hi = make_float4(tc::tf32_hi(v.x), tc::tf32_hi(v.y), tc::tf32_hi(v.z), tc::tf32_hi(v.w));
-                    const float4 lo = make_float4(tc::tf32_hi(v.x - hi.x), tc::tf32_hi(v.y - hi.y), tc::tf32_hi(v.z - hi.z),
-                                                  tc::tf32_hi(v.w - hi.w));
+                // thread = (row mod 32, position quad): rows advance by 32 per step
+                const int pq = lt & 7;
+                const uint32_t ssa = smem_u32(ss_s[u & 1]);
+                for (int r = lt >> 3; r < q.Cin; r += kTbLoaders / 8) {
+                    const float4 x = lds_v4(st + in_off + r * kDwPitch + pq * 16);
+                    const float2 s2 = lds_v2(ssa + r * 8);
+                    const float v[4] = {fmaxf(fmaf(s2.x, x.x, s2.y), 0.f), fmaxf(fmaf(s2.x, x.y, s2.y), 0.f),
+                                        fmaxf(fmaf(s2.x, x.z, s2.y), 0.f), fmaxf(fmaf(s2.x, x.w, s2.y), 0.f)};
+                    float4 hi, lo;
+                    tc::tf32_split4(v, hi, lo);
                     const uint32_t off = static_cast<uint32_t>(r) * 128u + static_cast<uint32_t>((pq ^ (r & 7)) * 16);
-                    *reinterpret_cast<float4 *>(ah + off) = hi;
-                    *reinterpret_cast<float4 *>(al + off) = lo;
+                    sts_v4(ah + off, hi);
+                    sts_v4(al + off, lo);
                 }
             }
             tc::fence_proxy_async();

@@ -43,10 +43,12 @@ tc_probe_kernel(int mode, int N, int K, int split3, const float *__restrict__ A,
         }
         for (int e = tid; e < N * K; e += blockDim.x) {
             const int r = e / K, k = e - r * K;
-            const float v = B[e], hi = split3 ? tc::tf32_hi(v) : v;
+            const float v = B[e];
+            float hi = split3 ? tc::tf32_hi(v) : v, lo = tc::tf32_hi(v - hi);
+            if (split3 && mode == 2) tc::tf32_split(v, hi, lo);
             const uint32_t off = static_cast<uint32_t>(k >> 5) * (N * 128u) + tc::sw128_offset(r, k & 31);
             *reinterpret_cast<float *>(b_hi + off) = hi;
-            if (split3) *reinterpret_cast<float *>(b_lo + off) = tc::tf32_hi(v - hi);
+            if (split3) *reinterpret_cast<float *>(b_lo + off) = lo;
         }
     } else {
         // column blocks over M / N: block cb = [K rows][32]
@@ -77,8 +79,8 @@ tc_probe_kernel(int mode, int N, int K, int split3, const float *__restrict__ A,
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const float v = A[tid * K + k0 + j];
-                hi[j] = split3 ? tc::tf32_hi(v) : v;
-                lo[j] = tc::tf32_hi(v - hi[j]);
+                hi[j] = v; lo[j] = 0.f;
+                if (split3) tc::tf32_split(v, hi[j], lo[j]);     // the integer split the fused kernels use
             }
             const uint32_t ta = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + a_col + static_cast<uint32_t>(k0);
             tc::tmem_st32(ta, hi);

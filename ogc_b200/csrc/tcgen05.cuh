@@ -154,6 +154,20 @@ __device__ __forceinline__ float tf32_hi(float x) {
     return __uint_as_float(r);
 }
 
+// The 3xTF32 split x = hi + lo with integer arithmetic: cvt.rna.tf32.f32 compiles to four instructions (add half an
+// ulp, inf/nan test, select, mask); the test is dropped here (finite inputs), and lo keeps its low 13 bits, which
+// the tensor core ignores -- adding 0x1000 first makes that truncation a round-to-nearest.  2 + 1 + 1 instructions.
+__device__ __forceinline__ void tf32_split(float x, float &hi, float &lo) {
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+    lo = __uint_as_float(__float_as_uint(x - hi) + 0x1000u);
+}
+__device__ __forceinline__ void tf32_split4(const float (&v)[4], float4 &hi, float4 &lo) {
+    tf32_split(v[0], hi.x, lo.x);
+    tf32_split(v[1], hi.y, lo.y);
+    tf32_split(v[2], hi.z, lo.z);
+    tf32_split(v[3], hi.w, lo.w);
+}
+
 }  // namespace tc
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
