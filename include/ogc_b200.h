@@ -314,6 +314,41 @@ OGC_API int ogc_icp_correspond(int b, int n1, int n2, int k, float temperature, 
                                const float *pc2, const float *mask1, const float *mask2, float *flow_out,
                                void *stream);
 
+/* =====================================================================================
+ * Fused feature-propagation block (csrc/fp_mlp.cu) -- replaces the torch-level stack of the reference FP
+ * module (utils/pointnet2_util.py:91-120): inverse-distance weights (:98-101), three_interpolate (:103), skip
+ * concat (:108-112) and SharedMLP = (Conv2d 1x1, GroupNorm(4), ReLU) x L (utils/nn_util.py:151-168) over the
+ * p = n points of the finer level, forward and backward.
+ * ===================================================================================== */
+
+/* x (b,c2+c1,n) = [three_interpolate(known_feats (b,c2,m), idx, w) ; skip (b,c1,n)] with
+ * w_j = (1/(sqrt(dist2_j)+1e-8)) / sum_j(.) written to weight (b,n,3).  idx, dist2 (b,n,3) from ogc_three_nn. */
+OGC_API int ogc_fp_interp_concat(int b, int c2, int m, int c1, int n, const float *known_feats, const int *idx,
+                                 const float *dist2, const float *skip, float *x, float *weight, void *stream);
+
+/* One pointwise layer y (b,cout,p) = W act(x), x (b,cin,p); act = relu(ss_prev[.,0]*x + ss_prev[.,1]) or identity
+ * when ss_prev == NULL (layer 0).  wt = W^T (cin,cout), any cin (streamed in chunks).  sums (b,4,2) fp64 +=
+ * GroupNorm sums as ogc_sa_mlp_layer_fwd.  cout multiple of 16, <= 256. */
+OGC_API int ogc_pw_mlp_layer_fwd(int b, int p, int cin, int cout, const float *x, const float *ss_prev,
+                                 const float *wt, float *y, double *sums, void *stream);
+
+/* out (b,c,p) = relu(scale*y + shift): the block's output. */
+OGC_API int ogc_gn_relu_apply(int b, int c, int p, const float *y, const float *scale_shift, float *out,
+                              void *stream);
+
+/* Backward entry: dz (b,c,p) = (scale*y+shift > 0) ? dout : 0; ab / dgamma / dbeta as ogc_sa_last_stats. */
+OGC_API int ogc_gn_relu_bwd_stats(int b, int c, int p, const float *dout, const float *y, const float *scale_shift,
+                                  const float *mean_rstd, const float *gamma, float *dz, double *ab, float *dgamma,
+                                  float *dbeta, void *stream);
+
+/* Gradient of a layer-0 input (no norm / activation in front of it): dx[b, dx_coff + r, :] = rows
+ * [row_off,row_off+rows) of W^T dY, W (cout,cin_full), dY rebuilt from dz, y, coef.  rows <= 128.
+ * (The layer-to-layer and weight gradients of the FP block use ogc_sa_mlp_layer_dx / _dw with nsample = 1;
+ * ogc_sa_mlp_layer_dw accepts ss_prev == NULL for a raw layer input.) */
+OGC_API int ogc_pw_mlp_input_grad(int b, int p, int cout, int cin_full, int row_off, int rows, const float *dz,
+                                  const float *y, const float *coef, const float *w, float *dx, int dx_ctotal,
+                                  int dx_coff, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,6 +52,11 @@ SIGNATURES = {
     "ogc_mask_match": [_I, _I, _P, _P, _P, _P],
     "ogc_lsap_maximize_host": [_I, _P, _P],
     "ogc_mask_nuclear_norm": [_I, _I, _I, _P, _P, _P, _P],
+    "ogc_fp_interp_concat": [_I] * 5 + [_P] * 7,
+    "ogc_pw_mlp_layer_fwd": [_I] * 4 + [_P] * 6,
+    "ogc_gn_relu_apply": [_I] * 3 + [_P] * 4,
+    "ogc_gn_relu_bwd_stats": [_I] * 3 + [_P] * 10,
+    "ogc_pw_mlp_input_grad": [_I] * 6 + [_P] * 5 + [_I, _I, _P],
     "ogc_adam_step_dev": [_LL, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _P, _P],
 }
 

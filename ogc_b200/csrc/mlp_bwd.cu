@@ -81,11 +81,18 @@ struct MlpDxParams {
     const int *idx;              // (B,M,S)
     float *dfeat_pm;             // (B,N,dfeat_stride), channels [dfeat_off, dfeat_off+rows)
     int N, dfeat_stride, dfeat_off;
+    // plain output (feature-propagation layer 0: no norm / activation in front): dx (B,dx_ctotal,P), channels
+    // [dx_coff, dx_coff+rows)
+    float *dx;
+    int dx_ctotal, dx_coff;
 };
 
-template <int R_T, int P_T, bool SCATTER>
+enum { kDxDense = 0, kDxScatter = 1, kDxPlain = 2 };
+
+template <int R_T, int P_T, int MODE>
 __global__ void __launch_bounds__(kMlpThreads, 2)
 mlp_dx_kernel(MlpDxParams q) {
+    constexpr bool SCATTER = MODE == kDxScatter;
     constexpr int TX = P_T / 8, LDB = P_T + 4, KC = 64;
     extern __shared__ __align__(16) float smem[];
     __shared__ float rowacc[R_T][2];
@@ -105,7 +112,7 @@ mlp_dx_kernel(MlpDxParams q) {
         sdz[i] = sdzy[i] = 0.f;
         sc[i] = sh[i] = mu[i] = rs[i] = 0.f;
         const int r = rows[i >> 2] + (i & 3);
-        if (!SCATTER && r < q.rows) {
+        if (MODE == kDxDense && r < q.rows) {
             const int g = r / (q.rows / kGnGroups);
             sc[i] = __ldg(q.ss_prev + (static_cast<size_t>(b) * q.rows + r) * 2);
             sh[i] = __ldg(q.ss_prev + (static_cast<size_t>(b) * q.rows + r) * 2 + 1);
@@ -169,6 +176,13 @@ mlp_dx_kernel(MlpDxParams q) {
                             const int pt = __ldg(q.idx + static_cast<size_t>(b) * P + p + j);
                             atomicAdd(q.dfeat_pm + (static_cast<size_t>(b) * q.N + pt) * q.dfeat_stride + q.dfeat_off + r, acc[i][cc * 4 + j]);
                         }
+                } else if (MODE == kDxPlain) {
+                    float *dp = q.dx + (static_cast<size_t>(b) * q.dx_ctotal + q.dx_coff + r) * P + p;
+                    if (p + 3 < P && (reinterpret_cast<uintptr_t>(dp) & 15u) == 0)
+                        *reinterpret_cast<float4 *>(dp) = make_float4(acc[i][cc * 4], acc[i][cc * 4 + 1], acc[i][cc * 4 + 2], acc[i][cc * 4 + 3]);
+                    else
+                        for (int j = 0; j < 4; ++j)
+                            if (p + j < P) dp[j] = acc[i][cc * 4 + j];
                 } else {
                     const float *yp = q.y_prev + (static_cast<size_t>(b) * q.rows + r) * P + p;
                     float *dp = q.dz_prev + (static_cast<size_t>(b) * q.rows + r) * P + p;
@@ -190,7 +204,7 @@ mlp_dx_kernel(MlpDxParams q) {
             }
         }
     }
-    if (SCATTER) return;
+    if (MODE != kDxDense) return;
     // per-channel sums over this CTA's positions -> dgamma / dbeta and the group sums of layer l-1
     constexpr int W = TX >= 32 ? 32 : TX;
 #pragma unroll
@@ -292,7 +306,16 @@ mlp_dw_kernel(MlpDwParams q) {
             for (int e = tid; e < C_T * (PK / 4); e += kMlpThreads) {
                 const int c = e % C_T, pq = e / C_T, ci = col0 + c, gp = p_base + pq * 4;
                 float o[4] = {0.f, 0.f, 0.f, 0.f};
-                if (ci < q.Cin) {
+                if (ci < q.Cin && !q.ss_prev) {           // raw layer input (feature propagation layer 0)
+                    const float *yp = q.y_prev + (static_cast<size_t>(b) * q.Cin + ci) * P + gp;
+                    if (gp + 3 < P && (reinterpret_cast<uintptr_t>(yp) & 15u) == 0) {
+                        const float4 t = __ldg(reinterpret_cast<const float4 *>(yp));
+                        o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+                    } else {
+                        for (int j = 0; j < 4; ++j)
+                            if (gp + j < P) o[j] = __ldg(yp + j);
+                    }
+                } else if (ci < q.Cin) {
                     const float s = __ldg(q.ss_prev + (static_cast<size_t>(b) * q.Cin + ci) * 2), h = __ldg(q.ss_prev + (static_cast<size_t>(b) * q.Cin + ci) * 2 + 1);
                     const float *yp = q.y_prev + (static_cast<size_t>(b) * q.Cin + ci) * P + gp;
                     if (gp + 3 < P && (reinterpret_cast<uintptr_t>(yp) & 15u) == 0) {
@@ -410,7 +433,7 @@ mlp_dw_small_kernel(MlpDwParams q) {
 }
 
 template <int R_T, int P_T>
-static cudaError_t launch_dx(const MlpDxParams &q, int B, bool scatter, cudaStream_t st) {
+static cudaError_t launch_dx(const MlpDxParams &q, int B, int mode, cudaStream_t st) {
     constexpr int KC = 64;
     const size_t smem = (static_cast<size_t>(KC) * R_T + static_cast<size_t>(KC) * (P_T + 4)) * sizeof(float);
     const int ntiles = (q.dy.P + P_T - 1) / P_T;
@@ -418,14 +441,18 @@ static cudaError_t launch_dx(const MlpDxParams &q, int B, bool scatter, cudaStre
     per_sample = per_sample > ntiles ? ntiles : (per_sample < 1 ? 1 : per_sample);
     dim3 grid(per_sample, B);
     cudaError_t e;
-    if (scatter) {
-        e = cudaFuncSetAttribute(mlp_dx_kernel<R_T, P_T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (mode == kDxScatter) {
+        e = cudaFuncSetAttribute(mlp_dx_kernel<R_T, P_T, kDxScatter>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;
-        mlp_dx_kernel<R_T, P_T, true><<<grid, kMlpThreads, smem, st>>>(q);
+        mlp_dx_kernel<R_T, P_T, kDxScatter><<<grid, kMlpThreads, smem, st>>>(q);
+    } else if (mode == kDxPlain) {
+        e = cudaFuncSetAttribute(mlp_dx_kernel<R_T, P_T, kDxPlain>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        mlp_dx_kernel<R_T, P_T, kDxPlain><<<grid, kMlpThreads, smem, st>>>(q);
     } else {
-        e = cudaFuncSetAttribute(mlp_dx_kernel<R_T, P_T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        e = cudaFuncSetAttribute(mlp_dx_kernel<R_T, P_T, kDxDense>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;
-        mlp_dx_kernel<R_T, P_T, false><<<grid, kMlpThreads, smem, st>>>(q);
+        mlp_dx_kernel<R_T, P_T, kDxDense><<<grid, kMlpThreads, smem, st>>>(q);
     }
     return cudaGetLastError();
 }
@@ -507,11 +534,39 @@ extern "C" int ogc_sa_mlp_layer_dx(int b, int n, int m, int nsample, int cout, i
     q.y_prev = y_prev; q.ss_prev = ss_prev; q.mean_rstd_prev = mean_rstd_prev; q.gamma_prev = gamma_prev;
     q.dz_prev = dz_prev; q.ab_prev = ab_prev; q.dgamma_prev = dgamma_prev; q.dbeta_prev = dbeta_prev;
     q.idx = idx; q.dfeat_pm = dfeat_pm; q.N = n; q.dfeat_stride = dfeat_stride; q.dfeat_off = dfeat_off;
+    q.dx = nullptr; q.dx_ctotal = q.dx_coff = 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e;
-    if (rows <= 32) e = launch_dx<32, 512>(q, b, scatter, st);
-    else if (rows <= 64) e = launch_dx<64, 256>(q, b, scatter, st);
-    else e = launch_dx<128, 128>(q, b, scatter, st);
+    const int mode = scatter ? kDxScatter : kDxDense;
+    if (rows <= 32) e = launch_dx<32, 512>(q, b, mode, st);
+    else if (rows <= 64) e = launch_dx<64, 256>(q, b, mode, st);
+    else e = launch_dx<128, 128>(q, b, mode, st);
+    return e == cudaSuccess ? OGC_OK : static_cast<int>(e);
+}
+
+extern "C" int ogc_pw_mlp_input_grad(int b, int p, int cout, int cin_full, int row_off, int rows, const float *dz,
+                                     const float *y, const float *coef, const float *w, float *dx, int dx_ctotal,
+                                     int dx_coff, void *stream) {
+    using namespace ogc;
+    if (b < 0 || p <= 0 || cout <= 0 || rows <= 0 || row_off < 0 || row_off + rows > cin_full || dx_coff < 0 ||
+        dx_coff + rows > dx_ctotal)
+        return OGC_ERR_INVALID_ARG;
+    if (b == 0) return OGC_OK;
+    if (!dz || !y || !coef || !w || !dx) return OGC_ERR_INVALID_ARG;
+    if (b > 65535 || rows > 128) return OGC_ERR_UNSUPPORTED;
+    MlpDxParams q;
+    int rc = fill_dy(q.dy, cout, p, 1, dz, nullptr, 0, 0, nullptr, y, coef);
+    if (rc != OGC_OK) return rc;
+    q.cin_full = cin_full; q.row_off = row_off; q.rows = rows; q.W = w;
+    q.y_prev = q.ss_prev = q.mean_rstd_prev = q.gamma_prev = nullptr;
+    q.dz_prev = nullptr; q.ab_prev = nullptr; q.dgamma_prev = q.dbeta_prev = nullptr;
+    q.idx = nullptr; q.dfeat_pm = nullptr; q.N = 0; q.dfeat_stride = q.dfeat_off = 0;
+    q.dx = dx; q.dx_ctotal = dx_ctotal; q.dx_coff = dx_coff;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    if (rows <= 32) e = launch_dx<32, 512>(q, b, kDxPlain, st);
+    else if (rows <= 64) e = launch_dx<64, 256>(q, b, kDxPlain, st);
+    else e = launch_dx<128, 128>(q, b, kDxPlain, st);
     return e == cudaSuccess ? OGC_OK : static_cast<int>(e);
 }
 
@@ -527,7 +582,7 @@ extern "C" int ogc_sa_mlp_layer_dw(int b, int n, int m, int nsample, int cout, i
     int rc = fill_dy(q.dy, cout, m, nsample, dz, go, go_ctotal, go_coff, sel, y, coef);
     if (rc != OGC_OK) return rc;
     if (gather && (!xyz || !new_xyz || !idx || cin < 3 || (cin > 3 && !feat_pm))) return OGC_ERR_INVALID_ARG;
-    if (!gather && (!y_prev || !ss_prev)) return OGC_ERR_INVALID_ARG;
+    if (!gather && !y_prev) return OGC_ERR_INVALID_ARG;    /* ss_prev == NULL: a_{l-1} = y_prev as is */
     q.Cin = cin; q.B = b; q.y_prev = y_prev; q.ss_prev = ss_prev; q.xyz = xyz; q.new_xyz = new_xyz;
     q.feat_pm = feat_pm; q.idx = idx; q.N = n; q.Cf = cin - 3; q.dW = dw;
     cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -31,6 +31,30 @@ FORCE_COMPOSED = False  # tests flip this to compare the two implementations on 
 REFERENCE_FAITHFUL = False
 
 
+# Neighbourhoods computed ahead of time by the trainer (they depend on the coordinates only, so they can run while
+# the latency-bound FPS chain occupies a handful of SMs): {(pc.data_ptr(), kind, k, radius): (dist, idx)}.
+NEIGHBOUR_CACHE = {}
+
+
+def neighbourhood(be, kind, k, radius, pc):
+    """(dist, idx) of one smoothness neighbourhood on the fused path; consumes a prefetched entry when present."""
+    hit = NEIGHBOUR_CACHE.pop((pc.data_ptr(), kind, k, radius), None)
+    if hit is not None:
+        return hit
+    if kind == "knn":
+        # neighbours beyond `radius` are replaced by the nearest one anyway (:121-122): bound the search
+        return be.knn_bounded(k, pc, pc, radius) if radius is not None else be.knn(k, pc, pc, sqrt=True)
+    return None, be.ball_query(radius, k, pc, pc)
+
+
+def smooth_specs(smooth_loss):
+    """The (kind, k, radius) neighbourhoods SmoothLoss will ask for on the fused path (None if it will not fuse)."""
+    a, b = smooth_loss.knn_loss, smooth_loss.ball_q_loss
+    if a.cross_entropy or b.cross_entropy or a.loss_norm != 1 or b.loss_norm != 1:
+        return None
+    return (("knn", a.k, a.radius), ("ball", b.k, b.radius))
+
+
 def _use_fused(*tensors):
     if FORCE_COMPOSED or REFERENCE_FAITHFUL or not all(t.is_cuda for t in tensors):
         return False
@@ -129,12 +153,10 @@ class _NeighborL1Fn(Function):
         grad = torch.zeros_like(mask) if mask.requires_grad else None
         total = None
         for kind, k, radius, coef in specs:
+            dist, idx = neighbourhood(be, kind, k, radius, pc)
             if kind == "knn":
-                # neighbours beyond `radius` are replaced by the nearest one anyway (:121-122): bound the search
-                dist, idx = (be.knn_bounded(k, pc, pc, radius) if radius is not None else be.knn(k, pc, pc, sqrt=True))
                 loss_pt = be.neighbor_l1(mask, idx, dist if radius is not None else None, radius, coef, grad)
             else:
-                idx = be.ball_query(radius, k, pc, pc)
                 loss_pt = be.neighbor_l1(mask, idx, None, None, coef, grad)
             term = loss_pt.mean() * coef
             total = term if total is None else total + term

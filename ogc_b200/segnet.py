@@ -25,7 +25,7 @@ import torch.nn.functional as F
 
 import pointnet2.pointnet2 as ops
 from ogc_b200 import backend as _backend_mod
-from ogc_b200 import sa_fused
+from ogc_b200 import fp_fused, sa_fused
 
 FORCE_COMPOSED = False   # tests: run the torch-composed SA path on the GPU to compare with the fused kernels
 # bench.py's "reference CUDA extension" arm: reproduce the reference's op sequence as written -- nn.Conv
@@ -121,10 +121,16 @@ class SetAbstraction(nn.Module):
         self.npoint, self.radii, self.nsamples = npoint, list(radii), list(nsamples)
         self.mlps = nn.ModuleList(SharedMLP([c[0] + 3] + c[1:]) for c in mlps)  # use_xyz adds 3 inputs
 
-    def forward(self, xyz, features):
-        """xyz (B,N,3), features (B,C,N) -> new_xyz (B,M,3), new_features (B,sum Cout,M)."""
+    def sample(self, xyz):
+        """FPS + centre gather of this level: depends on the coordinates only (see MaskFormer3D.sample_chain)."""
         sel = ops.furthest_point_sample(xyz, self.npoint).long()
-        new_xyz = ops.gather_nd(xyz, sel).contiguous()
+        return ops.gather_nd(xyz, sel).contiguous()
+
+    def forward(self, xyz, features, new_xyz=None):
+        """xyz (B,N,3), features (B,C,N) -> new_xyz (B,M,3), new_features (B,sum Cout,M).
+        `new_xyz`: this level's centres when they were sampled ahead of time."""
+        if new_xyz is None:
+            new_xyz = self.sample(xyz)
         fused = (not FORCE_COMPOSED and not REFERENCE_FAITHFUL and xyz.is_cuda and getattr(_backend_mod.get_backend(), "name", "") == "b200"
                  and all(sa_fused.supported(ns, [m.layer0.conv.weight.shape[1]] +
                                             [getattr(m, f"layer{i}").conv.weight.shape[0] for i in range(m.n_layers)])
@@ -165,6 +171,13 @@ class FeaturePropagation(nn.Module):
 
     def forward(self, unknown, known, unknown_feats, known_feats):
         """unknown (B,n,3), known (B,m,3), unknown_feats (B,C1,n), known_feats (B,C2,m) -> (B,Cout,n)."""
+        widths = [self.mlp.layer0.conv.weight.shape[1]] + [getattr(self.mlp, f"layer{i}").conv.weight.shape[0]
+                                                           for i in range(self.mlp.n_layers)]
+        if (not FORCE_COMPOSED and not REFERENCE_FAITHFUL and unknown.is_cuda and fp_fused.supported(widths)
+                and getattr(_backend_mod.get_backend(), "name", "") == "b200"):
+            layers = [(getattr(self.mlp, f"layer{i}").conv.weight, getattr(self.mlp, f"layer{i}").normlayer.gn.weight,
+                       getattr(self.mlp, f"layer{i}").normlayer.gn.bias) for i in range(self.mlp.n_layers)]
+            return fp_fused.fused_fp(unknown, known, unknown_feats, known_feats, layers)
         dist, idx = ops.three_nn(unknown.contiguous(), known.contiguous())
         recip = 1.0 / (dist + 1e-8)
         weight = recip / recip.sum(dim=2, keepdim=True)
@@ -263,10 +276,19 @@ class MaskFormer3D(nn.Module):
         self.MF_head = MaskFormerHead(n_slot, 256, n_transformer_layer, d, 8, d)
         self.object_mlp = nn.Sequential(ConvGNReLU(d, d, dim=1), ConvGNReLU(d, 64, dim=1, norm=False, act=False))
 
-    def forward(self, pc, point_feats):
-        l_pc, l_feats = [pc], [point_feats.transpose(1, 2).contiguous()]
+    def sample_chain(self, pc):
+        """Centres of every SA level.  The FPS chain is a function of the coordinates alone and is latency-bound on
+        B SMs (one CTA per cloud), so the trainer runs it on a side stream underneath wide kernels."""
+        chain = []
         for sa in self.SA_modules:
-            new_pc, new_feats = sa(l_pc[-1], l_feats[-1])
+            pc = sa.sample(pc)
+            chain.append(pc)
+        return chain
+
+    def forward(self, pc, point_feats, centres=None):
+        l_pc, l_feats = [pc], [point_feats.transpose(1, 2).contiguous()]
+        for i, sa in enumerate(self.SA_modules):
+            new_pc, new_feats = sa(l_pc[-1], l_feats[-1], None if centres is None else centres[i])
             l_pc.append(new_pc)
             l_feats.append(new_feats)
         for i in range(len(self.FP_modules) - 1, -1, -1):     # coarse -> fine; FP_modules[i] lifts level i+1 to i

@@ -111,6 +111,8 @@ class SegTrainer:
         self.sched = dict(lr=lr, lr_decay=lr_decay, decay_step=decay_step, lr_clip=lr_clip)
         self.global_batch_size, self.world_size = global_batch_size, world_size
         self.device = self.opt.flat_p.device
+        self.overlap_geometry = True      # FPS chain on a side stream under the loss neighbourhoods
+        self._geo_stream = None
 
     def _step_body(self, pcs, flows, it, aug_transform, defer):
         """zero_grad -> forward -> loss -> backward -> NaN count -> all-reduce -> Adam launch (no host sync when
@@ -119,8 +121,9 @@ class SegTrainer:
         self.opt.zero_grad()
         b, t, n, _ = pcs.shape
         flat = pcs.view(b * t, n, 3)
-        masks = self.segnet(flat, flat).view(b, t, n, -1)
         pcs_l = [pcs[:, i].contiguous() for i in range(t)]
+        centres = self._prefetch_geometry(flat, pcs_l) if self.overlap_geometry and flat.is_cuda else None
+        masks = self.segnet(flat, flat, centres).view(b, t, n, -1)
         masks_l = [masks[:, i].contiguous() for i in range(t)]
         flows_l = [flows[:, i].contiguous() for i in range(t)]
         self.criterion.defer_logging = defer
@@ -134,6 +137,31 @@ class SegTrainer:
         if self.world_size > 1:
             dist.all_reduce(self.opt.flat_g_ext)          # the step's only collective: grads + NaN counter
         return loss_dict
+
+    def _prefetch_geometry(self, flat, pcs_l):
+        """Everything that depends on the coordinates alone, arranged so that the latency-bound FPS chain (one CTA
+        per cloud: 16 of 148 SMs busy for ~1.8 ms at KITTI-SF sizes) runs on a side stream UNDERNEATH the loss
+        neighbourhoods (k-NN + ball query on 8192 x 8192, thousands of small CTAs that flow around it).  Fork / join
+        with stream events, so it is captured into the step's CUDA graph as two parallel branches."""
+        from . import losses
+        be = get_backend()
+        if getattr(be, "name", "") != "b200" or losses.FORCE_COMPOSED or losses.REFERENCE_FAITHFUL:
+            return None
+        main = torch.cuda.current_stream()
+        if self._geo_stream is None:
+            self._geo_stream = torch.cuda.Stream()
+        side = self._geo_stream
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            centres = self.segnet.sample_chain(flat)
+        specs = losses.smooth_specs(self.criterion.smooth_loss) if hasattr(self.criterion, "smooth_loss") else None
+        losses.NEIGHBOUR_CACHE.clear()
+        if specs:
+            for pc in pcs_l:
+                for kind, k, radius in specs:
+                    losses.NEIGHBOUR_CACHE[(pc.data_ptr(), kind, k, radius)] = losses.neighbourhood(be, kind, k, radius, pc)
+        main.wait_stream(side)
+        return centres
 
     def train_step(self, it, batch, aug_transform=False):
         """batch = (pcs (b,t,N,3), segms, flows (b,t,N,3), valids) on host or device.  Returns loss_dict.

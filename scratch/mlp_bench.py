@@ -10,6 +10,7 @@ torch.manual_seed(0)
 cfgs=[("SA1a",8192,2048,3,[32,32,32]),("SA1b",8192,2048,3,[32,32,64]),("SA2",2048,1024,96,[64,64,128]),("SA3",1024,512,128,[128,128,256])]
 reps=int(sys.argv[1]) if len(sys.argv)>1 else 3
 import os
+if os.environ.get('CFGS'): cfgs=[c for c in cfgs if c[0] in os.environ['CFGS'].split(',')]
 from ogc_b200 import sa_fused as _sf
 _sf.TC_DW_ALL = os.environ.get("TC_DW_ALL","0")=="1"
 for name,N,M,Cf,w in cfgs:
