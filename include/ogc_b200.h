@@ -349,6 +349,25 @@ OGC_API int ogc_pw_mlp_input_grad(int b, int p, int cout, int cin_full, int row_
                                   const float *y, const float *coef, const float *w, float *dx, int dx_ctotal,
                                   int dx_coff, void *stream);
 
+/* =====================================================================================
+ * Narrow SharedMLP layers (csrc/mlp_narrow.cu): the 32 -> 32 / 32 -> 64 layers of the first SA level
+ * (models/segnet_kitti.py:27-33) in a warp-per-centre / channels-in-registers mapping.  Same operands and results
+ * as ogc_sa_mlp_layer_fwd / _dx / _dw (dense, gather = 0); nsample == 64, cin (cprev) == 32, cout in {32, 64}.
+ * w is W (cout,cin) row-major (NOT transposed).
+ * ===================================================================================== */
+OGC_API int ogc_sa_mlp_narrow_fwd(int b, int m, int nsample, int cin, int cout, int last, const float *y_prev,
+                                  const float *ss_prev, const float *w, float *y, double *sums, float *ymax,
+                                  float *ymin, unsigned char *amax, unsigned char *amin, void *stream);
+OGC_API int ogc_sa_mlp_narrow_dx(int b, int m, int nsample, int cout, int cprev, const float *dz, const float *go,
+                                 int go_ctotal, int go_coff, const unsigned char *sel, const float *y,
+                                 const float *coef, const float *w, const float *y_prev, const float *ss_prev,
+                                 const float *mean_rstd_prev, const float *gamma_prev, float *dz_prev,
+                                 double *ab_prev, float *dgamma_prev, float *dbeta_prev, void *stream);
+OGC_API int ogc_sa_mlp_narrow_dw(int b, int m, int nsample, int cout, int cin, const float *dz, const float *go,
+                                 int go_ctotal, int go_coff, const unsigned char *sel, const float *y,
+                                 const float *coef, const float *y_prev, const float *ss_prev, float *dw,
+                                 void *stream);
+
 #ifdef __cplusplus
 }
 #endif

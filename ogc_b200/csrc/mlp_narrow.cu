@@ -1,0 +1,476 @@
+// Narrow SharedMLP layers of the first set-abstraction level (32 -> 32 and 32 -> 64 channels over
+// B * M * 64 = 2.1 M positions at KITTI-SF sizes): forward, input gradient and weight gradient.
+//
+// These layers move ~1 GB each and need only 2-4 KFLOP per position, so they are bound by how many bytes a
+// CTA keeps in flight, not by the contraction.  The tiled kernels (mlp.cu / mlp_tc*.cu: shared-memory operand
+// tiles, barriers and -- on the tensor-core path -- a 64-position tile per MMA round trip) reach 1.2-2.3 TB/s
+// here (profiles/r01_ncu_full_sa_mlp_tc_kernels.csv: DRAM bytes == algorithmic bytes, 20 % warp occupancy,
+// issue slots idle).  This file maps the work the other way round:
+//
+//   forward / dX : a WARP owns the 64 samples of one centre, a LANE owns two adjacent positions and keeps ALL
+//                  their channels in registers; every global access is a coalesced 256-byte row segment
+//                  (channel-major tensors), 64 of them in flight per warp before the first use; the weights are
+//                  broadcast from shared memory (one LDS.128 per 8 FMAs); no barrier inside the main loop.
+//                  GroupNorm+ReLU of the previous layer is applied in registers, the GroupNorm sums fall out of
+//                  the accumulators, the max / min over the 64 samples is two redux.sync + two ballots per
+//                  channel, and the per-channel backward sums use a 31-shuffle transpose-reduction.
+//   dW           : C_out x 32 outputs reduced over millions of positions: dY and a tiles are staged channel-major
+//                  in shared memory, lane = input channel, each warp a slice of the tile's positions, the whole
+//                  C_out column of partial sums in registers across all tiles of the CTA.
+//
+// fp32 FMA throughout (bit-level fp32 conv semantics).  Same operand / result contract as the generic kernels,
+// which the tests compare them against.
+#include "mlp_common.cuh"
+#include "mlp_dy.cuh"
+
+namespace ogc {
+
+constexpr int kNwThreads = 256;
+constexpr int kNwWarps = kNwThreads / 32;
+constexpr int kNwUnit = 64;   // positions per warp step == nsample
+
+// order-preserving map float -> uint32 (for redux.sync max / min)
+__device__ __forceinline__ uint32_t f2ord(float x) {
+    const uint32_t b = __float_as_uint(x);
+    return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t k) {
+    return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu));
+}
+
+// v[c] (c < 32) per lane  ->  returns sum over the 32 lanes of v[lane]  (31 shuffles instead of 160)
+__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const bool up = lane & 16;
+        const float send = up ? v[i] : v[i + 16];
+        const float keep = up ? v[i + 16] : v[i];
+        v[i] = keep + __shfl_xor_sync(OGC_FULL_MASK, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const bool up = lane & 8;
+        const float send = up ? v[i] : v[i + 8];
+        const float keep = up ? v[i + 8] : v[i];
+        v[i] = keep + __shfl_xor_sync(OGC_FULL_MASK, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const bool up = lane & 4;
+        const float send = up ? v[i] : v[i + 4];
+        const float keep = up ? v[i + 4] : v[i];
+        v[i] = keep + __shfl_xor_sync(OGC_FULL_MASK, send, 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const bool up = lane & 2;
+        const float send = up ? v[i] : v[i + 2];
+        const float keep = up ? v[i + 2] : v[i];
+        v[i] = keep + __shfl_xor_sync(OGC_FULL_MASK, send, 2);
+    }
+    {
+        const bool up = lane & 1;
+        const float send = up ? v[0] : v[1];
+        const float keep = up ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(OGC_FULL_MASK, send, 1);
+    }
+    return v[0];
+}
+
+// ------------------------------------------------------------------------------------------ forward
+struct NarrowFwdParams {
+    int P, M;
+    const float *y_prev, *ss_prev;   // (B,CIN,P), (B,CIN,2)
+    const float *W;                  // (COUT,CIN) row-major
+    float *y;                        // (B,COUT,P)
+    double *sums;                    // (B,4,2)
+    float *ymax, *ymin;              // (B,COUT,M) when LAST
+    unsigned char *amax, *amin;
+};
+
+template <int CIN, int COUT, bool LAST>
+__global__ void __launch_bounds__(kNwThreads, 2)
+narrow_fwd_kernel(NarrowFwdParams q) {
+    constexpr int CPG = COUT / kGnGroups;
+    __shared__ __align__(16) float Ws[COUT * CIN];
+    __shared__ float2 ss_s[CIN];
+    __shared__ double gs[kGnGroups][2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y, P = q.P;
+    for (int e = tid; e < COUT * CIN; e += kNwThreads) Ws[e] = __ldg(q.W + e);
+    for (int c = tid; c < CIN; c += kNwThreads) ss_s[c] = __ldg(reinterpret_cast<const float2 *>(q.ss_prev) + static_cast<size_t>(b) * CIN + c);
+    if (tid < kGnGroups * 2) (&gs[0][0])[tid] = 0.0;
+    __syncthreads();
+    const float4 *Ws4 = reinterpret_cast<const float4 *>(Ws);
+
+    float gsum[kGnGroups], gsq[kGnGroups];
+#pragma unroll
+    for (int g = 0; g < kGnGroups; ++g) gsum[g] = gsq[g] = 0.f;
+
+    const int nunits = P / kNwUnit;
+    for (int u = blockIdx.x * kNwWarps + warp; u < nunits; u += gridDim.x * kNwWarps) {
+        const size_t p0 = static_cast<size_t>(u) * kNwUnit + 2 * lane;
+        const float *src = q.y_prev + static_cast<size_t>(b) * CIN * P + p0;
+        float a0[CIN], a1[CIN];
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) {
+            const float2 v = __ldg(reinterpret_cast<const float2 *>(src + static_cast<size_t>(c) * P));
+            a0[c] = v.x; a1[c] = v.y;
+        }
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) {
+            const float2 s = ss_s[c];
+            a0[c] = fmaxf(fmaf(s.x, a0[c], s.y), 0.f);
+            a1[c] = fmaxf(fmaf(s.x, a1[c], s.y), 0.f);
+        }
+        float *dst = q.y + static_cast<size_t>(b) * COUT * P + p0;
+#pragma unroll
+        for (int g = 0; g < kGnGroups; ++g) {
+            float s = 0.f, sq = 0.f;
+#pragma unroll 1
+            for (int cb = 0; cb < CPG; cb += 4) {
+                const int co0 = g * CPG + cb;
+                float r0[4] = {0.f, 0.f, 0.f, 0.f}, r1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int c4 = 0; c4 < CIN / 4; ++c4) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 w = Ws4[(co0 + j) * (CIN / 4) + c4];
+                        r0[j] = fmaf(w.x, a0[c4 * 4 + 0], r0[j]); r1[j] = fmaf(w.x, a1[c4 * 4 + 0], r1[j]);
+                        r0[j] = fmaf(w.y, a0[c4 * 4 + 1], r0[j]); r1[j] = fmaf(w.y, a1[c4 * 4 + 1], r1[j]);
+                        r0[j] = fmaf(w.z, a0[c4 * 4 + 2], r0[j]); r1[j] = fmaf(w.z, a1[c4 * 4 + 2], r1[j]);
+                        r0[j] = fmaf(w.w, a0[c4 * 4 + 3], r0[j]); r1[j] = fmaf(w.w, a1[c4 * 4 + 3], r1[j]);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    *reinterpret_cast<float2 *>(dst + static_cast<size_t>(co0 + j) * P) = make_float2(r0[j], r1[j]);
+                    s += r0[j] + r1[j];
+                    sq += r0[j] * r0[j] + r1[j] * r1[j];
+                    if (LAST) {
+                        const uint32_t k0 = f2ord(r0[j]), k1 = f2ord(r1[j]);
+                        const uint32_t kmax = __reduce_max_sync(OGC_FULL_MASK, max(k0, k1));
+                        const uint32_t kmin = __reduce_min_sync(OGC_FULL_MASK, min(k0, k1));
+                        const unsigned bx0 = __ballot_sync(OGC_FULL_MASK, k0 == kmax), bx1 = __ballot_sync(OGC_FULL_MASK, k1 == kmax);
+                        const unsigned bn0 = __ballot_sync(OGC_FULL_MASK, k0 == kmin), bn1 = __ballot_sync(OGC_FULL_MASK, k1 == kmin);
+                        if (lane == 0) {
+                            // first position holding the extreme value: even positions are r0, odd ones r1
+                            const int px0 = bx0 ? 2 * (__ffs(bx0) - 1) : 64, px1 = bx1 ? 2 * (__ffs(bx1) - 1) + 1 : 64;
+                            const int pn0 = bn0 ? 2 * (__ffs(bn0) - 1) : 64, pn1 = bn1 ? 2 * (__ffs(bn1) - 1) + 1 : 64;
+                            const size_t o = (static_cast<size_t>(b) * COUT + co0 + j) * q.M + u;
+                            q.ymax[o] = ord2f(kmax); q.ymin[o] = ord2f(kmin);
+                            q.amax[o] = static_cast<unsigned char>(min(px0, px1));
+                            q.amin[o] = static_cast<unsigned char>(min(pn0, pn1));
+                        }
+                    }
+                }
+            }
+            gsum[g] += s; gsq[g] += sq;
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < kGnGroups; ++g) {
+        float s = gsum[g], sq = gsq[g];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(OGC_FULL_MASK, s, o);
+            sq += __shfl_xor_sync(OGC_FULL_MASK, sq, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&gs[g][0], static_cast<double>(s));
+            atomicAdd(&gs[g][1], static_cast<double>(sq));
+        }
+    }
+    __syncthreads();
+    if (tid < kGnGroups * 2) atomicAdd(q.sums + static_cast<size_t>(b) * kGnGroups * 2 + tid, (&gs[0][0])[tid]);
+}
+
+// ------------------------------------------------------------------------------------------ dX
+struct NarrowDxParams {
+    int P, M;
+    const float *dz;                  // (B,COUT,P), or NULL: synthesised from go / sel (last layer)
+    const float *go;                  // (B,go_ctotal,M)
+    const unsigned char *sel;         // (B,COUT,M)
+    int go_ctotal, go_coff;
+    const float *y, *coef;            // (B,COUT,P), (B,COUT,4) = k1, k2, k3r, mean
+    const float *W;                   // (COUT,CPREV) row-major
+    const float *y_prev, *ss_prev, *mean_rstd_prev, *gamma_prev;
+    float *dz_prev;                   // (B,CPREV,P)
+    double *ab_prev;                  // (B,4,2)
+    float *dgamma_prev, *dbeta_prev;
+};
+
+template <int COUT, bool SYNTH>
+__global__ void __launch_bounds__(kNwThreads, 2)
+narrow_dx_kernel(NarrowDxParams q) {
+    constexpr int CPREV = 32, CH = 8;
+    __shared__ __align__(16) float Ws[COUT * CPREV];
+    __shared__ __align__(16) float4 coef_s[COUT];
+    __shared__ float4 prev_s[CPREV];            // scale, shift, mean, rstd of the previous layer's channels
+    __shared__ float rowacc[CPREV][2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y, P = q.P;
+    for (int e = tid; e < COUT * CPREV; e += kNwThreads) Ws[e] = __ldg(q.W + e);
+    for (int c = tid; c < COUT; c += kNwThreads) coef_s[c] = __ldg(reinterpret_cast<const float4 *>(q.coef) + static_cast<size_t>(b) * COUT + c);
+    for (int c = tid; c < CPREV; c += kNwThreads) {
+        const int g = c / (CPREV / kGnGroups);
+        prev_s[c] = make_float4(__ldg(q.ss_prev + (static_cast<size_t>(b) * CPREV + c) * 2), __ldg(q.ss_prev + (static_cast<size_t>(b) * CPREV + c) * 2 + 1),
+                                __ldg(q.mean_rstd_prev + (b * kGnGroups + g) * 2), __ldg(q.mean_rstd_prev + (b * kGnGroups + g) * 2 + 1));
+        rowacc[c][0] = rowacc[c][1] = 0.f;
+    }
+    __syncthreads();
+    const float4 *Ws4 = reinterpret_cast<const float4 *>(Ws);
+    float tot_s = 0.f, tot_sy = 0.f;            // lane = channel of layer l-1
+
+    const int nunits = P / kNwUnit;
+    for (int u = blockIdx.x * kNwWarps + warp; u < nunits; u += gridDim.x * kNwWarps) {
+        const size_t p0 = static_cast<size_t>(u) * kNwUnit + 2 * lane;
+        const float *yp = q.y + static_cast<size_t>(b) * COUT * P + p0;
+        const float *zp = SYNTH ? nullptr : q.dz + static_cast<size_t>(b) * COUT * P + p0;
+        float acc0[CPREV], acc1[CPREV];
+#pragma unroll
+        for (int i = 0; i < CPREV; ++i) acc0[i] = acc1[i] = 0.f;
+#pragma unroll 1
+        for (int cb = 0; cb < COUT; cb += CH) {
+            float2 yv[CH], zv[CH];
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+                yv[j] = __ldg(reinterpret_cast<const float2 *>(yp + static_cast<size_t>(cb + j) * P));
+                if (SYNTH) {
+                    const size_t o = (static_cast<size_t>(b) * COUT + cb + j) * q.M + u;
+                    const int sl = __ldg(q.sel + o);
+                    const float g = __ldg(q.go + (static_cast<size_t>(b) * q.go_ctotal + q.go_coff + cb + j) * q.M + u);
+                    zv[j] = make_float2(sl == 2 * lane ? g : 0.f, sl == 2 * lane + 1 ? g : 0.f);
+                } else {
+                    zv[j] = __ldg(reinterpret_cast<const float2 *>(zp + static_cast<size_t>(cb + j) * P));
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+                const float4 cf = coef_s[cb + j];
+                const float d0 = fmaf(cf.x, zv[j].x, -cf.y) - (yv[j].x - cf.w) * cf.z;
+                const float d1 = fmaf(cf.x, zv[j].y, -cf.y) - (yv[j].y - cf.w) * cf.z;
+#pragma unroll
+                for (int c4 = 0; c4 < CPREV / 4; ++c4) {
+                    const float4 w = Ws4[(cb + j) * (CPREV / 4) + c4];
+                    acc0[c4 * 4 + 0] = fmaf(d0, w.x, acc0[c4 * 4 + 0]); acc1[c4 * 4 + 0] = fmaf(d1, w.x, acc1[c4 * 4 + 0]);
+                    acc0[c4 * 4 + 1] = fmaf(d0, w.y, acc0[c4 * 4 + 1]); acc1[c4 * 4 + 1] = fmaf(d1, w.y, acc1[c4 * 4 + 1]);
+                    acc0[c4 * 4 + 2] = fmaf(d0, w.z, acc0[c4 * 4 + 2]); acc1[c4 * 4 + 2] = fmaf(d1, w.z, acc1[c4 * 4 + 2]);
+                    acc0[c4 * 4 + 3] = fmaf(d0, w.w, acc0[c4 * 4 + 3]); acc1[c4 * 4 + 3] = fmaf(d1, w.w, acc1[c4 * 4 + 3]);
+                }
+            }
+        }
+        // ---- epilogue: ReLU mask of layer l-1, store dz_{l-1}, per-channel GroupNorm-backward sums ----
+        const float *pp = q.y_prev + static_cast<size_t>(b) * CPREV * P + p0;
+        float *dp = q.dz_prev + static_cast<size_t>(b) * CPREV * P + p0;
+#pragma unroll
+        for (int cb = 0; cb < CPREV; cb += CH) {
+            float2 pv[CH];
+#pragma unroll
+            for (int j = 0; j < CH; ++j) pv[j] = __ldg(reinterpret_cast<const float2 *>(pp + static_cast<size_t>(cb + j) * P));
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+                const float4 pr = prev_s[cb + j];
+                const float g0 = fmaf(pr.x, pv[j].x, pr.y) > 0.f ? acc0[cb + j] : 0.f;
+                const float g1 = fmaf(pr.x, pv[j].y, pr.y) > 0.f ? acc1[cb + j] : 0.f;
+                *reinterpret_cast<float2 *>(dp + static_cast<size_t>(cb + j) * P) = make_float2(g0, g1);
+                acc0[cb + j] = g0 + g1;
+                acc1[cb + j] = g0 * ((pv[j].x - pr.z) * pr.w) + g1 * ((pv[j].y - pr.z) * pr.w);
+            }
+        }
+        tot_s += warp_transpose_sum32(acc0, lane);
+        tot_sy += warp_transpose_sum32(acc1, lane);
+    }
+    atomicAdd(&rowacc[lane][0], tot_s);
+    atomicAdd(&rowacc[lane][1], tot_sy);
+    __syncthreads();
+    if (tid < CPREV) {
+        const float a = rowacc[tid][0], c = rowacc[tid][1];
+        atomicAdd(q.dbeta_prev + tid, a);
+        atomicAdd(q.dgamma_prev + tid, c);
+        const int g = tid / (CPREV / kGnGroups);
+        const double gm = static_cast<double>(__ldg(q.gamma_prev + tid));
+        atomicAdd(q.ab_prev + (b * kGnGroups + g) * 2, gm * a);
+        atomicAdd(q.ab_prev + (b * kGnGroups + g) * 2 + 1, gm * c);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ dW
+struct NarrowDwParams {
+    DySrc dy;                        // layer l (rows of dW = COUT)
+    int B;
+    const float *y_prev, *ss_prev;   // (B,32,P), (B,32,2)
+    float *dW;                       // (COUT,32), accumulated atomically
+};
+
+template <int COUT>
+__global__ void __launch_bounds__(kNwThreads, 2)
+narrow_dw_kernel(NarrowDwParams q) {
+    constexpr int CIN = 32, TP = 128, LD = TP + 4, Q4 = TP / 4;
+    extern __shared__ __align__(16) float smem[];
+    float *Ds = smem;                // [COUT][LD]  dY
+    float *As = smem + COUT * LD;    // [CIN][LD]   a_{l-1}
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int P = q.dy.P;
+    const int tiles_per_sample = P / TP;
+    const int total = q.B * tiles_per_sample;
+    float acc[COUT];
+#pragma unroll
+    for (int i = 0; i < COUT; ++i) acc[i] = 0.f;
+
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int b = w / tiles_per_sample, p_base = (w - b * tiles_per_sample) * TP;
+        __syncthreads();
+        // a tile: thread -> (channel, quad); 4 independent 16-byte loads in flight
+        {
+            float4 v[CIN * Q4 / kNwThreads];
+#pragma unroll
+            for (int i = 0; i < CIN * Q4 / kNwThreads; ++i) {
+                const int e = tid + i * kNwThreads, c = e / Q4, p = (e - c * Q4) * 4;
+                v[i] = __ldg(reinterpret_cast<const float4 *>(q.y_prev + (static_cast<size_t>(b) * CIN + c) * P + p_base + p));
+            }
+#pragma unroll
+            for (int i = 0; i < CIN * Q4 / kNwThreads; ++i) {
+                const int e = tid + i * kNwThreads, c = e / Q4, p = (e - c * Q4) * 4;
+                const float s = __ldg(q.ss_prev + (static_cast<size_t>(b) * CIN + c) * 2), h = __ldg(q.ss_prev + (static_cast<size_t>(b) * CIN + c) * 2 + 1);
+                *reinterpret_cast<float4 *>(As + c * LD + p) = make_float4(fmaxf(fmaf(s, v[i].x, h), 0.f), fmaxf(fmaf(s, v[i].y, h), 0.f),
+                                                                          fmaxf(fmaf(s, v[i].z, h), 0.f), fmaxf(fmaf(s, v[i].w, h), 0.f));
+            }
+        }
+        // dY tile
+#pragma unroll
+        for (int i0 = 0; i0 < COUT * Q4 / kNwThreads; i0 += 4) {
+            DyRaw raw[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int e = tid + (i0 + k) * kNwThreads, c = e / Q4, p = (e - c * Q4) * 4;
+                dy_quad_load(q.dy, b, c, p_base + p, raw[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int e = tid + (i0 + k) * kNwThreads, c = e / Q4, p = (e - c * Q4) * 4;
+                *reinterpret_cast<float4 *>(Ds + c * LD + p) = dy_quad_finish(q.dy, p_base + p, raw[k]);
+            }
+        }
+        __syncthreads();
+        // lane = input channel; warp = 16 positions of the tile
+#pragma unroll
+        for (int pq = 0; pq < TP / kNwWarps / 4; ++pq) {
+            const int p = warp * (TP / kNwWarps) + pq * 4;
+            const float4 av = *reinterpret_cast<const float4 *>(As + lane * LD + p);
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) {
+                const float4 d = *reinterpret_cast<const float4 *>(Ds + co * LD + p);
+                acc[co] = fmaf(d.x, av.x, fmaf(d.y, av.y, fmaf(d.z, av.z, fmaf(d.w, av.w, acc[co]))));
+            }
+        }
+    }
+    // reduce the 8 warps' partial columns through shared memory, then one atomic per output
+    __syncthreads();
+    float *red = smem;               // [kNwWarps][COUT][33]
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) red[(warp * COUT + co) * 33 + lane] = acc[co];
+    __syncthreads();
+    for (int e = tid; e < COUT * CIN; e += kNwThreads) {
+        const int co = e / CIN, ci = e - co * CIN;
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kNwWarps; ++w) s += red[(w * COUT + co) * 33 + ci];
+        atomicAdd(q.dW + e, s);
+    }
+}
+
+static int narrow_grid_x(int B, int nunits) {
+    int per_sample = (kNumSMs * 2 + B - 1) / B;
+    const int need = (nunits + kNwWarps - 1) / kNwWarps;
+    if (per_sample > need) per_sample = need;
+    return per_sample < 1 ? 1 : per_sample;
+}
+
+}  // namespace ogc
+
+extern "C" int ogc_sa_mlp_narrow_fwd(int b, int m, int nsample, int cin, int cout, int last, const float *y_prev,
+                                     const float *ss_prev, const float *w, float *y, double *sums, float *ymax,
+                                     float *ymin, unsigned char *amax, unsigned char *amin, void *stream) {
+    using namespace ogc;
+    if (b < 0 || m <= 0 || nsample <= 0 || cin <= 0 || cout <= 0) return OGC_ERR_INVALID_ARG;
+    if (b == 0) return OGC_OK;
+    if (!y_prev || !ss_prev || !w || !y || !sums) return OGC_ERR_INVALID_ARG;
+    if (last && (!ymax || !ymin || !amax || !amin)) return OGC_ERR_INVALID_ARG;
+    if (nsample != 64 || cin != 32 || (cout != 32 && cout != 64) || b > 65535) return OGC_ERR_UNSUPPORTED;
+    NarrowFwdParams q;
+    q.P = m * nsample; q.M = m; q.y_prev = y_prev; q.ss_prev = ss_prev; q.W = w; q.y = y; q.sums = sums;
+    q.ymax = ymax; q.ymin = ymin; q.amax = amax; q.amin = amin;
+    dim3 grid(narrow_grid_x(b, m), b);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (cout == 32) {
+        if (last) narrow_fwd_kernel<32, 32, true><<<grid, kNwThreads, 0, st>>>(q);
+        else narrow_fwd_kernel<32, 32, false><<<grid, kNwThreads, 0, st>>>(q);
+    } else {
+        if (last) narrow_fwd_kernel<32, 64, true><<<grid, kNwThreads, 0, st>>>(q);
+        else narrow_fwd_kernel<32, 64, false><<<grid, kNwThreads, 0, st>>>(q);
+    }
+    OGC_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int ogc_sa_mlp_narrow_dx(int b, int m, int nsample, int cout, int cprev, const float *dz, const float *go,
+                                    int go_ctotal, int go_coff, const unsigned char *sel, const float *y,
+                                    const float *coef, const float *w, const float *y_prev, const float *ss_prev,
+                                    const float *mean_rstd_prev, const float *gamma_prev, float *dz_prev,
+                                    double *ab_prev, float *dgamma_prev, float *dbeta_prev, void *stream) {
+    using namespace ogc;
+    if (b < 0 || m <= 0 || nsample <= 0 || cout <= 0 || cprev <= 0) return OGC_ERR_INVALID_ARG;
+    if (b == 0) return OGC_OK;
+    if (!y || !coef || !w || !y_prev || !ss_prev || !mean_rstd_prev || !gamma_prev || !dz_prev || !ab_prev || !dgamma_prev || !dbeta_prev)
+        return OGC_ERR_INVALID_ARG;
+    if (!dz && (!go || !sel)) return OGC_ERR_INVALID_ARG;
+    if (nsample != 64 || cprev != 32 || (cout != 32 && cout != 64) || b > 65535) return OGC_ERR_UNSUPPORTED;
+    NarrowDxParams q;
+    q.P = m * nsample; q.M = m; q.dz = dz; q.go = go; q.sel = sel; q.go_ctotal = go_ctotal; q.go_coff = go_coff;
+    q.y = y; q.coef = coef; q.W = w; q.y_prev = y_prev; q.ss_prev = ss_prev; q.mean_rstd_prev = mean_rstd_prev;
+    q.gamma_prev = gamma_prev; q.dz_prev = dz_prev; q.ab_prev = ab_prev; q.dgamma_prev = dgamma_prev; q.dbeta_prev = dbeta_prev;
+    dim3 grid(narrow_grid_x(b, m), b);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (cout == 32) {
+        if (dz) narrow_dx_kernel<32, false><<<grid, kNwThreads, 0, st>>>(q);
+        else narrow_dx_kernel<32, true><<<grid, kNwThreads, 0, st>>>(q);
+    } else {
+        if (dz) narrow_dx_kernel<64, false><<<grid, kNwThreads, 0, st>>>(q);
+        else narrow_dx_kernel<64, true><<<grid, kNwThreads, 0, st>>>(q);
+    }
+    OGC_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int ogc_sa_mlp_narrow_dw(int b, int m, int nsample, int cout, int cin, const float *dz, const float *go,
+                                    int go_ctotal, int go_coff, const unsigned char *sel, const float *y,
+                                    const float *coef, const float *y_prev, const float *ss_prev, float *dw,
+                                    void *stream) {
+    using namespace ogc;
+    if (b < 0 || m <= 0 || nsample <= 0 || cout <= 0 || cin <= 0 || !dw) return OGC_ERR_INVALID_ARG;
+    if (b == 0) return OGC_OK;
+    if (!y_prev || !ss_prev) return OGC_ERR_INVALID_ARG;
+    if (nsample != 64 || cin != 32 || (cout != 32 && cout != 64)) return OGC_ERR_UNSUPPORTED;
+    NarrowDwParams q;
+    int rc = fill_dy(q.dy, cout, m, nsample, dz, go, go_ctotal, go_coff, sel, y, coef);
+    if (rc != OGC_OK) return rc;
+    if ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(y_prev) | (dz ? reinterpret_cast<uintptr_t>(dz) : 0)) & 15u)
+        return OGC_ERR_UNSUPPORTED;
+    q.B = b; q.y_prev = y_prev; q.ss_prev = ss_prev; q.dW = dw;
+    const int total = b * (m * nsample / 128);
+    const int gx = total < kNumSMs * 2 ? total : kNumSMs * 2;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t smem_tile = static_cast<size_t>(cout + 32) * 132 * sizeof(float);
+    const size_t smem_red = static_cast<size_t>(kNwWarps) * cout * 33 * sizeof(float);
+    const size_t smem = smem_tile > smem_red ? smem_tile : smem_red;
+    cudaError_t e;
+    if (cout == 32) {
+        e = cudaFuncSetAttribute(narrow_dw_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return static_cast<int>(e);
+        narrow_dw_kernel<32><<<gx, kNwThreads, smem, st>>>(q);
+    } else {
+        e = cudaFuncSetAttribute(narrow_dw_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return static_cast<int>(e);
+        narrow_dw_kernel<64><<<gx, kNwThreads, smem, st>>>(q);
+    }
+    OGC_RETURN_LAUNCH_STATUS();
+}

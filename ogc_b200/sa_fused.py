@@ -24,6 +24,13 @@ def _tc_ok(S, cin, cout, gather):
     return USE_TC and S == 64 and cout >= 64 and cout % 16 == 0 and cout <= 256 and 32 <= k <= 128 and k % 4 == 0
 
 
+USE_NARROW = True   # warp-per-centre kernels (csrc/mlp_narrow.cu) for the dense 32 -> 32 / 32 -> 64 layers of SA level 1
+
+
+def _narrow_ok(S, cin, cout):
+    return USE_NARROW and S == 64 and cin == 32 and cout in (32, 64)
+
+
 TC_DW_ALL = False   # tests: route every supported dW through the tensor-core kernel
 
 
@@ -78,10 +85,16 @@ class _FusedSAMLP(Function):
             else:
                 ymax = ymin = amax = amin = None
             flops_bytes = B * (4 * cout * P + (4 * cin * P if l else 4 * P + 12 * N + 4 * N * Cf))
-            use_tc = _tc_ok(S, cin, cout, l == 0)
-            tag = "sa_mlp_fwd_tc" if use_tc else "sa_mlp_fwd"
+            use_nw = l > 0 and _narrow_ok(S, cin, cout)
+            use_tc = not use_nw and _tc_ok(S, cin, cout, l == 0)
+            tag = "sa_mlp_fwd_nw" if use_nw else "sa_mlp_fwd_tc" if use_tc else "sa_mlp_fwd"
             with TIMER.span(f"{tag}[{cin}>{cout}]" if TIMER.detail else tag, flops_bytes):
-                if use_tc:
+                if use_nw:
+                    w2d = W.detach().reshape(cout, cin).contiguous()
+                    _lib.check(lib.ogc_sa_mlp_narrow_fwd(
+                        B, M, S, cin, cout, int(last), _p(y_prev), _p(ss_prev), _p(w2d), _p(y), _p(sums), _p(ymax),
+                        _p(ymin), _p(amax), _p(amin), _st()), "ogc_sa_mlp_narrow_fwd")
+                elif use_tc:
                     w2d = W.detach().reshape(cout, cin).contiguous()
                     _lib.check(lib.ogc_sa_mlp_layer_fwd_tc(
                         B, N, M, S, cin, cout, int(l == 0), int(last), _p(xyz), _p(new_xyz), _p(feat_pm), _p(idx),
@@ -149,13 +162,20 @@ class _FusedSAMLP(Function):
             grads[3 * l + 1], grads[3 * l + 2] = dgamma, dbeta
             dW = torch.zeros(cout, cin, **f32)
             gather = l == 0
-            dw_tc = _tc_dw_ok(S, cin, cout)
+            dw_nw = not gather and _narrow_ok(S, cin, cout)
+            dw_tc = not dw_nw and _tc_dw_ok(S, cin, cout)
             dw_fn, dw_tag = (lib.ogc_sa_mlp_layer_dw_tc, "sa_mlp_dw_tc") if dw_tc else (lib.ogc_sa_mlp_layer_dw, "sa_mlp_dw")
-            with TIMER.span(f"{dw_tag}[{cin}>{cout}]" if TIMER.detail else dw_tag, B * P * 4 * (2 * cout + cin)):
-                _lib.check(dw_fn(
-                    B, N, M, S, cout, cin, int(gather), _p(dz), _p(go), cL, 0, _p(sel), _p(ys[l]), _p(coef),
-                    _p(ys[l - 1]) if l else None, _p(sss[l - 1]) if l else None,
-                    _p(xyz), _p(new_xyz), _p(feat_pm), _p(idx), _p(dW), _st()), "ogc_sa_mlp_layer_dw")
+            if dw_nw:
+                with TIMER.span(f"sa_mlp_dw_nw[{cin}>{cout}]" if TIMER.detail else "sa_mlp_dw_nw", B * P * 4 * (2 * cout + cin)):
+                    _lib.check(lib.ogc_sa_mlp_narrow_dw(
+                        B, M, S, cout, cin, _p(dz), _p(go), cL, 0, _p(sel), _p(ys[l]), _p(coef), _p(ys[l - 1]),
+                        _p(sss[l - 1]), _p(dW), _st()), "ogc_sa_mlp_narrow_dw")
+            else:
+                with TIMER.span(f"{dw_tag}[{cin}>{cout}]" if TIMER.detail else dw_tag, B * P * 4 * (2 * cout + cin)):
+                    _lib.check(dw_fn(
+                        B, N, M, S, cout, cin, int(gather), _p(dz), _p(go), cL, 0, _p(sel), _p(ys[l]), _p(coef),
+                        _p(ys[l - 1]) if l else None, _p(sss[l - 1]) if l else None,
+                        _p(xyz), _p(new_xyz), _p(feat_pm), _p(idx), _p(dW), _st()), "ogc_sa_mlp_layer_dw")
             be.launches += 2
             grads[3 * l] = dW.view_as(W)
             if l > 0:
@@ -164,13 +184,21 @@ class _FusedSAMLP(Function):
                 ab_prev = torch.zeros(B, 4, 2, dtype=torch.float64, device=dev)
                 dgamma_prev = torch.zeros(cprev, **f32)
                 dbeta_prev = torch.zeros(cprev, **f32)
-                dx_tc = _tc_dx_ok(S, cout, cprev, False)
+                dx_nw = _narrow_ok(S, cprev, cout)
+                dx_tc = not dx_nw and _tc_dx_ok(S, cout, cprev, False)
                 dx_fn, dx_tag = (lib.ogc_sa_mlp_layer_dx_tc, "sa_mlp_dx_tc") if dx_tc else (lib.ogc_sa_mlp_layer_dx, "sa_mlp_dx")
-                with TIMER.span(f"{dx_tag}[{cout}>{cprev}]" if TIMER.detail else dx_tag, B * P * 4 * (2 * cout + 2 * cprev)):
-                    _lib.check(dx_fn(
-                        B, N, M, S, cout, cin, 0, cprev, _p(dz), _p(go), cL, 0, _p(sel), _p(ys[l]), _p(coef), _p(w2d),
-                        _p(ys[l - 1]), _p(sss[l - 1]), _p(mrs[l - 1]), _p(params[3 * (l - 1) + 1]), _p(dz_prev),
-                        _p(ab_prev), _p(dgamma_prev), _p(dbeta_prev), None, None, 0, 0, _st()), "ogc_sa_mlp_layer_dx")
+                if dx_nw:
+                    with TIMER.span(f"sa_mlp_dx_nw[{cout}>{cprev}]" if TIMER.detail else "sa_mlp_dx_nw", B * P * 4 * (2 * cout + 2 * cprev)):
+                        _lib.check(lib.ogc_sa_mlp_narrow_dx(
+                            B, M, S, cout, cprev, _p(dz), _p(go), cL, 0, _p(sel), _p(ys[l]), _p(coef), _p(w2d),
+                            _p(ys[l - 1]), _p(sss[l - 1]), _p(mrs[l - 1]), _p(params[3 * (l - 1) + 1]), _p(dz_prev),
+                            _p(ab_prev), _p(dgamma_prev), _p(dbeta_prev), _st()), "ogc_sa_mlp_narrow_dx")
+                else:
+                    with TIMER.span(f"{dx_tag}[{cout}>{cprev}]" if TIMER.detail else dx_tag, B * P * 4 * (2 * cout + 2 * cprev)):
+                        _lib.check(dx_fn(
+                            B, N, M, S, cout, cin, 0, cprev, _p(dz), _p(go), cL, 0, _p(sel), _p(ys[l]), _p(coef), _p(w2d),
+                            _p(ys[l - 1]), _p(sss[l - 1]), _p(mrs[l - 1]), _p(params[3 * (l - 1) + 1]), _p(dz_prev),
+                            _p(ab_prev), _p(dgamma_prev), _p(dbeta_prev), None, None, 0, 0, _st()), "ogc_sa_mlp_layer_dx")
                 be.launches += 1
                 dz, ab, dgamma, dbeta = dz_prev, ab_prev, dgamma_prev, dbeta_prev
             elif ctx.feat_needs_grad:

@@ -160,3 +160,47 @@ def test_segnet_fused_equals_composed_full_model(b200):
     # summation-order noise is bounded.
     for n in g_ref:
         assert rel_err(g_fused[n], g_ref[n]) < 3e-2, (n, rel_err(g_fused[n], g_ref[n]))
+
+
+@pytest.mark.parametrize("widths", [[32, 32, 32], [32, 32, 64]])
+def test_narrow_kernels_match_generic_kernels(b200, widths):
+    """csrc/mlp_narrow.cu (warp-per-centre, channels in registers) vs the tiled kernels on SA level 1's shapes:
+    every tensor the forward saves (pre-norm activations, GroupNorm scale/shift, arg-max slots) and every gradient."""
+    from ogc_b200 import segnet, sa_fused
+    import pointnet2.pointnet2 as ops
+    torch.manual_seed(11)
+    B, S, N, M, Cf = 3, 64, 600, 150, 3
+    xyz = torch.randn(B, N, 3, device="cuda")
+    new_xyz = xyz[:, :M].contiguous()
+    feat_pm = torch.randn(B, N, Cf, device="cuda")
+    mlp = segnet.SharedMLP([Cf + 3] + widths).cuda()
+    with torch.no_grad():
+        for n_, p_ in mlp.named_parameters():
+            if "gn.weight" in n_:
+                p_.copy_(torch.randn_like(p_) * 0.5 + 0.8)
+            if "gn.bias" in n_:
+                p_.copy_(torch.randn_like(p_) * 0.3)
+    dist, idx = ops.knn(S, new_xyz, xyz)
+    idx = ops.clip_neighbours_by_radius(dist, idx, 1.2)
+    layers = [(getattr(mlp, f"layer{i}").conv.weight, getattr(mlp, f"layer{i}").normlayer.gn.weight,
+               getattr(mlp, f"layer{i}").normlayer.gn.bias) for i in range(3)]
+    probe = torch.randn(B, widths[-1], M, device="cuda")
+    saved, grads = {}, {}
+    for nw in (False, True):
+        sa_fused.USE_NARROW = nw
+        try:
+            mlp.zero_grad()
+            out = sa_fused.fused_sa_mlp(xyz, new_xyz, feat_pm, idx, layers)
+            saved[nw] = [out.detach().clone()] + [t.clone() for t in out.grad_fn.saved_tensors[4:]]
+            (out * probe).sum().backward()
+        finally:
+            sa_fused.USE_NARROW = True
+        grads[nw] = {n_: p_.grad.clone() for n_, p_ in mlp.named_parameters()}
+    for a, b in zip(saved[False], saved[True]):
+        if a.dtype == torch.uint8:
+            assert float((a != b).float().mean()) < 1e-4
+        else:
+            assert float((a - b).abs().max()) <= 2e-5 * max(1.0, float(a.abs().max()))
+    for n_ in grads[False]:
+        a, b = grads[False][n_], grads[True][n_]
+        assert float((a - b).norm() / a.norm().clamp_min(1e-12)) < 2e-3, (n_, float((a - b).norm() / a.norm()))
