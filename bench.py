@@ -254,11 +254,14 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     # per-kernel timing of OUR kernels over two more steps (CUDA events on the launching stream)
+    # (the FPS side-stream overlap is switched off here so that every kernel is timed alone)
     backend.TIMER.enabled = True
     backend.TIMER.reset()
+    trainer.overlap_geometry = False
     for i in range(2):
         trainer.train_step(it0 + i, resident[i % n_batches], aug_transform=aug)
     torch.cuda.synchronize()
+    trainer.overlap_geometry = True
     backend.TIMER.enabled = False
     ops = backend.TIMER.summary()
 
@@ -277,8 +280,14 @@ def main():
     top = max(op_rows, key=lambda k: op_rows[k]["ms_per_step"]) if op_rows else None
     roofline = None
     if top:
+        # DRAM bytes per launch of that kernel family from the committed `ncu --set full` capture (profiles/)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(top, {}).get("dram_bytes_per_launch")
         roofline = {"kernel": top, "bound": "hbm", "achieved": op_rows[top]["alg_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": op_rows[top]["alg_gbs"] / peak, "traffic": None,
+                    "frac": op_rows[top]["alg_gbs"] / peak, "traffic": traffic,
+                    "alg_bytes_per_launch": ops[top]["bytes"] / ops[top]["calls"],
                     "peak_source": "MEASURED_PEAKS.json (measured)" if measured else "fallback 6650 GB/s",
                     "share_of_step": op_rows[top]["ms_per_step"] / ms_step,
                     "note": "algorithmic bytes per launch / CUDA-event duration; see DESIGN.md for the byte formulas"}
