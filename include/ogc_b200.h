@@ -355,9 +355,11 @@ OGC_API int ogc_pw_mlp_input_grad(int b, int p, int cout, int cin_full, int row_
  * as ogc_sa_mlp_layer_fwd / _dx / _dw (dense, gather = 0); nsample == 64, cin (cprev) == 32, cout in {32, 64}.
  * w is W (cout,cin) row-major (NOT transposed).
  * ===================================================================================== */
+/* last = 1: gamma (cout) = this layer's GroupNorm weight; only the extreme the pooling will pick (max for
+ * gamma >= 0, min otherwise) is computed and written to BOTH ymax/ymin (and amax/amin). */
 OGC_API int ogc_sa_mlp_narrow_fwd(int b, int m, int nsample, int cin, int cout, int last, const float *y_prev,
-                                  const float *ss_prev, const float *w, float *y, double *sums, float *ymax,
-                                  float *ymin, unsigned char *amax, unsigned char *amin, void *stream);
+                                  const float *ss_prev, const float *w, const float *gamma, float *y, double *sums,
+                                  float *ymax, float *ymin, unsigned char *amax, unsigned char *amin, void *stream);
 OGC_API int ogc_sa_mlp_narrow_dx(int b, int m, int nsample, int cout, int cprev, const float *dz, const float *go,
                                  int go_ctotal, int go_coff, const unsigned char *sel, const float *y,
                                  const float *coef, const float *w, const float *y_prev, const float *ss_prev,

@@ -57,7 +57,7 @@ SIGNATURES = {
     "ogc_gn_relu_apply": [_I] * 3 + [_P] * 4,
     "ogc_gn_relu_bwd_stats": [_I] * 3 + [_P] * 10,
     "ogc_pw_mlp_input_grad": [_I] * 6 + [_P] * 5 + [_I, _I, _P],
-    "ogc_sa_mlp_narrow_fwd": [_I] * 6 + [_P] * 10,
+    "ogc_sa_mlp_narrow_fwd": [_I] * 6 + [_P] * 11,
     "ogc_sa_mlp_narrow_dx": [_I] * 5 + [_P, _P, _I, _I] + [_P] * 13,
     "ogc_sa_mlp_narrow_dw": [_I] * 5 + [_P, _P, _I, _I] + [_P] * 7,
     "ogc_adam_step_dev": [_LL, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _P, _P],

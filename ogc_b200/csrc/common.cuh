@@ -27,6 +27,16 @@ __device__ __forceinline__ float sqdist(float ax, float ay, float az, float bx, 
     return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
 
+// Packed fp32 FMA (Blackwell FFMA2): d = a * b + c on both halves, each half an IEEE fp32 fma.  A 3-register FFMA
+// issues every other cycle per scheduler; FFMA2 retires two FMAs per issue slot, which is what lets the fp32 SIMT
+// kernels approach the 128 FMA/clk/SM peak.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b),
+                       rc = *reinterpret_cast<unsigned long long *>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

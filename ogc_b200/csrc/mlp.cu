@@ -290,7 +290,7 @@ static cudaError_t launch_fwd(const MlpFwdParams &q, int B, bool gather, bool la
     const size_t smem = (static_cast<size_t>(q.Cin) * R_T + static_cast<size_t>(q.Cin) * (P_T + 4)) * sizeof(float);
     if (smem > static_cast<size_t>(kMaxSmemPerCta) - 1024) return cudaErrorInvalidValue;
     const int ntiles = (q.P + P_T - 1) / P_T;
-    int per_sample = (kNumSMs * 2 + B - 1) / B;
+    int per_sample = (kNumSMs * 2) / B;   // floor: the whole grid must be resident at 2 CTAs/SM (a 297th CTA would run as a second wave)
     if (per_sample > ntiles) per_sample = ntiles;
     if (per_sample < 1) per_sample = 1;
     dim3 grid(per_sample, B);

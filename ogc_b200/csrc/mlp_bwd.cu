@@ -437,7 +437,7 @@ static cudaError_t launch_dx(const MlpDxParams &q, int B, int mode, cudaStream_t
     constexpr int KC = 64;
     const size_t smem = (static_cast<size_t>(KC) * R_T + static_cast<size_t>(KC) * (P_T + 4)) * sizeof(float);
     const int ntiles = (q.dy.P + P_T - 1) / P_T;
-    int per_sample = (kNumSMs * 2 + B - 1) / B;
+    int per_sample = (kNumSMs * 2) / B;   // floor: the whole grid must be resident at 2 CTAs/SM (a 297th CTA would run as a second wave)
     per_sample = per_sample > ntiles ? ntiles : (per_sample < 1 ? 1 : per_sample);
     dim3 grid(per_sample, B);
     cudaError_t e;

@@ -20,6 +20,8 @@
 //
 // fp32 FMA throughout (bit-level fp32 conv semantics).  Same operand / result contract as the generic kernels,
 // which the tests compare them against.
+#include <type_traits>
+
 #include "mlp_common.cuh"
 #include "mlp_dy.cuh"
 
@@ -82,6 +84,7 @@ struct NarrowFwdParams {
     int P, M;
     const float *y_prev, *ss_prev;   // (B,CIN,P), (B,CIN,2)
     const float *W;                  // (COUT,CIN) row-major
+    const float *gamma;              // (COUT) GroupNorm weight of THIS layer (LAST: decides max vs min per channel)
     float *y;                        // (B,COUT,P)
     double *sums;                    // (B,4,2)
     float *ymax, *ymin;              // (B,COUT,M) when LAST
@@ -94,18 +97,19 @@ narrow_fwd_kernel(NarrowFwdParams q) {
     constexpr int CPG = COUT / kGnGroups;
     __shared__ __align__(16) float Ws[COUT * CIN];
     __shared__ float2 ss_s[CIN];
+    __shared__ uint32_t flip_s[COUT];   // LAST: 0xffffffff for channels whose pooled value is the MINIMUM (gamma < 0)
     __shared__ double gs[kGnGroups][2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y, P = q.P;
     for (int e = tid; e < COUT * CIN; e += kNwThreads) Ws[e] = __ldg(q.W + e);
     for (int c = tid; c < CIN; c += kNwThreads) ss_s[c] = __ldg(reinterpret_cast<const float2 *>(q.ss_prev) + static_cast<size_t>(b) * CIN + c);
+    if (LAST)
+        for (int c = tid; c < COUT; c += kNwThreads) flip_s[c] = __ldg(q.gamma + c) < 0.f ? 0xffffffffu : 0u;
     if (tid < kGnGroups * 2) (&gs[0][0])[tid] = 0.0;
     __syncthreads();
     const float4 *Ws4 = reinterpret_cast<const float4 *>(Ws);
 
-    float gsum[kGnGroups], gsq[kGnGroups];
-#pragma unroll
-    for (int g = 0; g < kGnGroups; ++g) gsum[g] = gsq[g] = 0.f;
+    float gsum0 = 0.f, gsum1 = 0.f, gsum2 = 0.f, gsum3 = 0.f, gsq0 = 0.f, gsq1 = 0.f, gsq2 = 0.f, gsq3 = 0.f;
 
     const int nunits = P / kNwUnit;
     for (int u = blockIdx.x * kNwWarps + warp; u < nunits; u += gridDim.x * kNwWarps) {
@@ -124,50 +128,58 @@ narrow_fwd_kernel(NarrowFwdParams q) {
             a1[c] = fmaxf(fmaf(s.x, a1[c], s.y), 0.f);
         }
         float *dst = q.y + static_cast<size_t>(b) * COUT * P + p0;
-#pragma unroll
-        for (int g = 0; g < kGnGroups; ++g) {
-            float s = 0.f, sq = 0.f;
+        float pool_v = 0.f;        // LAST: lane c collects the pooled value / slot of channel (32 k + c)
+        int pool_p = 0;
 #pragma unroll 1
-            for (int cb = 0; cb < CPG; cb += 4) {
-                const int co0 = g * CPG + cb;
-                float r0[4] = {0.f, 0.f, 0.f, 0.f}, r1[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int co0 = 0; co0 < COUT; co0 += 4) {
+            // packed FMAs over pairs of input channels: (even-c partial, odd-c partial) per output, summed at the end
+            float2 e0[4], e1[4];
 #pragma unroll
-                for (int c4 = 0; c4 < CIN / 4; ++c4) {
+            for (int j = 0; j < 4; ++j) e0[j] = e1[j] = make_float2(0.f, 0.f);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float4 w = Ws4[(co0 + j) * (CIN / 4) + c4];
-                        r0[j] = fmaf(w.x, a0[c4 * 4 + 0], r0[j]); r1[j] = fmaf(w.x, a1[c4 * 4 + 0], r1[j]);
-                        r0[j] = fmaf(w.y, a0[c4 * 4 + 1], r0[j]); r1[j] = fmaf(w.y, a1[c4 * 4 + 1], r1[j]);
-                        r0[j] = fmaf(w.z, a0[c4 * 4 + 2], r0[j]); r1[j] = fmaf(w.z, a1[c4 * 4 + 2], r1[j]);
-                        r0[j] = fmaf(w.w, a0[c4 * 4 + 3], r0[j]); r1[j] = fmaf(w.w, a1[c4 * 4 + 3], r1[j]);
-                    }
-                }
+            for (int c4 = 0; c4 < CIN / 4; ++c4) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    *reinterpret_cast<float2 *>(dst + static_cast<size_t>(co0 + j) * P) = make_float2(r0[j], r1[j]);
-                    s += r0[j] + r1[j];
-                    sq += r0[j] * r0[j] + r1[j] * r1[j];
-                    if (LAST) {
-                        const uint32_t k0 = f2ord(r0[j]), k1 = f2ord(r1[j]);
-                        const uint32_t kmax = __reduce_max_sync(OGC_FULL_MASK, max(k0, k1));
-                        const uint32_t kmin = __reduce_min_sync(OGC_FULL_MASK, min(k0, k1));
-                        const unsigned bx0 = __ballot_sync(OGC_FULL_MASK, k0 == kmax), bx1 = __ballot_sync(OGC_FULL_MASK, k1 == kmax);
-                        const unsigned bn0 = __ballot_sync(OGC_FULL_MASK, k0 == kmin), bn1 = __ballot_sync(OGC_FULL_MASK, k1 == kmin);
-                        if (lane == 0) {
-                            // first position holding the extreme value: even positions are r0, odd ones r1
-                            const int px0 = bx0 ? 2 * (__ffs(bx0) - 1) : 64, px1 = bx1 ? 2 * (__ffs(bx1) - 1) + 1 : 64;
-                            const int pn0 = bn0 ? 2 * (__ffs(bn0) - 1) : 64, pn1 = bn1 ? 2 * (__ffs(bn1) - 1) + 1 : 64;
-                            const size_t o = (static_cast<size_t>(b) * COUT + co0 + j) * q.M + u;
-                            q.ymax[o] = ord2f(kmax); q.ymin[o] = ord2f(kmin);
-                            q.amax[o] = static_cast<unsigned char>(min(px0, px1));
-                            q.amin[o] = static_cast<unsigned char>(min(pn0, pn1));
-                        }
-                    }
+                    const float4 w = Ws4[(co0 + j) * (CIN / 4) + c4];
+                    e0[j] = ffma2(make_float2(w.x, w.y), make_float2(a0[c4 * 4 + 0], a0[c4 * 4 + 1]), e0[j]);
+                    e1[j] = ffma2(make_float2(w.x, w.y), make_float2(a1[c4 * 4 + 0], a1[c4 * 4 + 1]), e1[j]);
+                    e0[j] = ffma2(make_float2(w.z, w.w), make_float2(a0[c4 * 4 + 2], a0[c4 * 4 + 3]), e0[j]);
+                    e1[j] = ffma2(make_float2(w.z, w.w), make_float2(a1[c4 * 4 + 2], a1[c4 * 4 + 3]), e1[j]);
                 }
             }
-            gsum[g] += s; gsq[g] += sq;
+            float r0[4], r1[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { r0[j] = e0[j].x + e0[j].y; r1[j] = e1[j].x + e1[j].y; }
+            float s = 0.f, sq = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                *reinterpret_cast<float2 *>(dst + static_cast<size_t>(co0 + j) * P) = make_float2(r0[j], r1[j]);
+                s += r0[j] + r1[j];
+                sq += r0[j] * r0[j] + r1[j] * r1[j];
+                if (LAST) {
+                    // pooled extreme of the 64 samples and its FIRST slot: one redux + two ballots per channel
+                    const uint32_t flip = flip_s[co0 + j];
+                    const uint32_t k0 = f2ord(r0[j]) ^ flip, k1 = f2ord(r1[j]) ^ flip;
+                    const uint32_t kbest = __reduce_max_sync(OGC_FULL_MASK, max(k0, k1));
+                    const unsigned e0 = __ballot_sync(OGC_FULL_MASK, k0 == kbest), e1 = __ballot_sync(OGC_FULL_MASK, k1 == kbest);
+                    const int q0 = e0 ? 2 * (__ffs(e0) - 1) : 64, q1 = e1 ? 2 * (__ffs(e1) - 1) + 1 : 64;   // even slots: r0, odd: r1
+                    if (lane == ((co0 + j) & 31)) { pool_v = ord2f(kbest ^ flip); pool_p = min(q0, q1); }
+                }
+            }
+            const int g = co0 / CPG;       // the 4 channels of a step share their group (CPG % 4 == 0)
+            gsum0 += g == 0 ? s : 0.f; gsq0 += g == 0 ? sq : 0.f;
+            gsum1 += g == 1 ? s : 0.f; gsq1 += g == 1 ? sq : 0.f;
+            gsum2 += g == 2 ? s : 0.f; gsq2 += g == 2 ? sq : 0.f;
+            gsum3 += g == 3 ? s : 0.f; gsq3 += g == 3 ? sq : 0.f;
+            if (LAST && ((co0 + 4) & 31) == 0) {
+                // both arrays get the value sa_finish will pick (it chooses by the sign of gamma * rstd)
+                const size_t o = (static_cast<size_t>(b) * COUT + (co0 + 4 - 32) + lane) * q.M + u;
+                q.ymax[o] = pool_v; q.ymin[o] = pool_v;
+                q.amax[o] = static_cast<unsigned char>(pool_p); q.amin[o] = static_cast<unsigned char>(pool_p);
+            }
         }
     }
+    float gsum[kGnGroups] = {gsum0, gsum1, gsum2, gsum3}, gsq[kGnGroups] = {gsq0, gsq1, gsq2, gsq3};
 #pragma unroll
     for (int g = 0; g < kGnGroups; ++g) {
         float s = gsum[g], sq = gsq[g];
@@ -200,10 +212,15 @@ struct NarrowDxParams {
     float *dgamma_prev, *dbeta_prev;
 };
 
+// One pipeline stage of the dX kernel: 4 channels x (y, dz) x 2 positions, or 8 channels of y_prev (epilogue)
+struct NwStage {
+    float2 v[8];
+};
+
 template <int COUT, bool SYNTH>
 __global__ void __launch_bounds__(kNwThreads, 2)
 narrow_dx_kernel(NarrowDxParams q) {
-    constexpr int CPREV = 32, CH = 8;
+    constexpr int CPREV = 32, CH = 4;
     __shared__ __align__(16) float Ws[COUT * CPREV];
     __shared__ __align__(16) float4 coef_s[COUT];
     __shared__ float4 prev_s[CPREV];            // scale, shift, mean, rstd of the previous layer's channels
@@ -223,63 +240,94 @@ narrow_dx_kernel(NarrowDxParams q) {
     float tot_s = 0.f, tot_sy = 0.f;            // lane = channel of layer l-1
 
     const int nunits = P / kNwUnit;
-    for (int u = blockIdx.x * kNwWarps + warp; u < nunits; u += gridDim.x * kNwWarps) {
+    const int u_first = blockIdx.x * kNwWarps + warp, u_step = gridDim.x * kNwWarps;
+
+    // stage loaders: every load of a stage is issued before any is consumed; the NEXT stage is always in flight
+    // while the current one is being multiplied (software pipeline across the channel loop, the epilogue and units)
+    auto load_main = [&](NwStage &st, int u, int cb) {
         const size_t p0 = static_cast<size_t>(u) * kNwUnit + 2 * lane;
-        const float *yp = q.y + static_cast<size_t>(b) * COUT * P + p0;
-        const float *zp = SYNTH ? nullptr : q.dz + static_cast<size_t>(b) * COUT * P + p0;
-        float acc0[CPREV], acc1[CPREV];
+        const float *yp = q.y + (static_cast<size_t>(b) * COUT + cb) * P + p0;
 #pragma unroll
-        for (int i = 0; i < CPREV; ++i) acc0[i] = acc1[i] = 0.f;
+        for (int j = 0; j < CH; ++j) st.v[j] = __ldg(reinterpret_cast<const float2 *>(yp + static_cast<size_t>(j) * P));
+        if (SYNTH) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+                const size_t o = (static_cast<size_t>(b) * COUT + cb + j) * q.M + u;
+                const int sl = __ldg(q.sel + o);
+                const float g = __ldg(q.go + (static_cast<size_t>(b) * q.go_ctotal + q.go_coff + cb + j) * q.M + u);
+                st.v[CH + j] = make_float2(sl == 2 * lane ? g : 0.f, sl == 2 * lane + 1 ? g : 0.f);
+            }
+        } else {
+            const float *zp = q.dz + (static_cast<size_t>(b) * COUT + cb) * P + p0;
+#pragma unroll
+            for (int j = 0; j < CH; ++j) st.v[CH + j] = __ldg(reinterpret_cast<const float2 *>(zp + static_cast<size_t>(j) * P));
+        }
+    };
+    auto load_prev = [&](NwStage &st, int u, int cb) {
+        const float *pp = q.y_prev + (static_cast<size_t>(b) * CPREV + cb) * P + static_cast<size_t>(u) * kNwUnit + 2 * lane;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) st.v[j] = __ldg(reinterpret_cast<const float2 *>(pp + static_cast<size_t>(j) * P));
+    };
+
+    float2 acc0[CPREV / 2], acc1[CPREV / 2];     // (channel 2k, channel 2k+1) of the two positions
+    auto mul_main = [&](const NwStage &st, int cb) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+            const float4 cf = coef_s[cb + j];
+            const float d0 = fmaf(cf.x, st.v[CH + j].x, -cf.y) - (st.v[j].x - cf.w) * cf.z;
+            const float d1 = fmaf(cf.x, st.v[CH + j].y, -cf.y) - (st.v[j].y - cf.w) * cf.z;
+            const float2 dd0 = make_float2(d0, d0), dd1 = make_float2(d1, d1);
+#pragma unroll
+            for (int c4 = 0; c4 < CPREV / 4; ++c4) {
+                const float4 w = Ws4[(cb + j) * (CPREV / 4) + c4];
+                acc0[c4 * 2 + 0] = ffma2(dd0, make_float2(w.x, w.y), acc0[c4 * 2 + 0]);
+                acc1[c4 * 2 + 0] = ffma2(dd1, make_float2(w.x, w.y), acc1[c4 * 2 + 0]);
+                acc0[c4 * 2 + 1] = ffma2(dd0, make_float2(w.z, w.w), acc0[c4 * 2 + 1]);
+                acc1[c4 * 2 + 1] = ffma2(dd1, make_float2(w.z, w.w), acc1[c4 * 2 + 1]);
+            }
+        }
+    };
+
+    NwStage sa, sb;
+    if (u_first < nunits) load_main(sa, u_first, 0);
+    for (int u = u_first; u < nunits; u += u_step) {
+#pragma unroll
+        for (int i = 0; i < CPREV / 2; ++i) acc0[i] = acc1[i] = make_float2(0.f, 0.f);
 #pragma unroll 1
-        for (int cb = 0; cb < COUT; cb += CH) {
-            float2 yv[CH], zv[CH];
-#pragma unroll
-            for (int j = 0; j < CH; ++j) {
-                yv[j] = __ldg(reinterpret_cast<const float2 *>(yp + static_cast<size_t>(cb + j) * P));
-                if (SYNTH) {
-                    const size_t o = (static_cast<size_t>(b) * COUT + cb + j) * q.M + u;
-                    const int sl = __ldg(q.sel + o);
-                    const float g = __ldg(q.go + (static_cast<size_t>(b) * q.go_ctotal + q.go_coff + cb + j) * q.M + u);
-                    zv[j] = make_float2(sl == 2 * lane ? g : 0.f, sl == 2 * lane + 1 ? g : 0.f);
-                } else {
-                    zv[j] = __ldg(reinterpret_cast<const float2 *>(zp + static_cast<size_t>(cb + j) * P));
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < CH; ++j) {
-                const float4 cf = coef_s[cb + j];
-                const float d0 = fmaf(cf.x, zv[j].x, -cf.y) - (yv[j].x - cf.w) * cf.z;
-                const float d1 = fmaf(cf.x, zv[j].y, -cf.y) - (yv[j].y - cf.w) * cf.z;
-#pragma unroll
-                for (int c4 = 0; c4 < CPREV / 4; ++c4) {
-                    const float4 w = Ws4[(cb + j) * (CPREV / 4) + c4];
-                    acc0[c4 * 4 + 0] = fmaf(d0, w.x, acc0[c4 * 4 + 0]); acc1[c4 * 4 + 0] = fmaf(d1, w.x, acc1[c4 * 4 + 0]);
-                    acc0[c4 * 4 + 1] = fmaf(d0, w.y, acc0[c4 * 4 + 1]); acc1[c4 * 4 + 1] = fmaf(d1, w.y, acc1[c4 * 4 + 1]);
-                    acc0[c4 * 4 + 2] = fmaf(d0, w.z, acc0[c4 * 4 + 2]); acc1[c4 * 4 + 2] = fmaf(d1, w.z, acc1[c4 * 4 + 2]);
-                    acc0[c4 * 4 + 3] = fmaf(d0, w.w, acc0[c4 * 4 + 3]); acc1[c4 * 4 + 3] = fmaf(d1, w.w, acc1[c4 * 4 + 3]);
-                }
-            }
+        for (int cb = 0; cb < COUT; cb += 2 * CH) {
+            load_main(sb, u, cb + CH);
+            mul_main(sa, cb);
+            if (cb + 2 * CH < COUT) load_main(sa, u, cb + 2 * CH);
+            else load_prev(sa, u, 0);
+            mul_main(sb, cb + CH);
         }
         // ---- epilogue: ReLU mask of layer l-1, store dz_{l-1}, per-channel GroupNorm-backward sums ----
-        const float *pp = q.y_prev + static_cast<size_t>(b) * CPREV * P + p0;
-        float *dp = q.dz_prev + static_cast<size_t>(b) * CPREV * P + p0;
+        float *dp = q.dz_prev + static_cast<size_t>(b) * CPREV * P + static_cast<size_t>(u) * kNwUnit + 2 * lane;
+        float fs[CPREV], fsy[CPREV];
+        auto finish8 = [&](const NwStage &st, auto cbc) {
+            constexpr int cb = decltype(cbc)::value;
 #pragma unroll
-        for (int cb = 0; cb < CPREV; cb += CH) {
-            float2 pv[CH];
-#pragma unroll
-            for (int j = 0; j < CH; ++j) pv[j] = __ldg(reinterpret_cast<const float2 *>(pp + static_cast<size_t>(cb + j) * P));
-#pragma unroll
-            for (int j = 0; j < CH; ++j) {
+            for (int j = 0; j < 8; ++j) {
                 const float4 pr = prev_s[cb + j];
-                const float g0 = fmaf(pr.x, pv[j].x, pr.y) > 0.f ? acc0[cb + j] : 0.f;
-                const float g1 = fmaf(pr.x, pv[j].y, pr.y) > 0.f ? acc1[cb + j] : 0.f;
+                const float x0 = (j & 1) ? acc0[(cb + j) >> 1].y : acc0[(cb + j) >> 1].x;
+                const float x1 = (j & 1) ? acc1[(cb + j) >> 1].y : acc1[(cb + j) >> 1].x;
+                const float g0 = fmaf(pr.x, st.v[j].x, pr.y) > 0.f ? x0 : 0.f;
+                const float g1 = fmaf(pr.x, st.v[j].y, pr.y) > 0.f ? x1 : 0.f;
                 *reinterpret_cast<float2 *>(dp + static_cast<size_t>(cb + j) * P) = make_float2(g0, g1);
-                acc0[cb + j] = g0 + g1;
-                acc1[cb + j] = g0 * ((pv[j].x - pr.z) * pr.w) + g1 * ((pv[j].y - pr.z) * pr.w);
+                fs[cb + j] = g0 + g1;
+                fsy[cb + j] = g0 * ((st.v[j].x - pr.z) * pr.w) + g1 * ((st.v[j].y - pr.z) * pr.w);
             }
-        }
-        tot_s += warp_transpose_sum32(acc0, lane);
-        tot_sy += warp_transpose_sum32(acc1, lane);
+        };
+        load_prev(sb, u, 8);
+        finish8(sa, std::integral_constant<int, 0>{});
+        load_prev(sa, u, 16);
+        finish8(sb, std::integral_constant<int, 8>{});
+        load_prev(sb, u, 24);
+        finish8(sa, std::integral_constant<int, 16>{});
+        if (u + u_step < nunits) load_main(sa, u + u_step, 0);      // next unit's first stage
+        finish8(sb, std::integral_constant<int, 24>{});
+        tot_s += warp_transpose_sum32(fs, lane);
+        tot_sy += warp_transpose_sum32(fsy, lane);
     }
     atomicAdd(&rowacc[lane][0], tot_s);
     atomicAdd(&rowacc[lane][1], tot_sy);
@@ -306,17 +354,17 @@ struct NarrowDwParams {
 template <int COUT>
 __global__ void __launch_bounds__(kNwThreads, 2)
 narrow_dw_kernel(NarrowDwParams q) {
-    constexpr int CIN = 32, TP = 128, LD = TP + 4, Q4 = TP / 4;
+    constexpr int CIN = 32, TP = 128, LD = TP + 4, LDD = 2 * TP + 8, Q4 = TP / 4;
     extern __shared__ __align__(16) float smem[];
-    float *Ds = smem;                // [COUT][LD]  dY
-    float *As = smem + COUT * LD;    // [CIN][LD]   a_{l-1}
+    float *Ds = smem;                      // [COUT/2][LDD]: (dY[2k][p], dY[2k+1][p]) interleaved per position
+    float *As = smem + (COUT / 2) * LDD;   // [CIN][LD]   a_{l-1}
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int P = q.dy.P;
     const int tiles_per_sample = P / TP;
     const int total = q.B * tiles_per_sample;
-    float acc[COUT];
+    float2 acc[COUT / 2];                  // (dW[2k][lane], dW[2k+1][lane])
 #pragma unroll
-    for (int i = 0; i < COUT; ++i) acc[i] = 0.f;
+    for (int i = 0; i < COUT / 2; ++i) acc[i] = make_float2(0.f, 0.f);
 
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
         const int b = w / tiles_per_sample, p_base = (w - b * tiles_per_sample) * TP;
@@ -337,19 +385,25 @@ narrow_dw_kernel(NarrowDwParams q) {
                                                                           fmaxf(fmaf(s, v[i].z, h), 0.f), fmaxf(fmaf(s, v[i].w, h), 0.f));
             }
         }
-        // dY tile
+        // dY tile: thread -> (channel PAIR, quad): both channels' quads are loaded, interleaved, stored as 2 x 16 B
+        // (COUT = 64 keeps 64 accumulators alive: one pair at a time there, two otherwise)
+        constexpr int DB = COUT > 32 ? 1 : 2;
 #pragma unroll
-        for (int i0 = 0; i0 < COUT * Q4 / kNwThreads; i0 += 4) {
-            DyRaw raw[4];
+        for (int i0 = 0; i0 < (COUT / 2) * Q4 / kNwThreads; i0 += DB) {
+            DyRaw raw[DB][2];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int e = tid + (i0 + k) * kNwThreads, c = e / Q4, p = (e - c * Q4) * 4;
-                dy_quad_load(q.dy, b, c, p_base + p, raw[k]);
+            for (int k = 0; k < DB; ++k) {
+                const int e = tid + (i0 + k) * kNwThreads, cp = e / Q4, p = (e - cp * Q4) * 4;
+                dy_quad_load(q.dy, b, 2 * cp, p_base + p, raw[k][0]);
+                dy_quad_load(q.dy, b, 2 * cp + 1, p_base + p, raw[k][1]);
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int e = tid + (i0 + k) * kNwThreads, c = e / Q4, p = (e - c * Q4) * 4;
-                *reinterpret_cast<float4 *>(Ds + c * LD + p) = dy_quad_finish(q.dy, p_base + p, raw[k]);
+            for (int k = 0; k < DB; ++k) {
+                const int e = tid + (i0 + k) * kNwThreads, cp = e / Q4, p = (e - cp * Q4) * 4;
+                const float4 d0 = dy_quad_finish(q.dy, p_base + p, raw[k][0]), d1 = dy_quad_finish(q.dy, p_base + p, raw[k][1]);
+                float4 *dst = reinterpret_cast<float4 *>(Ds + cp * LDD + 2 * p);
+                dst[0] = make_float4(d0.x, d1.x, d0.y, d1.y);
+                dst[1] = make_float4(d0.z, d1.z, d0.w, d1.w);
             }
         }
         __syncthreads();
@@ -358,10 +412,15 @@ narrow_dw_kernel(NarrowDwParams q) {
         for (int pq = 0; pq < TP / kNwWarps / 4; ++pq) {
             const int p = warp * (TP / kNwWarps) + pq * 4;
             const float4 av = *reinterpret_cast<const float4 *>(As + lane * LD + p);
+            const float2 ax = make_float2(av.x, av.x), ay = make_float2(av.y, av.y), az = make_float2(av.z, av.z), aw = make_float2(av.w, av.w);
 #pragma unroll
-            for (int co = 0; co < COUT; ++co) {
-                const float4 d = *reinterpret_cast<const float4 *>(Ds + co * LD + p);
-                acc[co] = fmaf(d.x, av.x, fmaf(d.y, av.y, fmaf(d.z, av.z, fmaf(d.w, av.w, acc[co]))));
+            for (int cp = 0; cp < COUT / 2; ++cp) {
+                const float4 d01 = *reinterpret_cast<const float4 *>(Ds + cp * LDD + 2 * p);
+                const float4 d23 = *reinterpret_cast<const float4 *>(Ds + cp * LDD + 2 * p + 4);
+                acc[cp] = ffma2(make_float2(d01.x, d01.y), ax, acc[cp]);
+                acc[cp] = ffma2(make_float2(d01.z, d01.w), ay, acc[cp]);
+                acc[cp] = ffma2(make_float2(d23.x, d23.y), az, acc[cp]);
+                acc[cp] = ffma2(make_float2(d23.z, d23.w), aw, acc[cp]);
             }
         }
     }
@@ -369,7 +428,10 @@ narrow_dw_kernel(NarrowDwParams q) {
     __syncthreads();
     float *red = smem;               // [kNwWarps][COUT][33]
 #pragma unroll
-    for (int co = 0; co < COUT; ++co) red[(warp * COUT + co) * 33 + lane] = acc[co];
+    for (int cp = 0; cp < COUT / 2; ++cp) {
+        red[(warp * COUT + 2 * cp) * 33 + lane] = acc[cp].x;
+        red[(warp * COUT + 2 * cp + 1) * 33 + lane] = acc[cp].y;
+    }
     __syncthreads();
     for (int e = tid; e < COUT * CIN; e += kNwThreads) {
         const int co = e / CIN, ci = e - co * CIN;
@@ -381,7 +443,7 @@ narrow_dw_kernel(NarrowDwParams q) {
 }
 
 static int narrow_grid_x(int B, int nunits) {
-    int per_sample = (kNumSMs * 2 + B - 1) / B;
+    int per_sample = (kNumSMs * 2) / B;   // floor: the whole grid must be resident at 2 CTAs/SM (a 297th CTA would run as a second wave)
     const int need = (nunits + kNwWarps - 1) / kNwWarps;
     if (per_sample > need) per_sample = need;
     return per_sample < 1 ? 1 : per_sample;
@@ -390,16 +452,16 @@ static int narrow_grid_x(int B, int nunits) {
 }  // namespace ogc
 
 extern "C" int ogc_sa_mlp_narrow_fwd(int b, int m, int nsample, int cin, int cout, int last, const float *y_prev,
-                                     const float *ss_prev, const float *w, float *y, double *sums, float *ymax,
-                                     float *ymin, unsigned char *amax, unsigned char *amin, void *stream) {
+                                     const float *ss_prev, const float *w, const float *gamma, float *y, double *sums,
+                                     float *ymax, float *ymin, unsigned char *amax, unsigned char *amin, void *stream) {
     using namespace ogc;
     if (b < 0 || m <= 0 || nsample <= 0 || cin <= 0 || cout <= 0) return OGC_ERR_INVALID_ARG;
     if (b == 0) return OGC_OK;
     if (!y_prev || !ss_prev || !w || !y || !sums) return OGC_ERR_INVALID_ARG;
-    if (last && (!ymax || !ymin || !amax || !amin)) return OGC_ERR_INVALID_ARG;
+    if (last && (!ymax || !ymin || !amax || !amin || !gamma)) return OGC_ERR_INVALID_ARG;
     if (nsample != 64 || cin != 32 || (cout != 32 && cout != 64) || b > 65535) return OGC_ERR_UNSUPPORTED;
     NarrowFwdParams q;
-    q.P = m * nsample; q.M = m; q.y_prev = y_prev; q.ss_prev = ss_prev; q.W = w; q.y = y; q.sums = sums;
+    q.P = m * nsample; q.M = m; q.y_prev = y_prev; q.ss_prev = ss_prev; q.W = w; q.gamma = gamma; q.y = y; q.sums = sums;
     q.ymax = ymax; q.ymin = ymin; q.amax = amax; q.amin = amin;
     dim3 grid(narrow_grid_x(b, m), b);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -459,7 +521,7 @@ extern "C" int ogc_sa_mlp_narrow_dw(int b, int m, int nsample, int cout, int cin
     const int total = b * (m * nsample / 128);
     const int gx = total < kNumSMs * 2 ? total : kNumSMs * 2;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const size_t smem_tile = static_cast<size_t>(cout + 32) * 132 * sizeof(float);
+    const size_t smem_tile = (static_cast<size_t>(cout / 2) * 264 + 32 * 132) * sizeof(float);
     const size_t smem_red = static_cast<size_t>(kNwWarps) * cout * 33 * sizeof(float);
     const size_t smem = smem_tile > smem_red ? smem_tile : smem_red;
     cudaError_t e;

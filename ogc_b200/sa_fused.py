@@ -92,7 +92,7 @@ class _FusedSAMLP(Function):
                 if use_nw:
                     w2d = W.detach().reshape(cout, cin).contiguous()
                     _lib.check(lib.ogc_sa_mlp_narrow_fwd(
-                        B, M, S, cin, cout, int(last), _p(y_prev), _p(ss_prev), _p(w2d), _p(y), _p(sums), _p(ymax),
+                        B, M, S, cin, cout, int(last), _p(y_prev), _p(ss_prev), _p(w2d), _p(gamma.detach()), _p(y), _p(sums), _p(ymax),
                         _p(ymin), _p(amax), _p(amin), _st()), "ogc_sa_mlp_narrow_fwd")
                 elif use_tc:
                     w2d = W.detach().reshape(cout, cin).contiguous()
