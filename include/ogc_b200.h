@@ -370,6 +370,18 @@ OGC_API int ogc_sa_mlp_narrow_dw(int b, int m, int nsample, int cout, int cin, c
                                  const float *coef, const float *y_prev, const float *ss_prev, float *dw,
                                  void *stream);
 
+/* =====================================================================================
+ * Mask head (csrc/mask_head.cu) -- replaces models/segnet_kitti.py:85-88:
+ *   mask (b,n,k) = softmax_k( <feats[:,n]/max(|feats[:,n]|,1e-12), slots_hat[:,k]> * inv_temperature )
+ * feats (b,d,n) channel-major, slots_hat (b,d,k) ALREADY normalised over d (tiny; stays in torch).  d == 64, k <= 16.
+ * Backward: dfeats (b,d,n) written, dslots_hat (b,d,k) accumulated atomically (zero it first).
+ * ===================================================================================== */
+OGC_API int ogc_mask_head_fwd(int b, int d, int n, int k, float inv_temperature, const float *feats,
+                              const float *slots_hat, float *mask, void *stream);
+OGC_API int ogc_mask_head_bwd(int b, int d, int n, int k, float inv_temperature, const float *feats,
+                              const float *slots_hat, const float *mask, const float *dmask, float *dfeats,
+                              float *dslots_hat, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -320,7 +320,12 @@ neighbor_l1_kernel(int n, int K, int S, const float *__restrict__ mask, const in
     const float *crow = mask + static_cast<size_t>(pt) * K;
     float total = 0.f;
     const float gscale = coef / static_cast<float>(S);
-    // K is small (8-16): loop over channels inside, neighbours across lanes
+    // K is small (8-16): loop over channels inside, neighbours across lanes.  The centre's own gradient is summed
+    // across the warp (in units of gscale, exact small integers) and written with ONE atomic per channel; only the
+    // gathered term scatters per neighbour.
+    float cg[kMaxSlots];
+#pragma unroll
+    for (int c = 0; c < kMaxSlots; ++c) cg[c] = 0.f;
     for (int s0 = 0; s0 < S; s0 += 32) {
         const int s = s0 + lane;
         int j = -1;
@@ -330,15 +335,25 @@ neighbor_l1_kernel(int n, int K, int S, const float *__restrict__ mask, const in
         }
         if (j >= 0 && j != pt) {
             const float *nrow = mask + static_cast<size_t>(j) * K;
-            for (int c = 0; c < K; ++c) {
+#pragma unroll
+            for (int c = 0; c < kMaxSlots; ++c) {
+                if (c >= K) break;
                 const float d = __ldg(crow + c) - __ldg(nrow + c);
                 total += fabsf(d);
                 if (grad_mask && d != 0.f) {
-                    const float g = d > 0.f ? gscale : -gscale;
-                    atomicAdd(grad_mask + static_cast<size_t>(pt) * K + c, g);
-                    atomicAdd(grad_mask + static_cast<size_t>(j) * K + c, -g);
+                    const float sg = d > 0.f ? 1.f : -1.f;
+                    cg[c] += sg;
+                    atomicAdd(grad_mask + static_cast<size_t>(j) * K + c, -sg * gscale);
                 }
             }
+        }
+    }
+    if (grad_mask) {
+#pragma unroll
+        for (int c = 0; c < kMaxSlots; ++c) {
+            if (c >= K) break;
+            const float v = warp_sum(cg[c]);
+            if (lane == 0 && v != 0.f) atomicAdd(grad_mask + static_cast<size_t>(pt) * K + c, v * gscale);
         }
     }
     total = warp_sum(total);

@@ -370,7 +370,11 @@ class UnsupervisedOGCLoss(nn.Module):
         scale = 0.5 if aug_transform else 1.0
         w = lambda weight, start: self.step_lossw(it, weight, start) if step_w else weight
 
-        l_dynamic = scale * sum(self.dynamic_loss(pcs[v], masks[v], flows[v]) for v in range(n_view))
+        if _use_fused(*pcs, *masks, *flows) and len({m.shape for m in masks}) == 1:
+            # the Kabsch kernel runs one CTA per cloud: all views in ONE launch (sum of per-view means = n_view * mean)
+            l_dynamic = scale * n_view * self.dynamic_loss(torch.cat(pcs, 0), torch.cat(masks, 0), torch.cat(flows, 0))
+        else:
+            l_dynamic = scale * sum(self.dynamic_loss(pcs[v], masks[v], flows[v]) for v in range(n_view))
         l_smooth = scale * sum(self.smooth_loss(pcs[v], masks[v]) for v in range(n_view))
         terms = [w(self.w_dynamic, self.start_step_dynamic) * l_dynamic,
                  w(self.w_smooth, self.start_step_smooth) * l_smooth]

@@ -187,6 +187,49 @@ class FeaturePropagation(nn.Module):
         return self.mlp(feats.unsqueeze(-1)).squeeze(-1)
 
 
+class _MaskHeadFn(torch.autograd.Function):
+    """softmax_k(cos(point feature, slot) / temperature) on csrc/mask_head.cu; slots arrive normalised."""
+
+    @staticmethod
+    def forward(ctx, feats, slots_hat, inv_temp):
+        import ctypes
+        from ogc_b200 import _lib
+        from ogc_b200.backend import TIMER
+        be = _backend_mod.get_backend()
+        feats, slots_hat = feats.contiguous(), slots_hat.contiguous()
+        B, D, N = feats.shape
+        K = slots_hat.shape[2]
+        mask = torch.empty(B, N, K, dtype=torch.float32, device=feats.device)
+        P = lambda t: ctypes.c_void_p(t.data_ptr())
+        with TIMER.span("mask_head_fwd", B * N * 4 * (D + K)):
+            _lib.check(be.lib.ogc_mask_head_fwd(B, D, N, K, float(inv_temp), P(feats), P(slots_hat), P(mask),
+                                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "ogc_mask_head_fwd")
+        be.launches += 1
+        ctx.inv_temp = float(inv_temp)
+        ctx.save_for_backward(feats, slots_hat, mask)
+        return mask
+
+    @staticmethod
+    def backward(ctx, dmask):
+        import ctypes
+        from ogc_b200 import _lib
+        from ogc_b200.backend import TIMER
+        be = _backend_mod.get_backend()
+        feats, slots_hat, mask = ctx.saved_tensors
+        B, D, N = feats.shape
+        K = slots_hat.shape[2]
+        dmask = dmask.contiguous()
+        dfeats = torch.empty_like(feats)
+        dslots = torch.zeros_like(slots_hat)
+        P = lambda t: ctypes.c_void_p(t.data_ptr())
+        with TIMER.span("mask_head_bwd", B * N * 4 * (2 * D + 2 * K)):
+            _lib.check(be.lib.ogc_mask_head_bwd(B, D, N, K, ctx.inv_temp, P(feats), P(slots_hat), P(mask), P(dmask),
+                                                P(dfeats), P(dslots),
+                                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "ogc_mask_head_bwd")
+        be.launches += 1
+        return dfeats, dslots, None
+
+
 class _OutProj(nn.Module):
     def __init__(self, dim):
         super().__init__()
@@ -295,5 +338,8 @@ class MaskFormer3D(nn.Module):
             l_feats[i] = self.FP_modules[i](l_pc[i], l_pc[i + 1], l_feats[i], l_feats[i + 1])
         slot = self.MF_head(l_feats[-1].transpose(1, 2))                      # (B,K,D)
         slot = self.object_mlp(slot.transpose(1, 2))                          # (B,64,K)
+        if (not FORCE_COMPOSED and not REFERENCE_FAITHFUL and pc.is_cuda and l_feats[0].shape[1] == 64 and slot.shape[2] <= 16
+                and getattr(_backend_mod.get_backend(), "name", "") == "b200"):
+            return _MaskHeadFn.apply(l_feats[0], F.normalize(slot, dim=1), 1.0 / 0.05)
         logits = torch.einsum("bdn,bdk->bnk", F.normalize(l_feats[0], dim=1), F.normalize(slot, dim=1)) / 0.05
         return logits.softmax(dim=-1)

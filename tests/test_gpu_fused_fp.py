@@ -82,3 +82,27 @@ def test_fused_fp_is_the_path_the_model_takes(b200):
         backend.TIMER.enabled = False
         backend.TIMER.reset()
     assert {"fp_interp_concat", "fp_mlp_fwd", "fp_mlp_dw", "fp_mlp_dx"} <= names, names
+
+
+@pytest.mark.parametrize("n,k", [(1000, 10), (512, 8), (77, 16)])
+def test_mask_head_matches_composed(b200, n, k):
+    """csrc/mask_head.cu vs normalize -> einsum -> /0.05 -> softmax (models/segnet_kitti.py:85-88), values and both gradients."""
+    import torch.nn.functional as F
+    from ogc_b200.segnet import _MaskHeadFn
+    torch.manual_seed(n)
+    B, D = 3, 64
+    feats = torch.randn(B, D, n, device="cuda") * torch.rand(B, 1, n, device="cuda") * 3
+    feats[:, :, 5] = 0.0                                   # a zero feature vector: F.normalize's eps branch
+    slot = torch.randn(B, D, k, device="cuda")
+    probe = torch.randn(B, n, k, device="cuda")
+
+    f1, s1 = feats.clone().requires_grad_(True), slot.clone().requires_grad_(True)
+    ref = (torch.einsum("bdn,bdk->bnk", F.normalize(f1, dim=1), F.normalize(s1, dim=1)) / 0.05).softmax(dim=-1)
+    (ref * probe).sum().backward()
+    f2, s2 = feats.clone().requires_grad_(True), slot.clone().requires_grad_(True)
+    out = _MaskHeadFn.apply(f2, F.normalize(s2, dim=1), 1.0 / 0.05)
+    (out * probe).sum().backward()
+    assert float((out - ref).abs().max()) < 2e-5
+    live = torch.ones(n, dtype=torch.bool, device="cuda"); live[5] = False      # d/df at f = 0 is eps-scaled noise in both
+    assert fro_err(f2.grad[:, :, live], f1.grad[:, :, live]) < 1e-4, fro_err(f2.grad[:, :, live], f1.grad[:, :, live])
+    assert fro_err(s2.grad, s1.grad) < 1e-4, fro_err(s2.grad, s1.grad)
