@@ -335,15 +335,34 @@ neighbor_l1_kernel(int n, int K, int S, const float *__restrict__ mask, const in
         }
         if (j >= 0 && j != pt) {
             const float *nrow = mask + static_cast<size_t>(j) * K;
+            if ((K & 1) == 0) {
+                // even K: rows are 8-byte aligned -> 64-bit row loads and ONE vector reduction (red.v2.f32) per channel pair
+                float *grow = grad_mask ? grad_mask + static_cast<size_t>(j) * K : nullptr;
 #pragma unroll
-            for (int c = 0; c < kMaxSlots; ++c) {
-                if (c >= K) break;
-                const float d = __ldg(crow + c) - __ldg(nrow + c);
-                total += fabsf(d);
-                if (grad_mask && d != 0.f) {
-                    const float sg = d > 0.f ? 1.f : -1.f;
-                    cg[c] += sg;
-                    atomicAdd(grad_mask + static_cast<size_t>(j) * K + c, -sg * gscale);
+                for (int c = 0; c < kMaxSlots; c += 2) {
+                    if (c >= K) break;
+                    const float2 a = __ldg(reinterpret_cast<const float2 *>(crow + c));
+                    const float2 o = __ldg(reinterpret_cast<const float2 *>(nrow + c));
+                    const float d0 = a.x - o.x, d1 = a.y - o.y;
+                    total += fabsf(d0) + fabsf(d1);
+                    if (grad_mask) {
+                        const float s0 = d0 > 0.f ? 1.f : (d0 < 0.f ? -1.f : 0.f), s1 = d1 > 0.f ? 1.f : (d1 < 0.f ? -1.f : 0.f);
+                        cg[c] += s0; cg[c + 1] += s1;
+                        if (s0 != 0.f || s1 != 0.f)
+                            asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(grow + c), "f"(-s0 * gscale), "f"(-s1 * gscale) : "memory");
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < kMaxSlots; ++c) {
+                    if (c >= K) break;
+                    const float d = __ldg(crow + c) - __ldg(nrow + c);
+                    total += fabsf(d);
+                    if (grad_mask && d != 0.f) {
+                        const float sg = d > 0.f ? 1.f : -1.f;
+                        cg[c] += sg;
+                        atomicAdd(grad_mask + static_cast<size_t>(j) * K + c, -sg * gscale);
+                    }
                 }
             }
         }

@@ -37,7 +37,7 @@ def supported(channels):
 
 class _FusedFP(Function):
     @staticmethod
-    def forward(ctx, unknown, known, skip, known_feats, *params):
+    def forward(ctx, unknown, known, skip, known_feats, nn_d2, nn_idx, *params):
         """params = (W_1, gamma_1, beta_1, ..., W_L, gamma_L, beta_L); W_l (Cout,Cin,1,1)."""
         be = get_backend()
         lib = be.lib
@@ -48,7 +48,7 @@ class _FusedFP(Function):
         c1 = 0 if skip is None else skip.shape[1]
         dev = unknown.device
         f32 = dict(dtype=torch.float32, device=dev)
-        d2, idx = be.three_nn(unknown, known)
+        d2, idx = (nn_d2, nn_idx) if nn_idx is not None else be.three_nn(unknown, known)
         x = torch.empty(B, c2 + c1, n, **f32)
         wgt = torch.empty(B, n, 3, **f32)
         with TIMER.span("fp_interp_concat", B * (4 * c2 * m + 24 * n + 4 * c1 * n + 4 * (c2 + c1) * n + 12 * n)):
@@ -153,12 +153,14 @@ class _FusedFP(Function):
                         d_known = be.three_interpolate_grad(dx, idx, wgt, m)
                     else:
                         d_skip = dx
-        return (None, None, d_skip, d_known, *grads)
+        return (None, None, d_skip, d_known, None, None, *grads)
 
 
-def fused_fp(unknown, known, skip, known_feats, layers):
+def fused_fp(unknown, known, skip, known_feats, layers, nn=None):
     """unknown (B,n,3), known (B,m,3), skip (B,C1,n) or None, known_feats (B,C2,m),
-    layers = [(W, gamma, beta), ...]  ->  (B, C_L, n)."""
+    layers = [(W, gamma, beta), ...]  ->  (B, C_L, n).  nn = (dist2, idx) of three_nn(unknown, known) when it was
+    computed ahead of time."""
     flat = [t for layer in layers for t in layer]
+    d2, idx = nn if nn is not None else (None, None)
     return _FusedFP.apply(unknown.contiguous(), known.contiguous(), None if skip is None else skip.contiguous(),
-                          known_feats.contiguous(), *flat)
+                          known_feats.contiguous(), d2, idx, *flat)

@@ -55,6 +55,17 @@ def smooth_specs(smooth_loss):
     return (("knn", a.k, a.radius), ("ball", b.k, b.radius))
 
 
+SIDE_STREAM = True      # run the masks-only latency-bound work of the criterion on a side stream (fused path)
+_SIDE = {}
+
+
+def _side_stream(device):
+    key = (device.type, device.index)
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=device)
+    return _SIDE[key]
+
+
 def _use_fused(*tensors):
     if FORCE_COMPOSED or REFERENCE_FAITHFUL or not all(t.is_cuda for t in tensors):
         return False
@@ -309,8 +320,9 @@ class InvarianceLoss(nn.Module):
             return F.binary_cross_entropy(pred, target, reduction="none").sum(dim=1).mean()
         return (pred - target).norm(p=self.loss_norm, dim=-1).mean()
 
-    def forward(self, mask1, mask2):
-        perm12, perm21 = match_indices_by_iou(mask1, mask2)
+    def forward(self, mask1, mask2, perms=None):
+        """`perms`: (perm12, perm21) when the matching was computed ahead of time (side stream)."""
+        perm12, perm21 = perms if perms is not None else match_indices_by_iou(mask1, mask2)
         dev = mask1.device
         if torch.is_tensor(perm12):                                   # fused matching: already on the device
             if not self.cross_entropy and self.loss_norm == 2:
@@ -370,28 +382,52 @@ class UnsupervisedOGCLoss(nn.Module):
         scale = 0.5 if aug_transform else 1.0
         w = lambda weight, start: self.step_lossw(it, weight, start) if step_w else weight
 
+        # Latency-bound work that depends on the masks only -- the device Hungarian matching of the invariance term
+        # (one warp per sample) and the logged-only entropy / nuclear norm (Jacobi on K x K Gram matrices) -- runs on
+        # a side stream underneath the dynamic / smoothness kernels (fork / join by events: parallel branches of the step graph).
+        fused_all = _use_fused(*masks) and len({m.shape for m in masks}) == 1
+        side = main = None
+        perms = [None, None]
+        logged = {}
+
+        def logged_terms():
+            with torch.no_grad():
+                if fused_all:
+                    # logged-only terms: one launch over all views (sum of per-view means = n_view * mean over all)
+                    allm = torch.cat([m.detach() for m in masks], dim=0)
+                    logged["entropy"] = scale * n_view * self.entropy_loss(allm)
+                    logged["rank"] = scale * n_view * self.rank_loss(allm)
+                else:
+                    logged["entropy"] = scale * sum(self.entropy_loss(m) for m in masks)
+                    logged["rank"] = scale * sum(self.rank_loss(m) for m in masks)
+
+        if fused_all and SIDE_STREAM:
+            main = torch.cuda.current_stream()
+            side = _side_stream(masks[0].device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                if aug_transform:
+                    perms = [match_indices_by_iou(masks[0], masks[2]), match_indices_by_iou(masks[1], masks[3])]
+                logged_terms()
         if _use_fused(*pcs, *masks, *flows) and len({m.shape for m in masks}) == 1:
             # the Kabsch kernel runs one CTA per cloud: all views in ONE launch (sum of per-view means = n_view * mean)
             l_dynamic = scale * n_view * self.dynamic_loss(torch.cat(pcs, 0), torch.cat(masks, 0), torch.cat(flows, 0))
         else:
             l_dynamic = scale * sum(self.dynamic_loss(pcs[v], masks[v], flows[v]) for v in range(n_view))
         l_smooth = scale * sum(self.smooth_loss(pcs[v], masks[v]) for v in range(n_view))
+        if side is not None:
+            main.wait_stream(side)
         terms = [w(self.w_dynamic, self.start_step_dynamic) * l_dynamic,
                  w(self.w_smooth, self.start_step_smooth) * l_smooth]
-        logged = {"dynamic": l_dynamic, "smooth": l_smooth}
+        ordered = {"dynamic": l_dynamic, "smooth": l_smooth}
         if aug_transform:
-            l_inv = self.invariance_loss(masks[0], masks[2]) + self.invariance_loss(masks[1], masks[3])
+            l_inv = self.invariance_loss(masks[0], masks[2], perms[0]) + self.invariance_loss(masks[1], masks[3], perms[1])
             terms.append(w(self.w_invariance, self.start_step_invariance) * l_inv)
-            logged["invariance"] = l_inv
-        with torch.no_grad():
-            if _use_fused(*masks) and len({m.shape for m in masks}) == 1:
-                # logged-only terms: one launch over all views (sum of per-view means = n_view * mean over all)
-                allm = torch.cat([m.detach() for m in masks], dim=0)
-                logged["entropy"] = scale * n_view * self.entropy_loss(allm)
-                logged["rank"] = scale * n_view * self.rank_loss(allm)
-            else:
-                logged["entropy"] = scale * sum(self.entropy_loss(m) for m in masks)
-                logged["rank"] = scale * sum(self.rank_loss(m) for m in masks)
+            ordered["invariance"] = l_inv
+        if side is None:
+            logged_terms()
+        ordered["entropy"], ordered["rank"] = logged["entropy"], logged["rank"]
+        logged = ordered
         loss = sum(terms)
         logged["sum"] = loss
         # one device->host transfer for every logged scalar (the reference calls .item() six times)

@@ -169,15 +169,16 @@ class FeaturePropagation(nn.Module):
         super().__init__()
         self.mlp = SharedMLP(channels)
 
-    def forward(self, unknown, known, unknown_feats, known_feats):
-        """unknown (B,n,3), known (B,m,3), unknown_feats (B,C1,n), known_feats (B,C2,m) -> (B,Cout,n)."""
+    def forward(self, unknown, known, unknown_feats, known_feats, nn=None):
+        """unknown (B,n,3), known (B,m,3), unknown_feats (B,C1,n), known_feats (B,C2,m) -> (B,Cout,n).
+        `nn`: (dist2, idx) of three_nn(unknown, known) when computed ahead of time (fused path only)."""
         widths = [self.mlp.layer0.conv.weight.shape[1]] + [getattr(self.mlp, f"layer{i}").conv.weight.shape[0]
                                                            for i in range(self.mlp.n_layers)]
         if (not FORCE_COMPOSED and not REFERENCE_FAITHFUL and unknown.is_cuda and fp_fused.supported(widths)
                 and getattr(_backend_mod.get_backend(), "name", "") == "b200"):
             layers = [(getattr(self.mlp, f"layer{i}").conv.weight, getattr(self.mlp, f"layer{i}").normlayer.gn.weight,
                        getattr(self.mlp, f"layer{i}").normlayer.gn.bias) for i in range(self.mlp.n_layers)]
-            return fp_fused.fused_fp(unknown, known, unknown_feats, known_feats, layers)
+            return fp_fused.fused_fp(unknown, known, unknown_feats, known_feats, layers, nn)
         dist, idx = ops.three_nn(unknown.contiguous(), known.contiguous())
         recip = 1.0 / (dist + 1e-8)
         weight = recip / recip.sum(dim=2, keepdim=True)
@@ -328,14 +329,23 @@ class MaskFormer3D(nn.Module):
             chain.append(pc)
         return chain
 
-    def forward(self, pc, point_feats, centres=None):
+    def geometry_chain(self, pc):
+        """sample_chain + the three_nn of every FP level: everything in the network that is a function of the
+        coordinates alone.  -> (centres, fp_nn)"""
+        centres = self.sample_chain(pc)
+        l_pc = [pc] + centres
+        be = _backend_mod.get_backend()
+        fp_nn = [be.three_nn(l_pc[i].contiguous(), l_pc[i + 1].contiguous()) for i in range(len(self.FP_modules))]
+        return centres, fp_nn
+
+    def forward(self, pc, point_feats, centres=None, fp_nn=None):
         l_pc, l_feats = [pc], [point_feats.transpose(1, 2).contiguous()]
         for i, sa in enumerate(self.SA_modules):
             new_pc, new_feats = sa(l_pc[-1], l_feats[-1], None if centres is None else centres[i])
             l_pc.append(new_pc)
             l_feats.append(new_feats)
         for i in range(len(self.FP_modules) - 1, -1, -1):     # coarse -> fine; FP_modules[i] lifts level i+1 to i
-            l_feats[i] = self.FP_modules[i](l_pc[i], l_pc[i + 1], l_feats[i], l_feats[i + 1])
+            l_feats[i] = self.FP_modules[i](l_pc[i], l_pc[i + 1], l_feats[i], l_feats[i + 1], None if fp_nn is None else fp_nn[i])
         slot = self.MF_head(l_feats[-1].transpose(1, 2))                      # (B,K,D)
         slot = self.object_mlp(slot.transpose(1, 2))                          # (B,64,K)
         if (not FORCE_COMPOSED and not REFERENCE_FAITHFUL and pc.is_cuda and l_feats[0].shape[1] == 64 and slot.shape[2] <= 16

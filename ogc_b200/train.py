@@ -122,8 +122,8 @@ class SegTrainer:
         b, t, n, _ = pcs.shape
         flat = pcs.view(b * t, n, 3)
         pcs_l = [pcs[:, i].contiguous() for i in range(t)]
-        centres = self._prefetch_geometry(flat, pcs_l) if self.overlap_geometry and flat.is_cuda else None
-        masks = self.segnet(flat, flat, centres).view(b, t, n, -1)
+        centres, fp_nn = self._prefetch_geometry(flat, pcs_l) if self.overlap_geometry and flat.is_cuda else (None, None)
+        masks = self.segnet(flat, flat, centres, fp_nn).view(b, t, n, -1)
         masks_l = [masks[:, i].contiguous() for i in range(t)]
         flows_l = [flows[:, i].contiguous() for i in range(t)]
         self.criterion.defer_logging = defer
@@ -146,14 +146,18 @@ class SegTrainer:
         from . import losses
         be = get_backend()
         if getattr(be, "name", "") != "b200" or losses.FORCE_COMPOSED or losses.REFERENCE_FAITHFUL:
-            return None
+            return None, None
         main = torch.cuda.current_stream()
         if self._geo_stream is None:
             self._geo_stream = torch.cuda.Stream()
         side = self._geo_stream
         side.wait_stream(main)
+        from . import segnet as _segnet
         with torch.cuda.stream(side):
-            centres = self.segnet.sample_chain(flat)
+            if _segnet.FORCE_COMPOSED or _segnet.REFERENCE_FAITHFUL:
+                centres, fp_nn = self.segnet.sample_chain(flat), None
+            else:
+                centres, fp_nn = self.segnet.geometry_chain(flat)
         specs = losses.smooth_specs(self.criterion.smooth_loss) if hasattr(self.criterion, "smooth_loss") else None
         losses.NEIGHBOUR_CACHE.clear()
         if specs:
@@ -161,7 +165,7 @@ class SegTrainer:
                 for kind, k, radius in specs:
                     losses.NEIGHBOUR_CACHE[(pc.data_ptr(), kind, k, radius)] = losses.neighbourhood(be, kind, k, radius, pc)
         main.wait_stream(side)
-        return centres
+        return centres, fp_nn
 
     def train_step(self, it, batch, aug_transform=False):
         """batch = (pcs (b,t,N,3), segms, flows (b,t,N,3), valids) on host or device.  Returns loss_dict.
