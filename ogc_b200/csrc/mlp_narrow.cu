@@ -31,6 +31,12 @@ constexpr int kNwThreads = 256;
 constexpr int kNwWarps = kNwThreads / 32;
 constexpr int kNwUnit = 64;   // positions per warp step == nsample
 
+// Weights of the layer being processed, (COUT,32) row-major, copied device-to-device in stream order before each
+// launch.  Every lane of a warp needs the same weight at the same time: from shared memory that is a broadcast
+// LDS.128 which still occupies the SM's load/store data path for 4 cycles (measured: the 32-wide forward kernel sat
+// at 1 LDS.128 per 4 FFMA2 = LSU-bound); from the constant bank it is a uniform load (or a direct c[][] operand).
+__constant__ float4 cNwW[64 * 32 / 4];
+
 // order-preserving map float -> uint32 (for redux.sync max / min)
 __device__ __forceinline__ uint32_t f2ord(float x) {
     const uint32_t b = __float_as_uint(x);
@@ -95,19 +101,16 @@ template <int CIN, int COUT, bool LAST>
 __global__ void __launch_bounds__(kNwThreads, 2)
 narrow_fwd_kernel(NarrowFwdParams q) {
     constexpr int CPG = COUT / kGnGroups;
-    __shared__ __align__(16) float Ws[COUT * CIN];
     __shared__ float2 ss_s[CIN];
     __shared__ uint32_t flip_s[COUT];   // LAST: 0xffffffff for channels whose pooled value is the MINIMUM (gamma < 0)
     __shared__ double gs[kGnGroups][2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y, P = q.P;
-    for (int e = tid; e < COUT * CIN; e += kNwThreads) Ws[e] = __ldg(q.W + e);
     for (int c = tid; c < CIN; c += kNwThreads) ss_s[c] = __ldg(reinterpret_cast<const float2 *>(q.ss_prev) + static_cast<size_t>(b) * CIN + c);
     if (LAST)
         for (int c = tid; c < COUT; c += kNwThreads) flip_s[c] = __ldg(q.gamma + c) < 0.f ? 0xffffffffu : 0u;
     if (tid < kGnGroups * 2) (&gs[0][0])[tid] = 0.0;
     __syncthreads();
-    const float4 *Ws4 = reinterpret_cast<const float4 *>(Ws);
 
     float gsum0 = 0.f, gsum1 = 0.f, gsum2 = 0.f, gsum3 = 0.f, gsq0 = 0.f, gsq1 = 0.f, gsq2 = 0.f, gsq3 = 0.f;
 
@@ -140,7 +143,7 @@ narrow_fwd_kernel(NarrowFwdParams q) {
             for (int c4 = 0; c4 < CIN / 4; ++c4) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float4 w = Ws4[(co0 + j) * (CIN / 4) + c4];
+                    const float4 w = cNwW[(co0 + j) * (CIN / 4) + c4];
                     e0[j] = ffma2(make_float2(w.x, w.y), make_float2(a0[c4 * 4 + 0], a0[c4 * 4 + 1]), e0[j]);
                     e1[j] = ffma2(make_float2(w.x, w.y), make_float2(a1[c4 * 4 + 0], a1[c4 * 4 + 1]), e1[j]);
                     e0[j] = ffma2(make_float2(w.z, w.w), make_float2(a0[c4 * 4 + 2], a0[c4 * 4 + 3]), e0[j]);
@@ -221,13 +224,11 @@ template <int COUT, bool SYNTH>
 __global__ void __launch_bounds__(kNwThreads, 2)
 narrow_dx_kernel(NarrowDxParams q) {
     constexpr int CPREV = 32, CH = 4;
-    __shared__ __align__(16) float Ws[COUT * CPREV];
     __shared__ __align__(16) float4 coef_s[COUT];
     __shared__ float4 prev_s[CPREV];            // scale, shift, mean, rstd of the previous layer's channels
     __shared__ float rowacc[CPREV][2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y, P = q.P;
-    for (int e = tid; e < COUT * CPREV; e += kNwThreads) Ws[e] = __ldg(q.W + e);
     for (int c = tid; c < COUT; c += kNwThreads) coef_s[c] = __ldg(reinterpret_cast<const float4 *>(q.coef) + static_cast<size_t>(b) * COUT + c);
     for (int c = tid; c < CPREV; c += kNwThreads) {
         const int g = c / (CPREV / kGnGroups);
@@ -236,7 +237,6 @@ narrow_dx_kernel(NarrowDxParams q) {
         rowacc[c][0] = rowacc[c][1] = 0.f;
     }
     __syncthreads();
-    const float4 *Ws4 = reinterpret_cast<const float4 *>(Ws);
     float tot_s = 0.f, tot_sy = 0.f;            // lane = channel of layer l-1
 
     const int nunits = P / kNwUnit;
@@ -279,7 +279,7 @@ narrow_dx_kernel(NarrowDxParams q) {
             const float2 dd0 = make_float2(d0, d0), dd1 = make_float2(d1, d1);
 #pragma unroll
             for (int c4 = 0; c4 < CPREV / 4; ++c4) {
-                const float4 w = Ws4[(cb + j) * (CPREV / 4) + c4];
+                const float4 w = cNwW[(cb + j) * (CPREV / 4) + c4];
                 acc0[c4 * 2 + 0] = ffma2(dd0, make_float2(w.x, w.y), acc0[c4 * 2 + 0]);
                 acc1[c4 * 2 + 0] = ffma2(dd1, make_float2(w.x, w.y), acc1[c4 * 2 + 0]);
                 acc0[c4 * 2 + 1] = ffma2(dd0, make_float2(w.z, w.w), acc0[c4 * 2 + 1]);
@@ -465,6 +465,8 @@ extern "C" int ogc_sa_mlp_narrow_fwd(int b, int m, int nsample, int cin, int cou
     q.ymax = ymax; q.ymin = ymin; q.amax = amax; q.amin = amin;
     dim3 grid(narrow_grid_x(b, m), b);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t ce = cudaMemcpyToSymbolAsync(cNwW, w, static_cast<size_t>(cout) * 32 * sizeof(float), 0, cudaMemcpyDeviceToDevice, st);
+    if (ce != cudaSuccess) return static_cast<int>(ce);
     if (cout == 32) {
         if (last) narrow_fwd_kernel<32, 32, true><<<grid, kNwThreads, 0, st>>>(q);
         else narrow_fwd_kernel<32, 32, false><<<grid, kNwThreads, 0, st>>>(q);
@@ -493,6 +495,8 @@ extern "C" int ogc_sa_mlp_narrow_dx(int b, int m, int nsample, int cout, int cpr
     q.gamma_prev = gamma_prev; q.dz_prev = dz_prev; q.ab_prev = ab_prev; q.dgamma_prev = dgamma_prev; q.dbeta_prev = dbeta_prev;
     dim3 grid(narrow_grid_x(b, m), b);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t ce = cudaMemcpyToSymbolAsync(cNwW, w, static_cast<size_t>(cout) * 32 * sizeof(float), 0, cudaMemcpyDeviceToDevice, st);
+    if (ce != cudaSuccess) return static_cast<int>(ce);
     if (cout == 32) {
         if (dz) narrow_dx_kernel<32, false><<<grid, kNwThreads, 0, st>>>(q);
         else narrow_dx_kernel<32, true><<<grid, kNwThreads, 0, st>>>(q);

@@ -114,7 +114,7 @@ class SegTrainer:
         self.overlap_geometry = True      # FPS chain on a side stream under the loss neighbourhoods
         self._geo_stream = None
 
-    def _step_body(self, pcs, flows, it, aug_transform, defer):
+    def _step_body(self, pcs, flows, it, aug_transform, defer, allreduce=True):
         """zero_grad -> forward -> loss -> backward -> NaN count -> all-reduce -> Adam launch (no host sync when
         `defer`).  pcs, flows: (b,t,N,3) on the device."""
         self.segnet.train()
@@ -134,7 +134,7 @@ class SegTrainer:
             self.criterion.defer_logging = False
         loss.backward()
         self.opt.count_nan()
-        if self.world_size > 1:
+        if self.world_size > 1 and allreduce:
             dist.all_reduce(self.opt.flat_g_ext)          # the step's only collective: grads + NaN counter
         return loss_dict
 
@@ -208,13 +208,18 @@ class SegTrainer:
             dst.copy_(src)
         launches0 = get_backend().launches
         host = torch.zeros(16, dtype=torch.float32).pin_memory()      # allocated BEFORE capture
+        # world_size > 1: the graph ends before the collective; the NCCL all-reduce, the Adam kernel and the D2H of the
+        # logged scalars follow it eagerly on the same stream (3 launches) -- no NCCL work inside a stream capture.
+        multi = self.world_size > 1
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            d = self._step_body(g["pcs"], g["flows"], it, aug_transform, defer=True)
-            opt.launch_step(1.0 / self.world_size)
+            d = self._step_body(g["pcs"], g["flows"], it, aug_transform, defer=True, allreduce=False)
             g["keys"] = d["_keys"]
+            g["values"] = d["_values"]
             g["host"] = host[:len(d["_keys"])]
-            g["host"].copy_(d["_values"], non_blocking=True)           # captured D2H of the logged scalars
+            if not multi:
+                opt.launch_step(1.0)
+                g["host"].copy_(d["_values"], non_blocking=True)       # captured D2H of the logged scalars
         g["launches"] = get_backend().launches - launches0
         g["graph"] = graph
         self._graphs[key] = g
@@ -234,6 +239,10 @@ class SegTrainer:
         self.opt.set_lr(self.opt.lr * lr_curve(it, self.global_batch_size, **self.sched))
         g["graph"].replay()
         get_backend().launches += g["launches"]
+        if self.world_size > 1:
+            dist.all_reduce(self.opt.flat_g_ext)           # the step's only collective: grads + NaN counter
+            self.opt.launch_step(1.0 / self.world_size)
+            g["host"].copy_(g["values"], non_blocking=True)
         torch.cuda.current_stream().synchronize()          # the logged scalars are in pinned host memory now
         out = dict(zip(g["keys"], g["host"].tolist()))
         out.setdefault("invariance", 0)
