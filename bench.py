@@ -174,6 +174,15 @@ def main():
     ap.add_argument("--no-ref-ext", action="store_true", help="skip timing the reference CUDA extension arm")
     args = ap.parse_args()
 
+    # stdout carries exactly ONE line, the JSON: everything else any library prints there (NCCL's version banner ...)
+    # is redirected to stderr at the file-descriptor level
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -196,7 +205,7 @@ def main():
                                  "sample": f"{args.steps} steps x 1 pair (2 clouds x {N_POINT} pts), fwd+loss+bwd+Adam"},
                 "e2e": {"value": value, "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return
 
     # ------------------------------------------------------------------ B200 arm
@@ -312,7 +321,7 @@ def main():
         v, ms, clouds = run_cpu_port(1, 0, 1, cores)
         line["cpu_baseline"] = {"value": v, "unit": "clouds/s", "cores": cores, "kind": "port", "ms_per_step": ms,
                                 "sample": f"1 step x 1 pair ({clouds} clouds x {N_POINT} pts, no aug): oracle kernels + torch CPU"}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

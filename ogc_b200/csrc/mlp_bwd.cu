@@ -361,7 +361,7 @@ mlp_dw_kernel(MlpDwParams q) {
 // stream the positions with coalesced 16-byte loads of dz / y, the gathered input tile sits in shared memory and
 // the CPW x CIN partial sums stay in registers across all tiles of the CTA (one reduction at the very end).
 template <int CIN, int CPW>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, CPW <= 4 ? 2 : 1)
 mlp_dw_small_kernel(MlpDwParams q) {
     constexpr int TP = 256;                       // positions per tile: 64 quads, two per lane
     __shared__ __align__(16) float a0[CIN][TP];
@@ -589,7 +589,9 @@ extern "C" int ogc_sa_mlp_layer_dw(int b, int n, int m, int nsample, int cout, i
     cudaError_t e;
     if (gather && cin == 6 && (cout == 32 || cout == 64) && (nsample % 4) == 0) {
         const int total = b * ((m * nsample + 255) / 256);
-        const int gx = total < kNumSMs * 4 ? total : kNumSMs * 4;
+        // cout = 32: 128 registers, 2 CTAs/SM, one resident wave; cout = 64 keeps 8 x 6 sums per warp: 1 CTA/SM
+        const int cap = cout == 32 ? kNumSMs * 2 : kNumSMs * 4;
+        const int gx = total < cap ? total : cap;
         if (cout == 32) mlp_dw_small_kernel<6, 4><<<gx, 256, 0, st>>>(q);
         else mlp_dw_small_kernel<6, 8><<<gx, 256, 0, st>>>(q);
         OGC_RETURN_LAUNCH_STATUS();

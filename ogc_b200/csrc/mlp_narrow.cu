@@ -31,10 +31,11 @@ constexpr int kNwThreads = 256;
 constexpr int kNwWarps = kNwThreads / 32;
 constexpr int kNwUnit = 64;   // positions per warp step == nsample
 
-// Weights of the layer being processed, (COUT,32) row-major, copied device-to-device in stream order before each
-// launch.  Every lane of a warp needs the same weight at the same time: from shared memory that is a broadcast
-// LDS.128 which still occupies the SM's load/store data path for 4 cycles (measured: the 32-wide forward kernel sat
-// at 1 LDS.128 per 4 FFMA2 = LSU-bound); from the constant bank it is a uniform load (or a direct c[][] operand).
+// Weights of the layer whose dX is being computed, (COUT,32) row-major, copied device-to-device in stream order
+// before the launch.  Every lane of a warp needs the same weight at the same time: from shared memory that is a
+// broadcast LDS.128, which still occupies the SM's load/store path that the dX kernel also needs for its three global
+// streams; through the constant bank (LDC) the weights bypass it.  Measured: dX 1.18 -> 1.03 ms per step with the
+// constant bank, forward 0.98 -> 1.18 ms (its LSU is otherwise idle), so only dX uses it.
 __constant__ float4 cNwW[64 * 32 / 4];
 
 // order-preserving map float -> uint32 (for redux.sync max / min)
@@ -101,16 +102,19 @@ template <int CIN, int COUT, bool LAST>
 __global__ void __launch_bounds__(kNwThreads, 2)
 narrow_fwd_kernel(NarrowFwdParams q) {
     constexpr int CPG = COUT / kGnGroups;
+    __shared__ __align__(16) float Ws[COUT * CIN];
     __shared__ float2 ss_s[CIN];
     __shared__ uint32_t flip_s[COUT];   // LAST: 0xffffffff for channels whose pooled value is the MINIMUM (gamma < 0)
     __shared__ double gs[kGnGroups][2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y, P = q.P;
+    for (int e = tid; e < COUT * CIN; e += kNwThreads) Ws[e] = __ldg(q.W + e);
     for (int c = tid; c < CIN; c += kNwThreads) ss_s[c] = __ldg(reinterpret_cast<const float2 *>(q.ss_prev) + static_cast<size_t>(b) * CIN + c);
     if (LAST)
         for (int c = tid; c < COUT; c += kNwThreads) flip_s[c] = __ldg(q.gamma + c) < 0.f ? 0xffffffffu : 0u;
     if (tid < kGnGroups * 2) (&gs[0][0])[tid] = 0.0;
     __syncthreads();
+    const float4 *Ws4 = reinterpret_cast<const float4 *>(Ws);
 
     float gsum0 = 0.f, gsum1 = 0.f, gsum2 = 0.f, gsum3 = 0.f, gsq0 = 0.f, gsq1 = 0.f, gsq2 = 0.f, gsq3 = 0.f;
 
@@ -143,7 +147,7 @@ narrow_fwd_kernel(NarrowFwdParams q) {
             for (int c4 = 0; c4 < CIN / 4; ++c4) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float4 w = cNwW[(co0 + j) * (CIN / 4) + c4];
+                    const float4 w = Ws4[(co0 + j) * (CIN / 4) + c4];
                     e0[j] = ffma2(make_float2(w.x, w.y), make_float2(a0[c4 * 4 + 0], a0[c4 * 4 + 1]), e0[j]);
                     e1[j] = ffma2(make_float2(w.x, w.y), make_float2(a1[c4 * 4 + 0], a1[c4 * 4 + 1]), e1[j]);
                     e0[j] = ffma2(make_float2(w.z, w.w), make_float2(a0[c4 * 4 + 2], a0[c4 * 4 + 3]), e0[j]);
@@ -351,20 +355,25 @@ struct NarrowDwParams {
     float *dW;                       // (COUT,32), accumulated atomically
 };
 
-template <int COUT>
+// One CTA handles 32 output channels [co_off, co_off+32) of layer l (C_out = 64: two CTAs streams via blockIdx.y).
+// lane = (position half h, input-channel pair {cq, cq+16}): per LDS.128 of the dY tile (2 positions x 2 output
+// channels) a lane issues 4 FFMA2 -- twice the arithmetic per shared-memory byte of a lane-per-input-channel mapping,
+// which matters because a warp-wide LDS.128 occupies the load/store path for 4 cycles even when it broadcasts.
 __global__ void __launch_bounds__(kNwThreads, 2)
 narrow_dw_kernel(NarrowDwParams q) {
-    constexpr int CIN = 32, TP = 128, LD = TP + 4, LDD = 2 * TP + 8, Q4 = TP / 4;
+    constexpr int CIN = 32, CO = 32, TP = 128, LD = TP + 4, LDD = 2 * TP + 8, Q4 = TP / 4;
     extern __shared__ __align__(16) float smem[];
-    float *Ds = smem;                      // [COUT/2][LDD]: (dY[2k][p], dY[2k+1][p]) interleaved per position
-    float *As = smem + (COUT / 2) * LDD;   // [CIN][LD]   a_{l-1}
+    float *Ds = smem;                      // [CO/2][LDD]: (dY[2k][p], dY[2k+1][p]) interleaved per position
+    float *As = smem + (CO / 2) * LDD;     // [CIN][LD]   a_{l-1}
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int h = lane >> 4, cq = lane & 15;
+    const int co_off = blockIdx.y * CO;
     const int P = q.dy.P;
     const int tiles_per_sample = P / TP;
     const int total = q.B * tiles_per_sample;
-    float2 acc[COUT / 2];                  // (dW[2k][lane], dW[2k+1][lane])
+    float2 acc0[CO / 2], acc1[CO / 2];     // (dW[2k][ci], dW[2k+1][ci]) for ci = cq and ci = cq + 16
 #pragma unroll
-    for (int i = 0; i < COUT / 2; ++i) acc[i] = make_float2(0.f, 0.f);
+    for (int i = 0; i < CO / 2; ++i) acc0[i] = acc1[i] = make_float2(0.f, 0.f);
 
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
         const int b = w / tiles_per_sample, p_base = (w - b * tiles_per_sample) * TP;
@@ -380,26 +389,23 @@ narrow_dw_kernel(NarrowDwParams q) {
 #pragma unroll
             for (int i = 0; i < CIN * Q4 / kNwThreads; ++i) {
                 const int e = tid + i * kNwThreads, c = e / Q4, p = (e - c * Q4) * 4;
-                const float s = __ldg(q.ss_prev + (static_cast<size_t>(b) * CIN + c) * 2), h = __ldg(q.ss_prev + (static_cast<size_t>(b) * CIN + c) * 2 + 1);
-                *reinterpret_cast<float4 *>(As + c * LD + p) = make_float4(fmaxf(fmaf(s, v[i].x, h), 0.f), fmaxf(fmaf(s, v[i].y, h), 0.f),
-                                                                          fmaxf(fmaf(s, v[i].z, h), 0.f), fmaxf(fmaf(s, v[i].w, h), 0.f));
+                const float s = __ldg(q.ss_prev + (static_cast<size_t>(b) * CIN + c) * 2), hh = __ldg(q.ss_prev + (static_cast<size_t>(b) * CIN + c) * 2 + 1);
+                *reinterpret_cast<float4 *>(As + c * LD + p) = make_float4(fmaxf(fmaf(s, v[i].x, hh), 0.f), fmaxf(fmaf(s, v[i].y, hh), 0.f),
+                                                                          fmaxf(fmaf(s, v[i].z, hh), 0.f), fmaxf(fmaf(s, v[i].w, hh), 0.f));
             }
         }
         // dY tile: thread -> (channel PAIR, quad): both channels' quads are loaded, interleaved, stored as 2 x 16 B
-        // (COUT = 64 keeps 64 accumulators alive: one pair at a time there, two otherwise)
-        constexpr int DB = COUT > 32 ? 1 : 2;
+        {
+            DyRaw raw[2][2];
 #pragma unroll
-        for (int i0 = 0; i0 < (COUT / 2) * Q4 / kNwThreads; i0 += DB) {
-            DyRaw raw[DB][2];
-#pragma unroll
-            for (int k = 0; k < DB; ++k) {
-                const int e = tid + (i0 + k) * kNwThreads, cp = e / Q4, p = (e - cp * Q4) * 4;
-                dy_quad_load(q.dy, b, 2 * cp, p_base + p, raw[k][0]);
-                dy_quad_load(q.dy, b, 2 * cp + 1, p_base + p, raw[k][1]);
+            for (int k = 0; k < 2; ++k) {
+                const int e = tid + k * kNwThreads, cp = e / Q4, p = (e - cp * Q4) * 4;
+                dy_quad_load(q.dy, b, co_off + 2 * cp, p_base + p, raw[k][0]);
+                dy_quad_load(q.dy, b, co_off + 2 * cp + 1, p_base + p, raw[k][1]);
             }
 #pragma unroll
-            for (int k = 0; k < DB; ++k) {
-                const int e = tid + (i0 + k) * kNwThreads, cp = e / Q4, p = (e - cp * Q4) * 4;
+            for (int k = 0; k < 2; ++k) {
+                const int e = tid + k * kNwThreads, cp = e / Q4, p = (e - cp * Q4) * 4;
                 const float4 d0 = dy_quad_finish(q.dy, p_base + p, raw[k][0]), d1 = dy_quad_finish(q.dy, p_base + p, raw[k][1]);
                 float4 *dst = reinterpret_cast<float4 *>(Ds + cp * LDD + 2 * p);
                 dst[0] = make_float4(d0.x, d1.x, d0.y, d1.y);
@@ -407,38 +413,40 @@ narrow_dw_kernel(NarrowDwParams q) {
             }
         }
         __syncthreads();
-        // lane = input channel; warp = 16 positions of the tile
+        // warp = 16 positions of the tile, half-warp h = 8 of them
 #pragma unroll
-        for (int pq = 0; pq < TP / kNwWarps / 4; ++pq) {
-            const int p = warp * (TP / kNwWarps) + pq * 4;
-            const float4 av = *reinterpret_cast<const float4 *>(As + lane * LD + p);
-            const float2 ax = make_float2(av.x, av.x), ay = make_float2(av.y, av.y), az = make_float2(av.z, av.z), aw = make_float2(av.w, av.w);
+        for (int pq = 0; pq < 2; ++pq) {
+            const int p = warp * (TP / kNwWarps) + h * 8 + pq * 4;
+            const float4 a0 = *reinterpret_cast<const float4 *>(As + cq * LD + p);
+            const float4 a1 = *reinterpret_cast<const float4 *>(As + (cq + 16) * LD + p);
 #pragma unroll
-            for (int cp = 0; cp < COUT / 2; ++cp) {
+            for (int cp = 0; cp < CO / 2; ++cp) {
                 const float4 d01 = *reinterpret_cast<const float4 *>(Ds + cp * LDD + 2 * p);
                 const float4 d23 = *reinterpret_cast<const float4 *>(Ds + cp * LDD + 2 * p + 4);
-                acc[cp] = ffma2(make_float2(d01.x, d01.y), ax, acc[cp]);
-                acc[cp] = ffma2(make_float2(d01.z, d01.w), ay, acc[cp]);
-                acc[cp] = ffma2(make_float2(d23.x, d23.y), az, acc[cp]);
-                acc[cp] = ffma2(make_float2(d23.z, d23.w), aw, acc[cp]);
+                const float2 e0 = make_float2(d01.x, d01.y), e1 = make_float2(d01.z, d01.w), e2 = make_float2(d23.x, d23.y), e3 = make_float2(d23.z, d23.w);
+                acc0[cp] = ffma2(e0, make_float2(a0.x, a0.x), acc0[cp]); acc1[cp] = ffma2(e0, make_float2(a1.x, a1.x), acc1[cp]);
+                acc0[cp] = ffma2(e1, make_float2(a0.y, a0.y), acc0[cp]); acc1[cp] = ffma2(e1, make_float2(a1.y, a1.y), acc1[cp]);
+                acc0[cp] = ffma2(e2, make_float2(a0.z, a0.z), acc0[cp]); acc1[cp] = ffma2(e2, make_float2(a1.z, a1.z), acc1[cp]);
+                acc0[cp] = ffma2(e3, make_float2(a0.w, a0.w), acc0[cp]); acc1[cp] = ffma2(e3, make_float2(a1.w, a1.w), acc1[cp]);
             }
         }
     }
-    // reduce the 8 warps' partial columns through shared memory, then one atomic per output
+    // reduce the 16 half-warps' partial sums through shared memory, then one atomic per output
     __syncthreads();
-    float *red = smem;               // [kNwWarps][COUT][33]
+    float *red = smem;               // [2 * kNwWarps][CO][33]
+    const int hw = warp * 2 + h;
 #pragma unroll
-    for (int cp = 0; cp < COUT / 2; ++cp) {
-        red[(warp * COUT + 2 * cp) * 33 + lane] = acc[cp].x;
-        red[(warp * COUT + 2 * cp + 1) * 33 + lane] = acc[cp].y;
+    for (int cp = 0; cp < CO / 2; ++cp) {
+        red[(hw * CO + 2 * cp) * 33 + cq] = acc0[cp].x;      red[(hw * CO + 2 * cp + 1) * 33 + cq] = acc0[cp].y;
+        red[(hw * CO + 2 * cp) * 33 + cq + 16] = acc1[cp].x; red[(hw * CO + 2 * cp + 1) * 33 + cq + 16] = acc1[cp].y;
     }
     __syncthreads();
-    for (int e = tid; e < COUT * CIN; e += kNwThreads) {
+    for (int e = tid; e < CO * CIN; e += kNwThreads) {
         const int co = e / CIN, ci = e - co * CIN;
         float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < kNwWarps; ++w) s += red[(w * COUT + co) * 33 + ci];
-        atomicAdd(q.dW + e, s);
+        for (int w = 0; w < 2 * kNwWarps; ++w) s += red[(w * CO + co) * 33 + ci];
+        atomicAdd(q.dW + static_cast<size_t>(co_off + co) * CIN + ci, s);
     }
 }
 
@@ -465,8 +473,6 @@ extern "C" int ogc_sa_mlp_narrow_fwd(int b, int m, int nsample, int cin, int cou
     q.ymax = ymax; q.ymin = ymin; q.amax = amax; q.amin = amin;
     dim3 grid(narrow_grid_x(b, m), b);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaError_t ce = cudaMemcpyToSymbolAsync(cNwW, w, static_cast<size_t>(cout) * 32 * sizeof(float), 0, cudaMemcpyDeviceToDevice, st);
-    if (ce != cudaSuccess) return static_cast<int>(ce);
     if (cout == 32) {
         if (last) narrow_fwd_kernel<32, 32, true><<<grid, kNwThreads, 0, st>>>(q);
         else narrow_fwd_kernel<32, 32, false><<<grid, kNwThreads, 0, st>>>(q);
@@ -523,20 +529,15 @@ extern "C" int ogc_sa_mlp_narrow_dw(int b, int m, int nsample, int cout, int cin
         return OGC_ERR_UNSUPPORTED;
     q.B = b; q.y_prev = y_prev; q.ss_prev = ss_prev; q.dW = dw;
     const int total = b * (m * nsample / 128);
-    const int gx = total < kNumSMs * 2 ? total : kNumSMs * 2;
+    const int halves = cout / 32;                       // C_out = 64: two CTA streams, 32 output channels each
+    int gx = (kNumSMs * 2) / halves;
+    gx = total < gx ? total : gx;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const size_t smem_tile = (static_cast<size_t>(cout / 2) * 264 + 32 * 132) * sizeof(float);
-    const size_t smem_red = static_cast<size_t>(kNwWarps) * cout * 33 * sizeof(float);
+    const size_t smem_tile = (static_cast<size_t>(16) * 264 + 32 * 132) * sizeof(float);
+    const size_t smem_red = static_cast<size_t>(2 * kNwWarps) * 32 * 33 * sizeof(float);
     const size_t smem = smem_tile > smem_red ? smem_tile : smem_red;
-    cudaError_t e;
-    if (cout == 32) {
-        e = cudaFuncSetAttribute(narrow_dw_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e != cudaSuccess) return static_cast<int>(e);
-        narrow_dw_kernel<32><<<gx, kNwThreads, smem, st>>>(q);
-    } else {
-        e = cudaFuncSetAttribute(narrow_dw_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e != cudaSuccess) return static_cast<int>(e);
-        narrow_dw_kernel<64><<<gx, kNwThreads, smem, st>>>(q);
-    }
+    cudaError_t e = cudaFuncSetAttribute(narrow_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    narrow_dw_kernel<<<dim3(gx, halves), kNwThreads, smem, st>>>(q);
     OGC_RETURN_LAUNCH_STATUS();
 }
