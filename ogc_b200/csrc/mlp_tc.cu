@@ -39,6 +39,8 @@ constexpr int kTcMaxK = 128;       // contraction length (TMEM: 128 accumulator 
 constexpr int kTcWCol = 2 * kTcNT; // first TMEM column of W_hi
 constexpr int kTcRowPad = 16;      // raw rows are padded by 16 B: 16-byte row reads at a 4-bank skew
 constexpr int kTcXfBar = 2;        // named barrier of the transformer warps
+constexpr int kTcStagePitch = kTcNT + 4;   // floats per row of the epilogue staging tile
+constexpr int kTcStageBytes = kTcM * kTcStagePitch * 4;
 
 struct MlpTcParams {
     MlpFwdParams f;
@@ -71,6 +73,10 @@ mlp_fwd_tc_kernel(MlpTcParams q) {
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t a_bytes = static_cast<uint32_t>(KB) * kTcNT * 128u;      // one of hi / lo
     uint8_t *raw_base = smem + static_cast<size_t>(n_op) * 2 * a_bytes;
+    // epilogue staging: the accumulator tile is (channel = thread) x 64 positions; storing it row by row from the
+    // registers puts 16 bytes into 32 different rows per instruction (ncu: 2-2.5x sector inflation, l1tex / lts the
+    // busiest units).  Through this buffer every store instruction writes two full 256-byte row segments.
+    float *stage_y = reinterpret_cast<float *>(raw_base + static_cast<size_t>(n_raw) * q.raw_stage_bytes);
     auto op_hi = [&](int ob) { return smem + static_cast<size_t>(ob) * 2 * a_bytes; };
     auto raw_stage = [&](int u) { return raw_base + static_cast<size_t>(u % n_raw) * q.raw_stage_bytes; };
     const uint32_t g_pitch = static_cast<uint32_t>(K) * 4u + kTcRowPad;     // gather: row = one neighbour's K features
@@ -296,11 +302,26 @@ mlp_fwd_tc_kernel(MlpTcParams q) {
                 for (int j = 0; j < kTcNT; ++j) { s += v[j]; sq = fmaf(v[j], v[j], sq); }
                 ds += static_cast<double>(s);
                 dq += static_cast<double>(sq);
-                if (f.y) {
-                    float4 *dst = reinterpret_cast<float4 *>(f.y + (static_cast<size_t>(b) * Cout + co) * P + p0);
+            }
+            if (f.y) {
+                // registers -> staging (row = channel, 16-byte stores, conflict-free at a 68-float pitch) -> coalesced rows
+                float *srow = stage_y + tid * kTcStagePitch;
 #pragma unroll
-                    for (int j = 0; j < kTcNT / 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                for (int j = 0; j < kTcNT / 4; ++j)
+                    *reinterpret_cast<float4 *>(srow + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                named_bar_sync(1, 128);
+                const int hl = lane & 15, hr = lane >> 4;          // half-warp = one row, lane = 16-byte chunk
+#pragma unroll 4
+                for (int i = 0; i < 16; ++i) {
+                    const int r = warp * 32 + i * 2 + hr, cr = mb * kTcM + r;
+                    if (cr < Cout) {
+                        const float4 t = *reinterpret_cast<const float4 *>(stage_y + r * kTcStagePitch + hl * 4);
+                        *reinterpret_cast<float4 *>(f.y + (static_cast<size_t>(b) * Cout + cr) * P + p0 + hl * 4) = t;
+                    }
                 }
+                named_bar_sync(1, 128);                            // staging free for the next tile
+            }
+            if (valid) {
                 if (LAST) {
                     float vmx = v[0], vmn = v[0];
                     int imx = 0, imn = 0;
@@ -335,12 +356,12 @@ static inline bool tc_fwd_plan(int K, bool gather, int &n_raw, int &n_op, int &s
     const size_t op = static_cast<size_t>(KB) * kTcNT * 128 * 2;
     stage = gather ? kTcNT * (K * 4 + kTcRowPad) + 1024 : K * (kTcNT * 4 + kTcRowPad);
     stage = (stage + 127) & ~127;
-    const size_t budget = static_cast<size_t>(kMaxSmemPerCta) - 6 * 1024 - 1024;
+    const size_t budget = static_cast<size_t>(kMaxSmemPerCta) - 6 * 1024 - 1024 - kTcStageBytes;
     for (n_op = 2; n_op >= 1; --n_op) {
         if (op * n_op + 2 * static_cast<size_t>(stage) > budget) continue;
         n_raw = static_cast<int>((budget - op * n_op) / stage);
         n_raw = n_raw > 4 ? 4 : n_raw;
-        smem = op * n_op + static_cast<size_t>(n_raw) * stage + 1024;
+        smem = op * n_op + static_cast<size_t>(n_raw) * stage + kTcStageBytes + 1024;
         return true;
     }
     return false;
