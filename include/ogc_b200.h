@@ -382,6 +382,13 @@ OGC_API int ogc_mask_head_bwd(int b, int d, int n, int k, float inv_temperature,
                               const float *slots_hat, const float *mask, const float *dmask, float *dfeats,
                               float *dslots_hat, void *stream);
 
+/* Soft correspondence transfer of the multi-frame voting (vote.py:17-28 softmax(-cdist/T) and its use corr @ mask,
+ * vote.py:121; chained correspondences vote.py:50-57 by repeated application -- see csrc/icp.cu):
+ *   out[m,:] = sum_n softmax_n(-|query[m] - key[n]| / temperature) val[n,:]
+ * query (b,n1,3) (= pc_src + flow), key (b,n2,3), val (b,n2,k), out (b,n1,k); k <= 16.  No N x N tensor. */
+OGC_API int ogc_softmax_transfer(int b, int n1, int n2, int k, float temperature, const float *query, const float *key,
+                                 const float *val, float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,6 +62,7 @@ SIGNATURES = {
     "ogc_sa_mlp_narrow_dw": [_I] * 5 + [_P, _P, _I, _I] + [_P] * 7,
     "ogc_mask_head_fwd": [_I] * 4 + [_F] + [_P] * 4,
     "ogc_mask_head_bwd": [_I] * 4 + [_F] + [_P] * 7,
+    "ogc_softmax_transfer": [_I] * 4 + [_F] + [_P] * 5,
     "ogc_adam_step_dev": [_LL, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _P, _P],
 }
 

@@ -313,6 +313,19 @@ class B200Backend:
         self.launches += 1
         return out
 
+    def softmax_transfer(self, query, key, val, temperature):
+        """out[m] = sum_n softmax_n(-|query_m - key_n| / T) val[n]; query (B,N1,3), key (B,N2,3), val (B,N2,K)."""
+        for t, nme in ((query, "query"), (key, "key"), (val, "val")):
+            _chk_f32(t, nme)
+        B, N1, _ = query.shape
+        N2, K = val.shape[1], val.shape[2]
+        out = torch.empty(B, N1, K, dtype=torch.float32, device=query.device)
+        with TIMER.span("softmax_transfer", B * (N1 * (12 + 4 * K) + N2 * (12 + 4 * K))):
+            _lib.check(self.lib.ogc_softmax_transfer(B, N1, N2, K, float(temperature), _ptr(query), _ptr(key), _ptr(val),
+                                                     _ptr(out), _stream()), "ogc_softmax_transfer")
+        self.launches += 1
+        return out
+
     def mask_match(self, inter):
         """inter (B,K,K) int32 -> (perm12, perm21) (B,K) int32, Hungarian on the device (no host sync)."""
         _chk_i32(inter, "inter")

@@ -48,11 +48,45 @@ CASES["flownet_ogcdr_512"] = {"kind": "flownet", "npoint": 512, "B": 2, "seed": 
                               "grad_params": ["encoder_loc.sa1.mlp_convs.0.weight", "gru.convq.mlp_convs.0.weight",
                                               "flow_regressor.fc.weight", "global_corr_layer.epsilon"]}
 CASES["oa_icp"] = {"kind": "oa_icp", "B": 2, "N": 768, "K": 6, "seed": 14, "scale": 8.0, "icp_iter": 4}
+CASES["vote"] = {"kind": "vote", "T": 5, "N": 384, "K": 5, "seed": 21, "window": 3}
 
 
 def make_inputs(case):
     rng = np.random.default_rng(case["seed"])
     f32 = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float32))
+    if case["kind"] == "vote":
+        # T frames of one scene: K rigid parts moving by small per-frame motions, points re-sampled (permuted + jittered)
+        # per frame, soft masks with a different slot order per frame, noisy adjacent flows in both directions
+        T, N, K = case["T"], case["N"], case["K"]
+        base = rng.uniform(-1, 1, size=(N, 3))
+        seg = np.clip(((base[:, 0] + 1) / 2 * K).astype(int), 0, K - 1)
+        frames, segs = [], []
+        cur = base.copy()
+        for t in range(T):
+            perm = rng.permutation(N)
+            frames.append(cur[perm] + rng.normal(size=(N, 3)) * 0.002)
+            segs.append(seg[perm])
+            nxt = cur.copy()
+            for k in range(K):
+                ang = rng.uniform(-0.05, 0.05)
+                Rz = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]])
+                nxt[seg == k] = cur[seg == k] @ Rz.T + rng.uniform(-0.05, 0.05, size=3)
+            cur = nxt
+        pc = np.stack(frames)
+        flows = np.zeros((T - 1, 2, N, 3))
+        for t in range(T - 1):
+            for a, b, slot in ((t, t + 1, 0), (t + 1, t, 1)):
+                d = ((pc[a][:, None, :] - pc[b][None, :, :]) ** 2).sum(-1)
+                # flow towards a nearby point of the same part in the other frame, plus noise
+                d = d + 1e3 * (segs[a][:, None] != segs[b][None, :])
+                flows[t, slot] = pc[b][d.argmin(1)] - pc[a] + rng.normal(size=(N, 3)) * 0.01
+        masks = []
+        for t in range(T):
+            lg = rng.normal(size=(N, K)) * 0.8
+            lg[np.arange(N), segs[t]] += 2.5
+            e = np.exp(lg - lg.max(-1, keepdims=True))
+            masks.append((e / e.sum(-1, keepdims=True))[:, rng.permutation(K)])
+        return {"pc": f32(pc), "mask": f32(np.stack(masks)), "flows": f32(flows)}
     if case["kind"] == "segnet":
         pc = f32(rng.uniform(-1, 1, size=(case["B"], case["n_point"], 3)) * case["scale"])
         probe = f32(rng.normal(size=(case["B"], case["n_point"], case["n_slot"])))
