@@ -318,9 +318,11 @@ def main():
             ref["speedup_e2e"] = line["e2e"]["value"] / ref["value"]
             line["ref_cuda_ext"] = ref
     if world == 1 and not args.no_cpu_baseline:
-        v, ms, clouds = run_cpu_port(1, 0, 1, cores)
+        cpu_steps = 10                      # ~10-15 s of CPU work on the box's host cores
+        v, ms, clouds = run_cpu_port(cpu_steps, 1, 1, cores)
         line["cpu_baseline"] = {"value": v, "unit": "clouds/s", "cores": cores, "kind": "port", "ms_per_step": ms,
-                                "sample": f"1 step x 1 pair ({clouds} clouds x {N_POINT} pts, no aug): oracle kernels + torch CPU"}
+                                "sample": f"{cpu_steps} steps (+1 warm-up) x 1 pair ({clouds} clouds x {N_POINT} pts, no aug): "
+                                          "oracle kernels + the same torch step on the host cores"}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -228,7 +228,8 @@ OGC_API int ogc_gn_bwd_coef(int b, int c, long long count_per_group, const doubl
  * Dense mode (dfeat_pm == NULL): dz_prev (b,rows,P) = relu'(.) * result, and the GroupNorm-backward sums
  * of layer l-1 (ab_prev, dgamma_prev, dbeta_prev) are accumulated.
  * Scatter mode (layer 1): result is scatter-added through idx into dfeat_pm (b,n,dfeat_stride) at
- * channel offset dfeat_off (replaces group_points_grad, src/group_points_gpu.cu:8-25). rows <= 128. */
+ * channel offset dfeat_off (replaces group_points_grad, src/group_points_gpu.cu:8-25); rows <= 128 there.
+ * Dense mode accepts any rows % 16 == 0 (one launch per 128-row block). */
 OGC_API int ogc_sa_mlp_layer_dx(int b, int n, int m, int nsample, int cout, int cin_full, int row_off, int rows,
                                 const float *dz, const float *go, int go_ctotal, int go_coff,
                                 const unsigned char *sel, const float *y, const float *coef, const float *w,

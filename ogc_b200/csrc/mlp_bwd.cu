@@ -81,6 +81,9 @@ struct MlpDxParams {
     const int *idx;              // (B,M,S)
     float *dfeat_pm;             // (B,N,dfeat_stride), channels [dfeat_off, dfeat_off+rows)
     int N, dfeat_stride, dfeat_off;
+    // dense mode over a layer wider than one CTA's 128 rows: this launch covers channels [prev_off, prev_off+rows)
+    // of prev_total (GroupNorm groups are defined on prev_total)
+    int prev_total, prev_off;
     // plain output (feature-propagation layer 0: no norm / activation in front): dx (B,dx_ctotal,P), channels
     // [dx_coff, dx_coff+rows)
     float *dx;
@@ -113,9 +116,9 @@ mlp_dx_kernel(MlpDxParams q) {
         sc[i] = sh[i] = mu[i] = rs[i] = 0.f;
         const int r = rows[i >> 2] + (i & 3);
         if (MODE == kDxDense && r < q.rows) {
-            const int g = r / (q.rows / kGnGroups);
-            sc[i] = __ldg(q.ss_prev + (static_cast<size_t>(b) * q.rows + r) * 2);
-            sh[i] = __ldg(q.ss_prev + (static_cast<size_t>(b) * q.rows + r) * 2 + 1);
+            const int g = (q.prev_off + r) / (q.prev_total / kGnGroups);
+            sc[i] = __ldg(q.ss_prev + (static_cast<size_t>(b) * q.prev_total + q.prev_off + r) * 2);
+            sh[i] = __ldg(q.ss_prev + (static_cast<size_t>(b) * q.prev_total + q.prev_off + r) * 2 + 1);
             mu[i] = __ldg(q.mean_rstd_prev + (b * kGnGroups + g) * 2);
             rs[i] = __ldg(q.mean_rstd_prev + (b * kGnGroups + g) * 2 + 1);
         }
@@ -184,8 +187,8 @@ mlp_dx_kernel(MlpDxParams q) {
                         for (int j = 0; j < 4; ++j)
                             if (p + j < P) dp[j] = acc[i][cc * 4 + j];
                 } else {
-                    const float *yp = q.y_prev + (static_cast<size_t>(b) * q.rows + r) * P + p;
-                    float *dp = q.dz_prev + (static_cast<size_t>(b) * q.rows + r) * P + p;
+                    const float *yp = q.y_prev + (static_cast<size_t>(b) * q.prev_total + q.prev_off + r) * P + p;
+                    float *dp = q.dz_prev + (static_cast<size_t>(b) * q.prev_total + q.prev_off + r) * P + p;
                     float o[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -224,10 +227,10 @@ mlp_dx_kernel(MlpDxParams q) {
     __syncthreads();
     for (int r = tid; r < q.rows; r += kMlpThreads) {
         const float a = rowacc[r][0], c = rowacc[r][1];
-        atomicAdd(q.dbeta_prev + r, a);
-        atomicAdd(q.dgamma_prev + r, c);
-        const int g = r / (q.rows / kGnGroups);
-        const double gm = static_cast<double>(__ldg(q.gamma_prev + r));
+        atomicAdd(q.dbeta_prev + q.prev_off + r, a);
+        atomicAdd(q.dgamma_prev + q.prev_off + r, c);
+        const int g = (q.prev_off + r) / (q.prev_total / kGnGroups);
+        const double gm = static_cast<double>(__ldg(q.gamma_prev + q.prev_off + r));
         atomicAdd(q.ab_prev + (b * kGnGroups + g) * 2, gm * a);
         atomicAdd(q.ab_prev + (b * kGnGroups + g) * 2 + 1, gm * c);
     }
@@ -518,8 +521,9 @@ extern "C" int ogc_sa_mlp_layer_dx(int b, int n, int m, int nsample, int cout, i
     if (b < 0 || m <= 0 || nsample <= 0 || cout <= 0 || rows <= 0 || row_off < 0 || row_off + rows > cin_full || !w)
         return OGC_ERR_INVALID_ARG;
     if (b == 0) return OGC_OK;
-    if (b > 65535 || rows > 128) return OGC_ERR_UNSUPPORTED;
+    if (b > 65535) return OGC_ERR_UNSUPPORTED;
     const bool scatter = dfeat_pm != nullptr;
+    if (scatter && rows > 128) return OGC_ERR_UNSUPPORTED;
     MlpDxParams q;
     int rc = fill_dy(q.dy, cout, m, nsample, dz, go, go_ctotal, go_coff, sel, y, coef);
     if (rc != OGC_OK) return rc;
@@ -530,18 +534,24 @@ extern "C" int ogc_sa_mlp_layer_dx(int b, int n, int m, int nsample, int cout, i
             return OGC_ERR_INVALID_ARG;
         if (rows % 16 != 0) return OGC_ERR_UNSUPPORTED;
     }
-    q.cin_full = cin_full; q.row_off = row_off; q.rows = rows; q.W = w;
+    q.cin_full = cin_full; q.W = w;
     q.y_prev = y_prev; q.ss_prev = ss_prev; q.mean_rstd_prev = mean_rstd_prev; q.gamma_prev = gamma_prev;
     q.dz_prev = dz_prev; q.ab_prev = ab_prev; q.dgamma_prev = dgamma_prev; q.dbeta_prev = dbeta_prev;
     q.idx = idx; q.dfeat_pm = dfeat_pm; q.N = n; q.dfeat_stride = dfeat_stride; q.dfeat_off = dfeat_off;
     q.dx = nullptr; q.dx_ctotal = q.dx_coff = 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaError_t e;
     const int mode = scatter ? kDxScatter : kDxDense;
-    if (rows <= 32) e = launch_dx<32, 512>(q, b, mode, st);
-    else if (rows <= 64) e = launch_dx<64, 256>(q, b, mode, st);
-    else e = launch_dx<128, 128>(q, b, mode, st);
-    return e == cudaSuccess ? OGC_OK : static_cast<int>(e);
+    // dense layers wider than 128 channels: one launch per 128-row block (GroupNorm groups span prev_total = rows)
+    for (int off = 0; off < rows; off += 128) {
+        const int chunk = rows - off < 128 ? rows - off : 128;
+        q.row_off = row_off + off; q.rows = chunk; q.prev_total = rows; q.prev_off = off;
+        cudaError_t e;
+        if (chunk <= 32) e = launch_dx<32, 512>(q, b, mode, st);
+        else if (chunk <= 64) e = launch_dx<64, 256>(q, b, mode, st);
+        else e = launch_dx<128, 128>(q, b, mode, st);
+        if (e != cudaSuccess) return static_cast<int>(e);
+    }
+    return OGC_OK;
 }
 
 extern "C" int ogc_pw_mlp_input_grad(int b, int p, int cout, int cin_full, int row_off, int rows, const float *dz,
@@ -561,7 +571,7 @@ extern "C" int ogc_pw_mlp_input_grad(int b, int p, int cout, int cin_full, int r
     q.y_prev = q.ss_prev = q.mean_rstd_prev = q.gamma_prev = nullptr;
     q.dz_prev = nullptr; q.ab_prev = nullptr; q.dgamma_prev = q.dbeta_prev = nullptr;
     q.idx = nullptr; q.dfeat_pm = nullptr; q.N = 0; q.dfeat_stride = q.dfeat_off = 0;
-    q.dx = dx; q.dx_ctotal = dx_ctotal; q.dx_coff = dx_coff;
+    q.dx = dx; q.dx_ctotal = dx_ctotal; q.dx_coff = dx_coff; q.prev_total = rows; q.prev_off = 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e;
     if (rows <= 32) e = launch_dx<32, 512>(q, b, kDxPlain, st);

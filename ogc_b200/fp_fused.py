@@ -29,10 +29,8 @@ def _st():
 
 
 def supported(channels):
-    """Layer widths the kernels cover: outputs multiples of 16 up to 256 (GroupNorm(4) rows per tile), hidden
-    widths <= 128 (the dense input-gradient kernel owns all channels of a GroupNorm layer in one CTA)."""
-    outs = channels[1:]
-    return all(c % 16 == 0 and c <= 256 for c in outs) and all(c <= 128 for c in outs[:-1])
+    """Layer widths the kernels cover: outputs multiples of 16 up to 256 (GroupNorm(4) rows per tile)."""
+    return all(c % 16 == 0 and c <= 256 for c in channels[1:])
 
 
 class _FusedFP(Function):
