@@ -8,6 +8,10 @@
 //                                          TMEM columns), K = input channels, fp32 accumulators in TMEM
 //   fp32-grade accuracy from tf32 tensor cores: x = hi + lo (hi = rna_tf32(x), lo = rna_tf32(x - hi));
 //   D += W_hi a_hi + W_hi a_lo + W_lo a_hi      (error ~3x an fp32 GEMM: tests/test_gpu_tcgen05.py)
+//   issued as TWO instructions per k-step: the hi and lo operand rows of a K block are stacked (64 + 64 rows), so
+//   W_hi x [a_hi ; a_lo] is one N = 128 MMA into 128 accumulator columns and W_lo x a_hi one N = 64 MMA into the
+//   first 64; the epilogue adds the two column halves.  (The source-level profile showed every warp waiting for the
+//   tensor pipe at ~140 cycles per tiny M128 N64 K8 instruction: fewer, larger instructions.)
 //
 // One persistent CTA per SM, warp-specialised, every stage asynchronous to the next:
 //   W (hi and lo)  lives in TENSOR MEMORY for the CTA's lifetime (2 x K columns next to the accumulators) and is
@@ -36,7 +40,8 @@ constexpr int kTcThreads = (kTcMmaWarp + 1) * 32;
 constexpr int kTcNT = 64;          // positions per tile == nsample
 constexpr int kTcM = 128;          // output channels per CTA (one M block)
 constexpr int kTcMaxK = 128;       // contraction length (TMEM: 128 accumulator + 2 * 128 weight columns)
-constexpr int kTcWCol = 2 * kTcNT; // first TMEM column of W_hi
+constexpr int kTcAccCols = 2 * kTcNT;   // accumulator columns per buffer: [W_hi a_hi + W_lo a_hi | W_hi a_lo]
+constexpr int kTcWCol = 2 * kTcAccCols; // first TMEM column of W_hi
 constexpr int kTcRowPad = 16;      // raw rows are padded by 16 B: 16-byte row reads at a 4-bank skew
 constexpr int kTcXfBar = 2;        // named barrier of the transformer warps
 constexpr int kTcStagePitch = kTcNT + 4;   // floats per row of the epilogue staging tile
@@ -183,7 +188,7 @@ mlp_fwd_tc_kernel(MlpTcParams q) {
             if (GATHER) jn = load_idx(u + D + 1);
             mbar_wait(&bar_empty[ob], ((u / n_op) & 1) ^ 1);            // MMAs of the tile that used this buffer are done
             const uint32_t st = raw_u32 + static_cast<uint32_t>(u % n_raw) * q.raw_stage_bytes;
-            const uint32_t a_hi = smem_u32(op_hi(ob)), a_lo = a_hi + a_bytes;
+            const uint32_t a_hi = smem_u32(op_hi(ob)), a_lo = a_hi + kTcNT * 128u;   // K block = [64 hi rows | 64 lo rows]
             if (GATHER) {
                 // rel[tb] was last read by the epilogue of tile u-2, which arrives on bar_tempty AFTER that read
                 mbar_wait(&bar_tempty[tb], ((u >> 1) & 1) ^ 1);
@@ -196,7 +201,7 @@ mlp_fwd_tc_kernel(MlpTcParams q) {
                 // every address is a per-thread constant plus a multiple of the loop counter
                 const int cq = lane, pw = warp - 4;
                 const uint32_t rd = st + pw * g_pitch + cq * 16;
-                const uint32_t wr = static_cast<uint32_t>(cq >> 3) * (kTcNT * 128u) + pw * 128u + (((cq & 7) ^ (pw & 7)) * 16u);
+                const uint32_t wr = static_cast<uint32_t>(cq >> 3) * (2u * kTcNT * 128u) + pw * 128u + (((cq & 7) ^ (pw & 7)) * 16u);
                 if (cq < KB * 8) {
 #pragma unroll 4
                     for (int i = 0; i < kTcNT / kTcXfWarps; ++i) {
@@ -229,7 +234,7 @@ mlp_fwd_tc_kernel(MlpTcParams q) {
                     }
                     float4 hi, lo;
                     tc::tf32_split4(v, hi, lo);
-                    const uint32_t off = static_cast<uint32_t>(i >> 1) * (kTcNT * 128u) + ((i & 1) ? wr1 : wr0);
+                    const uint32_t off = static_cast<uint32_t>(i >> 1) * (2u * kTcNT * 128u) + ((i & 1) ? wr1 : wr0);
                     sts_v4(a_hi + off, hi);
                     sts_v4(a_lo + off, lo);
                 }
@@ -241,23 +246,21 @@ mlp_fwd_tc_kernel(MlpTcParams q) {
     } else if (warp == kTcMmaWarp) {
         // ================================ MMA issuer ================================
         if (lane == 0) {
-            const uint32_t idesc = tc::make_idesc_tf32(kTcM, kTcNT, 0, 0);
+            const uint32_t idesc = tc::make_idesc_tf32(kTcM, kTcNT, 0, 0), idesc2 = tc::make_idesc_tf32(kTcM, 2 * kTcNT, 0, 0);
             for (int u = 0; u < n_my; ++u) {
                 const int ob = u % n_op, tb = u & 1;
                 mbar_wait(&bar_full[ob], (u / n_op) & 1);
                 mbar_wait(&bar_tempty[tb], ((u >> 1) & 1) ^ 1);
                 tc::fence_after_sync();
-                const uint32_t d = tmem_base + static_cast<uint32_t>(tb * kTcNT);
-                const uint32_t bh0 = smem_u32(op_hi(ob)), bl0 = bh0 + a_bytes;
+                const uint32_t d = tmem_base + static_cast<uint32_t>(tb * kTcAccCols);
+                const uint32_t bh0 = smem_u32(op_hi(ob));
                 uint32_t acc = 0;
                 for (int s = 0; s < KB * 4; ++s) {
-                    const uint32_t bo = static_cast<uint32_t>(s >> 2) * (kTcNT * 128u) + static_cast<uint32_t>(s & 3) * 32u;
-                    const uint64_t bhd = tc::make_desc_sw128(bh0 + bo, 16, 1024);
-                    const uint64_t bld = tc::make_desc_sw128(bl0 + bo, 16, 1024);
+                    const uint32_t bo = static_cast<uint32_t>(s >> 2) * (2u * kTcNT * 128u) + static_cast<uint32_t>(s & 3) * 32u;
+                    const uint64_t bd = tc::make_desc_sw128(bh0 + bo, 16, 1024);     // rows 0-63 hi, 64-127 lo
                     const uint32_t wh = tmem_base + kTcWCol + static_cast<uint32_t>(s * 8), wl = wh + Kp;
-                    tc::mma_tf32_ts(d, wh, bhd, idesc, acc);
-                    tc::mma_tf32_ts(d, wh, bld, idesc, 1);
-                    tc::mma_tf32_ts(d, wl, bhd, idesc, 1);
+                    tc::mma_tf32_ts(d, wh, bd, idesc2, acc);     // cols [0,64) (+)= W_hi a_hi, [64,128) (+)= W_hi a_lo
+                    tc::mma_tf32_ts(d, wl, bd, idesc, 1);        // cols [0,64) += W_lo a_hi
                     acc = 1;
                 }
                 tc::mma_commit(&bar_empty[ob]);    // operand buffer may be overwritten
@@ -279,14 +282,20 @@ mlp_fwd_tc_kernel(MlpTcParams q) {
             tc::fence_after_sync();
             float v[kTcNT];
             {
-                float h[32];
-                const uint32_t ta = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(buf * kTcNT);
-                tc::tmem_ld32(ta, h);
+                // four loads in flight, one wait: [0,32) + [64,96) and [32,64) + [96,128) are the two halves' partial sums
+                uint32_t r0[32], r1[32], r2[32], r3[32];
+                const uint32_t ta = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(buf * kTcAccCols);
+                tc::tmem_ld32_issue(ta, r0);
+                tc::tmem_ld32_issue(ta + kTcNT, r1);
+                tc::tmem_ld32_issue(ta + 32, r2);
+                tc::tmem_ld32_issue(ta + kTcNT + 32, r3);
+                tc::tmem_ld_wait();
+                tc::tmem_ld_fence(r0); tc::tmem_ld_fence(r1); tc::tmem_ld_fence(r2); tc::tmem_ld_fence(r3);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = h[j];
-                tc::tmem_ld32(ta + 32, h);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[32 + j] = h[j];
+                for (int j = 0; j < 32; ++j) {
+                    v[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+                    v[32 + j] = __uint_as_float(r2[j]) + __uint_as_float(r3[j]);
+                }
             }
             if (GATHER) {
                 // the three xyz input channels stay on the CUDA cores

@@ -20,6 +20,7 @@ constexpr int kTbLoaderWarps = 8;
 constexpr int kTbLoaders = kTbLoaderWarps * 32;
 constexpr int kTbMmaWarp = 4 + kTbLoaderWarps;
 constexpr int kTbThreads = (kTbMmaWarp + 1) * 32;
+constexpr int kTbDxThreads = kTbThreads + 128;   // dX: a second epilogue warpgroup (warps 13-16) takes the odd tiles
 constexpr int kTbNT = 64;     // positions per tile
 constexpr int kTbM = 128;
 
@@ -48,9 +49,17 @@ constexpr int kTbXfBar = 2;
 // Same skeleton as mlp_fwd_tc_kernel (mlp_tc.cu): W^T (hi, lo) stationary in TENSOR MEMORY as the A operand, raw
 // y_l / dz_l rows of tile u+D streamed into a shared-memory ring with cp.async, dY built from them (GroupNorm
 // backward folded into 4 coefficients per channel) as the K-major B operand, accumulator double buffered.
+// The epilogue (y_prev reads, ReLU mask, per-channel sums, dz_prev stores: ~2 KB of global traffic per thread and tile at
+// 16 bytes per row and instruction) is the slowest stage of this kernel (source-level profile: transformer and MMA
+// warps wait for free accumulators), so TWO epilogue warpgroups alternate tiles: group g owns accumulator buffer g.
+// (Scatter variant only: with 544 threads the register budget drops to 96 per thread, which the dense variant's
+// epilogue -- 64 prefetched y_prev values next to the accumulator half -- does not fit without spilling; measured
+// 0.437 -> 0.303 ms and 0.280 -> 0.260 ms for the two scatter launches, a net loss for the dense ones.)
 template <bool SCATTER>
-__global__ void __launch_bounds__(kTbThreads, 1)
+__global__ void __launch_bounds__(SCATTER ? kTbDxThreads : kTbThreads, 1)
 mlp_dx_tc_kernel(MlpDxTcParams q) {
+    constexpr int kEpGroups = SCATTER ? 2 : 1;
+    constexpr int kThreads = SCATTER ? kTbDxThreads : kTbThreads;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[2], bar_empty[2], bar_tfull[2], bar_tempty[2];
     __shared__ uint32_t tmem_base_s;
@@ -84,7 +93,7 @@ mlp_dx_tc_kernel(MlpDxTcParams q) {
         mbar_fence_init();
     }
     if (tid < kGnGroups * 2) (&gs[0][0])[tid] = 0.0;
-    for (int c = tid; c < kn; c += kTbThreads)
+    for (int c = tid; c < kn; c += kThreads)
         coef_s[c] = __ldg(reinterpret_cast<const float4 *>(q.dy.coef) + static_cast<size_t>(b) * q.dy.C + q.k0 + c);
     tc::fence_before_sync();
     __syncthreads();
@@ -217,7 +226,8 @@ mlp_dx_tc_kernel(MlpDxTcParams q) {
         }
     } else {
         // ================================ epilogue: thread = input channel r ============================
-        const int r = tid;
+        const int eg = (kEpGroups == 2 && warp > kTbMmaWarp) ? 1 : 0;   // epilogue group: warps 0-3 even tiles, warps 13-16 odd tiles
+        const int r = (warp & 3) * 32 + lane;              // TMEM lane quarter of a warp = warp % 4
         const bool valid = r < q.rows;
         const bool mask = !SCATTER && q.final;
         float sc = 0.f, sh = 0.f, mu = 0.f, rs = 0.f;
@@ -229,10 +239,10 @@ mlp_dx_tc_kernel(MlpDxTcParams q) {
             rs = __ldg(q.mean_rstd_prev + (b * kGnGroups + g) * 2 + 1);
         }
         double dsum = 0.0, dsumy = 0.0;
-        for (int u = 0; u < n_my; ++u) {
+        for (int u = eg; u < n_my; u += kEpGroups) {
             const int buf = u & 1;
             const int p0 = (blockIdx.x + u * gridDim.x) * kTbNT;
-            const uint32_t ta = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(buf * kTbNT);
+            const uint32_t ta = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + static_cast<uint32_t>(buf * kTbNT);
             // the tile is finished in two halves of 32 positions; the y_prev row reads (ReLU mask) of the first half are
             // issued BEFORE waiting for the accumulator, those of the second half fly while the first is processed
             const float4 *yp = reinterpret_cast<const float4 *>(q.y_prev + (static_cast<size_t>(b) * q.rows + (valid ? r : 0)) * P + p0);
@@ -306,12 +316,11 @@ mlp_dx_tc_kernel(MlpDxTcParams q) {
             atomicAdd(&gs[g][0], gm * dsum);
             atomicAdd(&gs[g][1], gm * dsumy);
         }
-        named_bar_sync(1, 128);
-        if (mask && tid < kGnGroups * 2)
-            atomicAdd(q.ab_prev + static_cast<size_t>(b) * kGnGroups * 2 + tid, (&gs[0][0])[tid]);
     }
     tc::fence_before_sync();
     __syncthreads();
+    if (!SCATTER && q.final && tid < kGnGroups * 2)        // both epilogue groups have added their group sums
+        atomicAdd(q.ab_prev + static_cast<size_t>(b) * kGnGroups * 2 + tid, (&gs[0][0])[tid]);
     if (warp == kTbMmaWarp) tc::tmem_dealloc(tmem_base, 512);
 }
 
@@ -692,7 +701,7 @@ extern "C" int ogc_sa_mlp_layer_dx_tc(int b, int n, int m, int nsample, int cout
         if (scatter) {
             e = cudaFuncSetAttribute(mlp_dx_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
             if (e != cudaSuccess) return static_cast<int>(e);
-            mlp_dx_tc_kernel<true><<<grid, kTbThreads, smem, st>>>(q);
+            mlp_dx_tc_kernel<true><<<grid, kTbDxThreads, smem, st>>>(q);
         } else {
             e = cudaFuncSetAttribute(mlp_dx_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
             if (e != cudaSuccess) return static_cast<int>(e);
