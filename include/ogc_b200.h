@@ -51,8 +51,10 @@ OGC_API const char *ogc_version(void);
  *   dataset (b,n,3) -> idxs (b,m).  idxs[.,0] = 0; ties between equal distances resolve
  *   exactly as the reference block reduction does for its block size 2^floor(log2 n) <= 1024
  *   (bit-exact indices).  `temp` (b,n) is the reference's running-min scratch: it is only
- *   REQUIRED (and then clobbered) when n > 16384; otherwise it may be NULL and is untouched.
- *   It need not be pre-filled with 1e10.
+ *   used (and then clobbered) by the single-CTA fallback for n > 131072 (or when a thread-block
+ *   cluster cannot be placed); pass it whenever n > 16384, otherwise it may be NULL and is untouched.
+ *   It need not be pre-filled with 1e10.  16384 < n <= 131072 (raw scenes) runs on a cluster of 8 / 16 CTAs
+ *   per cloud.
  * ------------------------------------------------------------------------------------- */
 OGC_API int ogc_furthest_point_sampling(int b, int n, int m, const float *dataset, float *temp,
                                 int *idxs, void *stream);

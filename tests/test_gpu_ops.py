@@ -28,6 +28,9 @@ def clouds(seed, b, n, kind="normal"):
     (1024, 512, "scene"), (1500, 700, "int"), (2048, 1024, "scene"), (3000, 100, "normal"),
     (4096, 1024, "scene"), (5000, 333, "int"), (8192, 2048, "scene"), (10000, 200, "normal"),
     (16384, 128, "scene"), (20000, 64, "normal"),
+    # raw-scene sizes: thread-block-cluster kernel (8 CTAs x 4 / 8 points per thread, 16 CTAs), then the single-CTA fallback
+    (16385, 40, "int"), (30000, 150, "scene"), (50000, 300, "int"), (65536, 64, "normal"), (100000, 200, "scene"),
+    (131072, 32, "normal"), (140000, 24, "normal"),
 ])
 def test_fps_bit_exact(b200, oracle, n, m, kind):
     xyz = clouds(n + m, 3, n, kind)
