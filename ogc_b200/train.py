@@ -113,6 +113,7 @@ class SegTrainer:
         self.device = self.opt.flat_p.device
         self.overlap_geometry = True      # FPS chain on a side stream under the loss neighbourhoods
         self._geo_stream = None
+        self._geo_stream2 = None
 
     def _step_body(self, pcs, flows, it, aug_transform, defer, allreduce=True):
         """zero_grad -> forward -> loss -> backward -> NaN count -> all-reduce -> Adam launch (no host sync when
@@ -153,11 +154,28 @@ class SegTrainer:
         side = self._geo_stream
         side.wait_stream(main)
         from . import segnet as _segnet
+        third = None
         with torch.cuda.stream(side):
             if _segnet.FORCE_COMPOSED or _segnet.REFERENCE_FAITHFUL:
                 centres, fp_nn = self.segnet.sample_chain(flat), None
             else:
-                centres, fp_nn = self.segnet.geometry_chain(flat)
+                # the three_nn of the finest FP level (8192 <- 2048, the only sizeable one) needs the first level's
+                # centres only: it runs on a third stream next to the rest of the (16-CTA) FPS chain
+                if self._geo_stream2 is None:
+                    self._geo_stream2 = torch.cuda.Stream()
+                third = self._geo_stream2
+                sa = self.segnet.SA_modules
+                centres = [sa[0].sample(flat)]
+                first_done = torch.cuda.Event()
+                first_done.record(side)
+                with torch.cuda.stream(third):
+                    third.wait_event(first_done)
+                    nn0 = be.three_nn(flat.contiguous(), centres[0])
+                for m in sa[1:]:
+                    centres.append(m.sample(centres[-1]))
+                l_pc = [flat] + centres
+                fp_nn = [nn0] + [be.three_nn(l_pc[i].contiguous(), l_pc[i + 1].contiguous())
+                                 for i in range(1, len(self.segnet.FP_modules))]
         specs = losses.smooth_specs(self.criterion.smooth_loss) if hasattr(self.criterion, "smooth_loss") else None
         losses.NEIGHBOUR_CACHE.clear()
         if specs:
@@ -165,6 +183,8 @@ class SegTrainer:
                 for kind, k, radius in specs:
                     losses.NEIGHBOUR_CACHE[(pc.data_ptr(), kind, k, radius)] = losses.neighbourhood(be, kind, k, radius, pc)
         main.wait_stream(side)
+        if third is not None:
+            main.wait_stream(third)
         return centres, fp_nn
 
     def train_step(self, it, batch, aug_transform=False):
