@@ -14,10 +14,13 @@ work is fixed; ranks hold different seeded shards and exchange one NCCL all-redu
 
 Prints ONE JSON line (rank 0).  `value` = clouds/s with the batch already resident in HBM; `e2e` = the
 same through the public step API with pinned-host inputs copied in and the loss dict read back every step.
-`roofline` is for the dominant libogc_b200 kernel of the step (CUDA events on the launching stream);
+`roofline` is for the dominant libogc_b200 kernel family of the step (CUDA events on the launching stream, side-stream
+overlap switched off for that pass; `traffic` = DRAM bytes per span from the committed ncu capture, profiles/ncu_traffic.json);
 `ops` lists every kernel family of ours (FPS and ball_query included, as BASELINE.json's metric asks).
 `cpu_baseline` (rank 0, N=1) times the CPU port (oracle kernels + the same torch step on the host cores)
-on a bounded sample.
+on a bounded sample (10 steps of one pair); `ref_cuda_ext` (N=1) times the reference's own CUDA extension under the
+reference's op sequence on the same GPU.  stdout carries exactly the JSON line (library banners go to stderr).
+With N > 1 the NCCL all-reduce, Adam and the log read-back follow the step graph eagerly.
 """
 import argparse
 import json
