@@ -247,13 +247,6 @@ OGC_API int ogc_sa_mlp_layer_dw(int b, int n, int m, int nsample, int cout, int 
                                 const float *xyz, const float *new_xyz, const float *feat_pm, const int *idx,
                                 float *dw, void *stream);
 
-/* Diagnostic: one 128 x n x k GEMM through tcgen05.mma kind::tf32 (accumulator in TMEM, 128B-swizzled
- * shared-memory operands).  mode 0: a (128,k), b (n,k) -> d = a b^T (K-major operands); mode 1: a (k,128),
- * b (k,n) -> d = a^T b (MN-major operands).  split3 != 0: 3xTF32 (hi*hi + hi*lo + lo*hi), fp32-grade.
- * n, k multiples of 32, n <= 256.  Used by the tests to pin the descriptor conventions on hardware. */
-OGC_API int ogc_tc_probe_gemm(int mode, int n, int k, int split3, const float *a, const float *b, float *d,
-                              void *stream);
-
 /* Tensor-core variant of ogc_sa_mlp_layer_fwd: tcgen05.mma kind::tf32 with the 3xTF32 split (fp32-grade), fp32
  * accumulators in TMEM, warp-specialised loader / MMA / epilogue (csrc/mlp_tc.cu).  Same arguments, except that
  * `w` is W (cout,cin) row-major (not transposed).  nsample == 64; returns OGC_ERR_UNSUPPORTED for shapes it does

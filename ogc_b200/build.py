@@ -54,5 +54,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return OUT
 
 
+PROBE_SRC = os.path.join(HERE, "..", "tests", "csrc")
+PROBE_OUT = os.path.join(PROBE_SRC, "libogc_probe.so")
+
+
+def build_probe(force: bool = False) -> str:
+    """Test-only diagnostics (tests/csrc/*.cu: the tcgen05 descriptor probe, the MMA issue-rate probe) -> their own
+    library, so that nothing test-only is linked into libogc_b200.so."""
+    srcs = sorted(glob.glob(os.path.join(PROBE_SRC, "*.cu")))
+    deps = srcs + glob.glob(os.path.join(CSRC, "*.cuh"))
+    if not force and os.path.exists(PROBE_OUT) and all(os.path.getmtime(d) <= os.path.getmtime(PROBE_OUT) for d in deps):
+        return PROBE_OUT
+    subprocess.check_call([NVCC] + FLAGS + ["-shared", "-o", PROBE_OUT] + srcs)
+    return PROBE_OUT
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build_probe(force="--force" in sys.argv))

@@ -2,7 +2,7 @@
 // accumulator in TMEM, operands in 128B-swizzled shared-memory tiles), used by tests/test_gpu_tcgen05.py to
 // pin the descriptor conventions of tcgen05.cuh (K-major and MN-major operands, single-pass TF32 and the
 // 3xTF32 split) against torch on a B200 before the fused kernels rely on them.
-#include "tcgen05.cuh"
+#include "../../ogc_b200/csrc/tcgen05.cuh"
 
 namespace ogc {
 
@@ -151,7 +151,7 @@ tc_probe_kernel(int mode, int N, int K, int split3, const float *__restrict__ A,
 
 }  // namespace ogc
 
-extern "C" int ogc_tc_probe_gemm(int mode, int n, int k, int split3, const float *a, const float *b, float *d,
+extern "C" __attribute__((visibility("default"))) int ogc_tc_probe_gemm(int mode, int n, int k, int split3, const float *a, const float *b, float *d,
                                  void *stream) {
     using namespace ogc;
     if (n < 32 || n > 256 || n % 32 != 0 || k < 32 || k % 32 != 0 || !a || !b || !d) return OGC_ERR_INVALID_ARG;

@@ -9,8 +9,8 @@ pytestmark = pytest.mark.gpu
 
 
 def run(mode, n, k, split3, a, b):
-    from ogc_b200 import _lib
-    lib = _lib.load()
+    import os
+    lib = ctypes.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libogc_probe.so"))
     d = torch.full((128, n), float("nan"), device="cuda")
     P = lambda t: ctypes.c_void_p(t.data_ptr())
     rc = lib.ogc_tc_probe_gemm(mode, n, k, split3, P(a), P(b), P(d), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
