@@ -247,6 +247,31 @@ OGC_API int ogc_sa_mlp_layer_dw(int b, int n, int m, int nsample, int cout, int 
                                 const float *xyz, const float *new_xyz, const float *feat_pm, const int *idx,
                                 float *dw, void *stream);
 
+/* ---- Chained set-abstraction MLP (round 2; csrc/sa_chain_fwd.cu) ----------------------------------------------------
+ * Replaces, for one grouper of a PointNet++ SA level, grouping_operation x2 + concat + (conv1x1, GroupNorm(4), ReLU) x L
+ * (+ max over nsample) of utils/pointnet2_util.py:33-44 / pointnet2/pointnet2.py:283-294 / utils/nn_util.py:151-168
+ * with positions on the tensor-core M axis and the activations of up to three layers chained through tensor memory.
+ * One launch computes layers 1..nl for every position and reduces the LAST of them: GroupNorm sums, optionally the
+ * stored pre-norm tensor y_out (b,c,m*64), optionally the max / min over each half centre (b,2m,c).  A grouper of L
+ * layers is L launches (nl = 1..L); nothing but `sums` and the pooled extremes is written.
+ *   gather != 0: input = [xyz[idx] - new_xyz (3) | feat_pm[idx] (cf)], w1 (c1, 3 + cf) row-major
+ *   gather == 0: input = relu(scale * y_in + shift), y_in (b, cf, m*64), ss_in (b, cf, 2), w1 (c1, cf)
+ * widths[l]: output channels of layer l (multiples of 32, <= 256).  ss1 / ss2: (b,c_l,2) scale/shift of layers 1 / 2.
+ * nsample == 64, m even.  OGC_ERR_UNSUPPORTED when the shape does not fit (see ogc_sa_chain_fits). */
+OGC_API int ogc_sa_chain_fits(int m, int nsample, int cf, int gather, int nl, const int *widths);
+OGC_API int ogc_sa_chain_fwd(int b, int n, int m, int nsample, int cf, int gather, int nl, const int *widths,
+                             const float *xyz, const float *new_xyz, const float *feat_pm, const int *idx,
+                             const float *y_in, const float *ss_in, const float *w1, const float *w2, const float *w3,
+                             const float *ss1, const float *ss2, double *sums, float *y_out, float *ymax_h,
+                             float *ymin_h, unsigned char *amax_h, unsigned char *amin_h, void *stream);
+/* Combines the half-centre extremes of ogc_sa_chain_fwd and applies GroupNorm + ReLU of the last layer: same outputs
+ * as ogc_sa_finish (out (b,c_total,m) at channel offset c_offset, optional point-major twin out_pm (b,m,c_total),
+ * sel / ysel (b,c,m): winning position (255 = clamped by the ReLU) and its pre-norm value). */
+OGC_API int ogc_sa_pool_finish(int b, int c, int m, const float *ymax_h, const float *ymin_h,
+                               const unsigned char *amax_h, const unsigned char *amin_h, const float *scale_shift,
+                               float *out, float *out_pm, int c_total, int c_offset, unsigned char *sel, float *ysel,
+                               void *stream);
+
 /* Tensor-core variant of ogc_sa_mlp_layer_fwd: tcgen05.mma kind::tf32 with the 3xTF32 split (fp32-grade), fp32
  * accumulators in TMEM, warp-specialised loader / MMA / epilogue (csrc/mlp_tc.cu).  Same arguments, except that
  * `w` is W (cout,cin) row-major (not transposed).  nsample == 64; returns OGC_ERR_UNSUPPORTED for shapes it does

@@ -47,6 +47,28 @@ def _tc_dx_ok(S, cout, rows, scatter):
     return USE_TC and S == 64 and 32 <= cout <= (128 if scatter else 256) and rows <= 128 and (scatter or rows % 16 == 0)
 
 
+STORE_Y = True      # stage 1: keep the pre-norm tensors for the per-layer backward kernels
+USE_CHAIN = True    # round-2 kernels (csrc/sa_chain_*.cu): positions on the MMA's M axis, layers chained through TMEM
+
+
+def _chain_plan(M, S, Cf, widths):
+    """How the chained forward covers a grouper: "full" = all layers resident (L passes, nothing stored),
+    "layer" = one layer per launch with the pre-norm tensors stored once, None = not covered."""
+    if not USE_CHAIN or S != 64 or M % 2:
+        return None
+    lib = get_backend().lib
+    arr = (ctypes.c_int * 3)(*(list(widths) + [0, 0])[:3])
+    if lib.ogc_sa_chain_fits(M, S, Cf, 1, len(widths), arr):
+        return "full"
+    if not lib.ogc_sa_chain_fits(M, S, Cf, 1, 1, arr):
+        return None
+    for l in range(1, len(widths)):
+        one = (ctypes.c_int * 3)(widths[l], 0, 0)
+        if not lib.ogc_sa_chain_fits(M, S, widths[l - 1], 0, 1, one):
+            return None
+    return "layer"
+
+
 def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -70,6 +92,58 @@ class _FusedSAMLP(Function):
         f32 = dict(dtype=torch.float32, device=dev)
         ys, sss, mrs = [], [], []
         y_prev = ss_prev = None
+        widths = [params[3 * l].shape[0] for l in range(L)]
+        plan = _chain_plan(M, S, Cf, widths) if feat_pm is not None and L <= 3 else None
+        if plan is not None:
+            cL = widths[-1]
+            w2d = [params[3 * l].detach().reshape(widths[l], -1).contiguous() for l in range(L)]
+            hx = torch.empty(B, 2 * M, cL, **f32)
+            hn = torch.empty(B, 2 * M, cL, **f32)
+            ax = torch.empty(B, 2 * M, cL, dtype=torch.uint8, device=dev)
+            an = torch.empty(B, 2 * M, cL, dtype=torch.uint8, device=dev)
+            for l in range(L):
+                last = l == L - 1
+                y = torch.empty(B, widths[l], P, **f32) if (STORE_Y or plan == "layer") else None
+                sums = torch.zeros(B, 4, 2, dtype=torch.float64, device=dev)
+                pool = (_p(hx), _p(hn), _p(ax), _p(an)) if last else (None, None, None, None)
+                with TIMER.span(f"sa_chain_fwd[{plan}:{l + 1}/{L}>{widths[l]}]" if TIMER.detail else "sa_chain_fwd",
+                                B * (12 * N + 4 * N * Cf + 4 * P)):
+                    if plan == "full":
+                        arr = (ctypes.c_int * 3)(*(widths[:l + 1] + [0, 0])[:3])
+                        _lib.check(lib.ogc_sa_chain_fwd(
+                            B, N, M, S, Cf, 1, l + 1, arr, _p(xyz), _p(new_xyz), _p(feat_pm), _p(idx), None, None,
+                            _p(w2d[0]), _p(w2d[1]) if L > 1 else None, _p(w2d[2]) if L > 2 else None,
+                            _p(sss[0]) if l > 0 else None, _p(sss[1]) if l > 1 else None, _p(sums), _p(y), *pool, _st()),
+                            "ogc_sa_chain_fwd")
+                    elif l == 0:
+                        arr = (ctypes.c_int * 3)(widths[0], 0, 0)
+                        _lib.check(lib.ogc_sa_chain_fwd(
+                            B, N, M, S, Cf, 1, 1, arr, _p(xyz), _p(new_xyz), _p(feat_pm), _p(idx), None, None,
+                            _p(w2d[0]), None, None, None, None, _p(sums), _p(y), *pool, _st()), "ogc_sa_chain_fwd")
+                    else:
+                        arr = (ctypes.c_int * 3)(widths[l], 0, 0)
+                        _lib.check(lib.ogc_sa_chain_fwd(
+                            B, N, M, S, widths[l - 1], 0, 1, arr, None, None, None, None, _p(ys[l - 1]), _p(sss[l - 1]),
+                            _p(w2d[l]), None, None, None, None, _p(sums), _p(y) if STORE_Y else None, *pool, _st()),
+                            "ogc_sa_chain_fwd")
+                gamma, beta = params[3 * l + 1], params[3 * l + 2]
+                ss = torch.empty(B, widths[l], 2, **f32)
+                mr = torch.empty(B, 4, 2, **f32)
+                _lib.check(lib.ogc_gn_finalize(B, widths[l], (widths[l] // 4) * P, _p(sums), _p(gamma.detach()),
+                                               _p(beta.detach()), _p(ss), _p(mr), _st()), "ogc_gn_finalize")
+                be.launches += 2
+                ys.append(y); sss.append(ss); mrs.append(mr)
+            out = torch.empty(B, cL, M, **f32)
+            sel = torch.empty(B, cL, M, dtype=torch.uint8, device=dev)
+            ysel = torch.empty(B, cL, M, **f32)
+            _lib.check(lib.ogc_sa_pool_finish(B, cL, M, _p(hx), _p(hn), _p(ax), _p(an), _p(sss[-1]), _p(out), None,
+                                              cL, 0, _p(sel), _p(ysel), _st()), "ogc_sa_pool_finish")
+            be.launches += 1
+            ctx.dims = (B, N, M, S, Cf, L)
+            ctx.feat_needs_grad = feat_pm.requires_grad
+            ctx.has_feat = True
+            ctx.save_for_backward(xyz, new_xyz, feat_pm, idx, sel, ysel, *ys, *sss, *mrs, *[p.detach() for p in params])
+            return out
         for l in range(L):
             W, gamma, beta = params[3 * l], params[3 * l + 1], params[3 * l + 2]
             cout, cin = W.shape[0], W.shape[1]

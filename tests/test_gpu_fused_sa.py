@@ -8,6 +8,15 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture
+def per_layer_kernels():
+    """The round-1 per-layer kernels (fallback for shapes the chained kernels do not cover) compared among themselves."""
+    from ogc_b200 import sa_fused
+    sa_fused.USE_CHAIN = False
+    yield
+    sa_fused.USE_CHAIN = True
+
+
 def rel_err(a, b):
     a, b = a.detach(), b.detach()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
@@ -71,7 +80,7 @@ def test_fused_sa_mlp_matches_composed(b200, N, M, Cf, widths):
 
 
 @pytest.mark.parametrize("N,M,Cf,widths", [(400, 100, 96, [64, 64, 128]), (300, 70, 128, [128, 128, 256])])
-def test_tensor_core_forward_matches_simt_forward(b200, N, M, Cf, widths):
+def test_tensor_core_forward_matches_simt_forward(b200, per_layer_kernels, N, M, Cf, widths):
     """tcgen05 3xTF32 kernels vs the fp32 SIMT kernels: every tensor the forward produces (pooled output, stored
     pre-norm activations, GroupNorm scale/shift, arg-max positions) to fp32 accuracy."""
     from ogc_b200 import segnet, sa_fused
@@ -107,7 +116,7 @@ def test_tensor_core_forward_matches_simt_forward(b200, N, M, Cf, widths):
             assert float((a - b).abs().max()) <= 2e-5 * max(1.0, float(a.abs().max()))
 
 
-def test_tensor_core_dw_kernel_matches_simt(b200):
+def test_tensor_core_dw_kernel_matches_simt(b200, per_layer_kernels):
     """Every supported weight-gradient shape through the tcgen05 dW kernel (it is only the default for 128x128)."""
     from ogc_b200 import segnet, sa_fused
     import pointnet2.pointnet2 as ops
@@ -163,7 +172,7 @@ def test_segnet_fused_equals_composed_full_model(b200):
 
 
 @pytest.mark.parametrize("widths", [[32, 32, 32], [32, 32, 64]])
-def test_narrow_kernels_match_generic_kernels(b200, widths):
+def test_narrow_kernels_match_generic_kernels(b200, per_layer_kernels, widths):
     """csrc/mlp_narrow.cu (warp-per-centre, channels in registers) vs the tiled kernels on SA level 1's shapes:
     every tensor the forward saves (pre-norm activations, GroupNorm scale/shift, arg-max slots) and every gradient."""
     from ogc_b200 import segnet, sa_fused

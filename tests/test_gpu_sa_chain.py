@@ -1,0 +1,87 @@
+"""GPU: the chained set-abstraction kernels (csrc/sa_chain_*.cu: positions on the MMA's M axis, layers chained through
+tensor memory) against the round-1 per-layer kernels and against the torch-composed reference expression
+(utils/pointnet2_util.py:33-44): pooled output, GroupNorm scale/shift, arg-max positions, stored pre-norm tensors."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [
+    (512, 128, 3, [32, 32, 32]),          # SA1 scale a (features = raw coordinates): "full" chain, small-row producer
+    (512, 128, 3, [32, 32, 64]),          # SA1 scale b
+    (400, 100, 96, [64, 64, 128]),        # SA2: "full" chain (3 passes, nothing stored)
+    (300, 70, 128, [128, 128, 256]),      # SA3: one layer per launch (weights exceed one SM), last layer in 2 channel slices
+    (256, 64, 16, [64, 64]),              # two-layer MLP, K1 = 16 (8-column operand tail)
+    (256, 64, 40, [32, 96, 160]),         # odd widths: 40-channel rows (32 + 8 tail), group sizes 8 / 24 / 40
+]
+
+
+def _setup(N, M, Cf, widths, B=3):
+    from ogc_b200 import segnet
+    import pointnet2.pointnet2 as ops
+    torch.manual_seed(N + Cf)
+    xyz = torch.randn(B, N, 3, device="cuda")
+    new_xyz = xyz[:, :M].contiguous()
+    feat_pm = torch.randn(B, N, Cf, device="cuda")
+    mlp = segnet.SharedMLP([Cf + 3] + widths).cuda()
+    with torch.no_grad():
+        for n_, p_ in mlp.named_parameters():
+            if "gn.weight" in n_:
+                p_.copy_(torch.randn_like(p_) * 0.5 + 0.8)     # some negative gammas exercise the min branch
+            if "gn.bias" in n_:
+                p_.copy_(torch.randn_like(p_) * 0.3)
+    dist, idx = ops.knn(64, new_xyz, xyz)
+    idx = ops.clip_neighbours_by_radius(dist, idx, 1.2)
+    layers = [(getattr(mlp, f"layer{i}").conv.weight, getattr(mlp, f"layer{i}").normlayer.gn.weight,
+               getattr(mlp, f"layer{i}").normlayer.gn.bias) for i in range(mlp.n_layers)]
+    return xyz, new_xyz, feat_pm, idx, mlp, layers
+
+
+@pytest.mark.parametrize("N,M,Cf,widths", SHAPES)
+def test_chain_forward_matches_per_layer_kernels(b200, N, M, Cf, widths):
+    from ogc_b200 import sa_fused
+    xyz, new_xyz, feat_pm, idx, mlp, layers = _setup(N, M, Cf, widths)
+    assert sa_fused._chain_plan(M, 64, Cf, widths) is not None
+    saved = {}
+    for chain in (False, True):
+        sa_fused.USE_CHAIN, sa_fused.STORE_Y = chain, True
+        try:
+            out = sa_fused.fused_sa_mlp(xyz, new_xyz, feat_pm.clone().requires_grad_(True), idx, layers)
+        finally:
+            sa_fused.USE_CHAIN = True
+        saved[chain] = [out.detach().clone()] + [t.clone() for t in out.grad_fn.saved_tensors[4:]]
+    assert len(saved[False]) == len(saved[True])
+    for a, b in zip(saved[False], saved[True]):
+        assert a.shape == b.shape
+        if a.dtype == torch.uint8:
+            assert float((a != b).float().mean()) < 1e-4       # arg-max positions (ties aside) identical
+        else:
+            assert float((a - b).abs().max()) <= 2e-5 * max(1.0, float(a.abs().max())), float((a - b).abs().max())
+
+
+@pytest.mark.parametrize("N,M,Cf,widths", SHAPES)
+def test_chain_matches_composed_reference_expression(b200, N, M, Cf, widths):
+    """Values and every gradient against grouping_operation + SharedMLP + max in torch (the reference's op sequence)."""
+    import pointnet2.pointnet2 as ops
+    from ogc_b200.sa_fused import fused_sa_mlp
+    xyz, new_xyz, feat_pm, idx, mlp, layers = _setup(N, M, Cf, widths)
+    probe = torch.randn(3, widths[-1], M, device="cuda")
+    f1 = feat_pm.transpose(1, 2).contiguous().requires_grad_(True)
+    grouped = torch.cat([ops.grouping_operation(xyz.transpose(1, 2).contiguous(), idx) - new_xyz.transpose(1, 2).unsqueeze(-1),
+                         ops.grouping_operation(f1, idx)], dim=1)
+    ref = mlp(grouped).max(dim=3).values
+    (ref * probe).sum().backward()
+    ref_grads = {n: p.grad.clone() for n, p in mlp.named_parameters()}
+    ref_df = f1.grad.clone()
+    mlp.zero_grad()
+    f2 = feat_pm.clone().requires_grad_(True)
+    out = fused_sa_mlp(xyz, new_xyz, f2, idx, layers)
+    (out * probe).sum().backward()
+    err = float((out - ref).abs().max() / ref.abs().max())
+    assert err < 2e-5, err
+
+    def fro(a, b):
+        return float((a - b).norm() / b.norm().clamp_min(1e-12))
+    assert fro(f2.grad.transpose(1, 2), ref_df) < 2e-3
+    for n, p in mlp.named_parameters():
+        assert fro(p.grad, ref_grads[n]) < 2e-3, (n, fro(p.grad, ref_grads[n]))
