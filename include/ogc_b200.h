@@ -258,6 +258,9 @@ OGC_API int ogc_sa_mlp_layer_dw(int b, int n, int m, int nsample, int cout, int 
  *   gather == 0: input = relu(scale * y_in + shift), y_in (b, cf, m*64), ss_in (b, cf, 2), w1 (c1, cf)
  * widths[l]: output channels of layer l (multiples of 32, <= 256).  ss1 / ss2: (b,c_l,2) scale/shift of layers 1 / 2.
  * nsample == 64, m even.  OGC_ERR_UNSUPPORTED when the shape does not fit (see ogc_sa_chain_fits). */
+/* Diagnostics (not thread-safe): buf = device int64[3*64*8] or NULL; subsequent ogc_sa_chain_fwd launches record the
+ * SM-clock timeline of CTA (0,0,0): [producer | MMA issuer | epilogue][tile][event]. */
+OGC_API int ogc_sa_chain_debug(long long *buf);
 OGC_API int ogc_sa_chain_fits(int m, int nsample, int cf, int gather, int nl, const int *widths);
 OGC_API int ogc_sa_chain_fwd(int b, int n, int m, int nsample, int cf, int gather, int nl, const int *widths,
                              const float *xyz, const float *new_xyz, const float *feat_pm, const int *idx,

@@ -44,6 +44,7 @@ SIGNATURES = {
     "ogc_gn_bwd_coef": [_I, _I, _LL, _P, _P, _P, _P, _P],
     "ogc_sa_mlp_layer_dx": [_I] * 8 + [_P, _P, _I, _I] + [_P] * 14 + [_I, _I, _P],
     "ogc_sa_mlp_layer_dw": [_I] * 7 + [_P, _P, _I, _I] + [_P] * 11,
+    "ogc_sa_chain_debug": [_P],
     "ogc_sa_chain_fits": [_I] * 5 + [_P],
     "ogc_sa_chain_fwd": [_I] * 7 + [_P] * 19,
     "ogc_sa_pool_finish": [_I] * 3 + [_P] * 7 + [_I, _I, _P, _P, _P],

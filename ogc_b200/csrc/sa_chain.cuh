@@ -20,9 +20,13 @@ namespace chain {
 
 constexpr int kTile = 128;        // positions per tile
 constexpr int kNS = 64;           // nsample (positions per centre)
-constexpr int kThreads = 288;     // warps 0-3 epilogue, 4-7 producer, 8 MMA issuer / TMEM owner
-constexpr int kMmaWarp = 8;
-constexpr int kProdBar = 2, kEpiBar = 3;
+constexpr int kEpiWarps = 8;      // warps 0-7 epilogue: lane quadrant = warp & 3, column group = warp >> 2
+constexpr int kEpi = kEpiWarps * 32;
+constexpr int kProdWarp0 = kEpiWarps;               // warps 8-15 producer: lane quadrant = warp & 3, chunk group = (warp - 8) >> 2
+constexpr int kMmaWarp = kProdWarp0 + 8;            // warp 16 MMA issuer / TMEM owner
+constexpr int kThreads = (kMmaWarp + 1) * 32;       // 544: one warp per scheduler and role left every stage latency-bound
+constexpr int kProdBar = 2, kEpiBar = 4;            // named barriers: 2, 3 = producer groups, 4 = epilogue
+constexpr int kDensePitch = kTile * 4 + 16;         // raw-stage row pitch of a stored channel row (128 positions)
 constexpr int kMaxC = 256;
 
 __host__ __device__ constexpr int align_up(int v, int a) { return (v + a - 1) / a * a; }
@@ -49,18 +53,21 @@ __device__ __forceinline__ void build_weights(uint8_t *dst, const float *__restr
     }
 }
 
-// One layer's MMAs (issued by ONE thread): D[tmem_d] = A[tmem, hi at a_col, lo at a_col + k] x B[smem tile]^T, 3xTF32.
+// One layer's MMAs (executed by ALL lanes of the issuing warp, one elected lane issues): D[tmem_d] = A[tmem, hi at a_col, lo at a_col + k] x B[smem tile]^T, 3xTF32.
 __device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t tmem_a, int k, uint32_t b_smem, int n) {
     const uint32_t idesc = tc::make_idesc_tf32(kTile, n, 0, 0);
-    const uint32_t blk = 2u * static_cast<uint32_t>(n) * 128u, lo_rows = static_cast<uint32_t>(n) * 128u;
-    const int ksteps = k >> 3;
-    for (int s = 0; s < ksteps; ++s) {
-        const uint32_t bo = b_smem + static_cast<uint32_t>(s >> 2) * blk + static_cast<uint32_t>(s & 3) * 32u;
-        const uint64_t bh = tc::make_desc_sw128(bo, 16, 1024), bl = tc::make_desc_sw128(bo + lo_rows, 16, 1024);
-        const uint32_t ah = tmem_a + static_cast<uint32_t>(s * 8), al = ah + static_cast<uint32_t>(k);
-        tc::mma_tf32_ts(tmem_d, ah, bh, idesc, s > 0 ? 1u : 0u);
-        tc::mma_tf32_ts(tmem_d, ah, bl, idesc, 1u);
-        tc::mma_tf32_ts(tmem_d, al, bh, idesc, 1u);
+    const uint32_t blk16 = (2u * static_cast<uint32_t>(n) * 128u) >> 4, lo16 = (static_cast<uint32_t>(n) * 128u) >> 4;
+    const uint64_t d0 = tc::make_desc_sw128(b_smem, 16, 1024);           // start-address field += byte offset >> 4
+    const int kblocks = k >> 5;
+    for (int kb = 0; kb < kblocks; ++kb) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const uint64_t bh = d0 + (static_cast<uint32_t>(kb) * blk16 + static_cast<uint32_t>(s) * 2u), bl = bh + lo16;
+            const uint32_t ah = tmem_a + static_cast<uint32_t>(kb * 32 + s * 8), al = ah + static_cast<uint32_t>(k);
+            tc::mma_tf32_ts_elect(tmem_d, ah, bh, idesc, (kb | s) ? 1u : 0u);
+            tc::mma_tf32_ts_elect(tmem_d, ah, bl, idesc, 1u);
+            tc::mma_tf32_ts_elect(tmem_d, al, bh, idesc, 1u);
+        }
     }
 }
 

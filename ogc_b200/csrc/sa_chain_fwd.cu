@@ -10,11 +10,11 @@
 // through the dense producer.
 //
 // Per persistent CTA (one per SM), tile = 2 centres x 64 neighbours:
-//   producer warps 4-7: cp.async the tile's raw input into a shared-memory stage one tile ahead (gathered
+//   producer warps 8-15 (two per lane quadrant, alternating K chunks): cp.async the tile's raw input into a shared-memory stage one tile ahead (gathered
 //        feature rows, or rows of the stored previous layer), then thread = position turns its row into the layer-1
 //        A operand in TENSOR MEMORY (GroupNorm+ReLU of the stored layer, hi/lo split)
-//   MMA warp 8: one thread issues the layer's k-steps (A from tensor memory, B = resident weights), commits to mbarriers
-//   epilogue warps 0-3: thread = position reads its accumulator row, adds the three relative-coordinate input
+//   MMA warp 16: one thread issues the layer's k-steps (A from tensor memory, B = resident weights), commits to mbarriers
+//   epilogue warps 0-7 (two per lane quadrant, alternating 32-column chunks): thread = position reads its accumulator row, adds the three relative-coordinate input
 //        channels (kept on the CUDA cores: exact fp32, no extra k-step), then either writes GroupNorm+ReLU of it as the
 //        next layer's A operand back into tensor memory, or -- last computed layer -- accumulates the group sums,
 //        stores y, reduces the per-centre extremes (redux.sync over the warp's 32 positions)
@@ -40,12 +40,22 @@ struct FwdParams {
     float *ymax, *ymin;                 // (B,2M,c_total) extremes per half centre, or null
     unsigned char *amax, *amin;
     uint32_t off_w[3], off_raw, off_tab, raw_pitch;
+    uint32_t col_a23, col_acc[2];       // tensor-memory columns (A1 at 0)
+    int dual;                           // two accumulator regions (see the MMA issuer)
+    long long *dbg;                     // optional timeline of CTA (0,0,0): [role 3][tile 64][event 8] SM clocks
 };
+
+#define OGC_DBG(role, u, ev)                                                                                     \
+    do {                                                                                                          \
+        if (q.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && (u) < 64)               \
+            q.dbg[((role) * 64 + (u)) * 8 + (ev)] = clock64();                                                     \
+    } while (0)
 
 __global__ void __launch_bounds__(kThreads, 1)
 sa_chain_fwd_kernel(FwdParams q) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_a[3], bar_acc[3], bar_a1free, bar_accfree;
+    __shared__ __align__(8) uint64_t bar_a[3], bar_acc[3], bar_accfree[2];
+    __shared__ __align__(8) uint64_t bar_kfull[8], bar_kfree[8];      // layer-1 operand, per 32-column K chunk
     __shared__ uint32_t tmem_base_s;
     __shared__ double gs[kGnGroups * 2];
 
@@ -60,18 +70,21 @@ sa_chain_fwd_kernel(FwdParams q) {
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float2 *tab_in = reinterpret_cast<float2 *>(smem + q.off_tab);            // [K1] dense input scale/shift
     float2 *tab_ss0 = tab_in + kMaxC, *tab_ss1 = tab_ss0 + kMaxC;             // layers 1, 2
-    float4 *tab_wx = reinterpret_cast<float4 *>(tab_ss1 + kMaxC);            // [C0] xyz columns of W1
+    float4 *tab_wx = reinterpret_cast<float4 *>(tab_ss1 + kMaxC);            // xyz columns of W1, per channel quad: wx[4] wy[4] wz[4]
+    float *pool_s = reinterpret_cast<float *>(tab_wx + kMaxC);                // [8 epilogue warps][8][33] pooling transpose
 
-    // tensor-memory columns
-    const uint32_t colA1 = 0, colA23 = static_cast<uint32_t>(align_up(2 * K1, 32));
-    const uint32_t a23 = nl > 1 ? 2u * static_cast<uint32_t>(max(q.C[0], nl > 2 ? q.C[1] : 0)) : 0u;
-    const uint32_t colACC = colA23 + a23;
-
+    // tensor-memory columns: A1 (hi | lo) at 0, A2 / A3 (hi | lo) at col_a23, accumulator regions 0 / 1.
+    // Chained layers: layer 1 accumulates in region 1, layers 2.. in region 0, so the next tile's first layer runs
+    // underneath the last (heaviest) epilogue of the current tile.  One layer per launch: tiles alternate regions.
+    const uint32_t colA1 = 0, colA23 = q.col_a23;
+    const bool dual = q.dual != 0, single = nl == 1;
     if (warp == kMmaWarp) tc::tmem_alloc(&tmem_base_s, 512);
     if (tid == 0) {
-        for (int l = 0; l < 3; ++l) { mbar_init(&bar_a[l], 128); mbar_init(&bar_acc[l], 1); }
-        mbar_init(&bar_a1free, 1);
-        mbar_init(&bar_accfree, 128);
+        for (int l = 1; l < 3; ++l) mbar_init(&bar_a[l], kEpi);
+        for (int c = 0; c < 8; ++c) { mbar_init(&bar_kfull[c], 128); mbar_init(&bar_kfree[c], 1); }
+        for (int l = 0; l < 3; ++l) mbar_init(&bar_acc[l], 1);
+        mbar_init(&bar_accfree[0], kEpi);
+        mbar_init(&bar_accfree[1], kEpi);
         mbar_fence_init();
     }
     if (tid < kGnGroups * 2) gs[tid] = 0.0;
@@ -88,9 +101,10 @@ sa_chain_fwd_kernel(FwdParams q) {
     }
     if (gather) {
         const float *W0 = q.W[0] + (nl == 1 ? static_cast<size_t>(c_off) * q.ldw[0] : 0);
-        for (int c = tid; c < q.C[0]; c += kThreads)
-            tab_wx[c] = make_float4(__ldg(W0 + static_cast<size_t>(c) * q.ldw[0]), __ldg(W0 + static_cast<size_t>(c) * q.ldw[0] + 1),
-                                    __ldg(W0 + static_cast<size_t>(c) * q.ldw[0] + 2), 0.f);
+        for (int e = tid; e < q.C[0] * 3; e += kThreads) {
+            const int c = e / 3, x = e - c * 3;
+            reinterpret_cast<float *>(tab_wx)[(c >> 2) * 12 + x * 4 + (c & 3)] = __ldg(W0 + static_cast<size_t>(c) * q.ldw[0] + x);
+        }
     } else {
         for (int c = tid; c < K1; c += kThreads)
             tab_in[c] = __ldg(reinterpret_cast<const float2 *>(q.ss_in) + static_cast<size_t>(b) * K1 + c);
@@ -106,57 +120,95 @@ sa_chain_fwd_kernel(FwdParams q) {
     tc::fence_after_sync();
     const uint32_t tmem_base = tmem_base_s;
 
-    if (warp >= 4 && warp < kMmaWarp) {
+    if (warp >= kProdWarp0 && warp < kMmaWarp) {
         // ============================================ producer ============================================
-        const int pt = tid - 128, pw = warp - 4;
+        const int pw = warp & 3, pg = (warp - kProdWarp0) >> 2;      // lane quadrant; chunk group: chunks pg, pg + 2, ...
+        const int pt = pw * 32 + lane;                               // position within the tile
         const uint32_t raw = smem_u32(smem + q.off_raw), pitch = q.raw_pitch;
         const uint32_t trow = tmem_base + (static_cast<uint32_t>(pw * 32) << 16) + colA1;
         const int Cf = q.Cf;
         auto tile_p0 = [&](int u) { return (static_cast<int>(blockIdx.x) + u * static_cast<int>(gridDim.x)) * kTile; };
         auto load_j = [&](int u) { return (gather && u < n_my) ? __ldg(q.idx + static_cast<size_t>(b) * P + tile_p0(u) + pt) : 0; };
-        auto issue = [&](int u, int j) {
+        // Raw-stage copies, per 32-column K chunk (cp.async, a handful of instructions per row): chunk c of the NEXT
+        // tile is requested as soon as every producer thread has consumed chunk c of the current one, so each copy has
+        // a whole tile period to land (a single whole-tile stage exposed the full L2 latency once per tile).
+        const int nchunks = (K1 + 31) >> 5;
+        const int my_chunks = (nchunks - pg + 1) >> 1;               // the two groups are independent pipelines
+        const int pbar = kProdBar + pg;
+        const float *gsrc = q.feat_pm + static_cast<size_t>(b) * q.N * Cf + (lane & 7) * 4;
+        const uint32_t gdst = raw + static_cast<uint32_t>(pw * 32 + (lane >> 3)) * pitch + (lane & 7) * 16;
+        const float *dsrc = q.y_in + static_cast<size_t>(b) * K1 * P + static_cast<size_t>(pt >> 5) * P + (pt & 31) * 4;
+        const uint32_t ddst = raw + static_cast<uint32_t>(pt >> 5) * kDensePitch + (pt & 31) * 16;
+        auto issue_chunk = [&](int u, int c, int j) {
             if (gather) {
                 if (q.small) return;
-                for (int i = 0; i < 32; ++i) {
-                    const int ji = __shfl_sync(OGC_FULL_MASK, j, i);
-                    const float *src = q.feat_pm + (static_cast<size_t>(b) * q.N + ji) * Cf;
-                    const uint32_t dst = raw + static_cast<uint32_t>(pw * 32 + i) * pitch;
-                    for (int ch = lane; ch < (Cf >> 2); ch += 32) cp_async16_s(dst + ch * 16, src + ch * 4);
+                const bool act = (lane & 7) * 4 < K1 - 32 * c;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {                      // 4 rows x 128 B per instruction
+                    const int ji = __shfl_sync(OGC_FULL_MASK, j, 4 * i + (lane >> 3));
+                    if (act) cp_async16_s(gdst + static_cast<uint32_t>(4 * i) * pitch + c * 128, gsrc + static_cast<size_t>(ji) * Cf + 32 * c);
                 }
             } else {
-                const float *src = q.y_in + static_cast<size_t>(b) * K1 * P + tile_p0(u) + (pt & 31) * 4;
-                for (int c = pt >> 5; c < K1; c += 4)
-                    cp_async16_s(raw + static_cast<uint32_t>(c) * pitch + (pt & 31) * 16, src + static_cast<size_t>(c) * P);
+                const float *src = dsrc + tile_p0(u) + static_cast<size_t>(32 * c) * P;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)                        // rows 32c + (pt>>5) + 4i
+                    cp_async16_s(ddst + static_cast<uint32_t>(32 * c + 4 * i) * kDensePitch, src + static_cast<size_t>(4 * i) * P);
             }
         };
+        auto load_small = [&](int j, float (&f8)[8]) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) f8[c] = c < Cf ? __ldg(q.feat_pm + (static_cast<size_t>(b) * q.N + j) * Cf + c) : 0.f;
+        };
         int j_cur = load_j(0);
-        if (n_my > 0) issue(0, j_cur);
-        cp_async_commit();
+        float f8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (gather && q.small && n_my > 0) load_small(j_cur, f8);
+        for (int c = pg; c < nchunks; c += 2) {
+            if (n_my > 0) issue_chunk(0, c, j_cur);
+            cp_async_commit();
+        }
         for (int u = 0; u < n_my; ++u) {
             const int j_next = load_j(u + 1);
-            float f8[8];
+            const uint32_t fpar = (u & 1) ^ 1;
+            if (warp == kProdWarp0) OGC_DBG(0, u, 0);
+            // The operand is handed over per K chunk as well: chunk c of this tile is written as soon as the previous
+            // tile's MMAs have consumed chunk c, and the MMAs of this tile start on chunk 0 while chunk 1 is written.
             if (gather && q.small) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) f8[c] = c < Cf ? __ldg(q.feat_pm + (static_cast<size_t>(b) * q.N + j_cur) * Cf + c) : 0.f;
-            }
-            cp_async_wait(0);
-            named_bar_sync(kProdBar, 128);                 // the tile's raw rows have landed for every producer thread
-            mbar_wait(&bar_a1free, (u & 1) ^ 1);           // layer-1 MMAs of the previous tile have read the operand
-            tc::fence_after_sync();
-            if (gather && q.small) {
+                if (pg != 0) { j_cur = j_next; continue; }
+                mbar_wait(&bar_kfree[0], fpar);
+                tc::fence_after_sync();
                 float hi[8], lo[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) tc::tf32_split(f8[c], hi[c], lo[c]);
                 tc::tmem_st8_nowait(trow, hi);
                 tc::tmem_st8_nowait(trow + 8, lo);
-            } else {
-                for (int k0 = 0; k0 < K1; k0 += 32) {
-                    if (k0 + 32 <= K1) {
-                        float hi[32], lo[32];
+                tc::tmem_st_wait();
+                tc::fence_before_sync();
+                mbar_arrive(&bar_kfull[0]);
+                if (u + 1 < n_my) load_small(j_next, f8);      // next tile's rows: in flight during this tile's chain
+                j_cur = j_next;
+                continue;
+            }
+            for (int c = pg; c < nchunks; c += 2) {
+                const int k0 = 32 * c;
+                // groups committed after (u, c): the rest of this tile's chunks and the next tile's chunks requested so far
+                cp_async_wait(c == pg ? my_chunks - 1 : my_chunks - 2);   // this thread's copies of (u, c) have landed ...
+                named_bar_sync(pbar, 128);                     // ... the group's; and its previous chunk has been consumed
+                if (warp == kProdWarp0 && c == 0) OGC_DBG(0, u, 1);
+                if (c >= 2) {
+                    if (u + 1 < n_my) issue_chunk(u + 1, c - 2, j_next);
+                    cp_async_commit();
+                }
+                mbar_wait(&bar_kfree[c], fpar);
+                tc::fence_after_sync();
+                if (warp == kProdWarp0 && c == 0) OGC_DBG(0, u, 2);
+                if (k0 + 32 <= K1) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {                  // 16 columns at a time: 48 live registers
+                        float hi[16], lo[16];
                         if (gather) {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const float4 x = lds_v4(raw + static_cast<uint32_t>(pt) * pitch + (k0 + 4 * i) * 4);
+                            for (int i = 0; i < 4; ++i) {
+                                const float4 x = lds_v4(raw + static_cast<uint32_t>(pt) * pitch + (k0 + 16 * h + 4 * i) * 4);
                                 tc::tf32_split(x.x, hi[4 * i], lo[4 * i]);
                                 tc::tf32_split(x.y, hi[4 * i + 1], lo[4 * i + 1]);
                                 tc::tf32_split(x.z, hi[4 * i + 2], lo[4 * i + 2]);
@@ -164,156 +216,272 @@ sa_chain_fwd_kernel(FwdParams q) {
                             }
                         } else {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const float2 s2 = tab_in[k0 + i];
-                                const float y = lds_f32(raw + static_cast<uint32_t>(k0 + i) * pitch + pt * 4);
+                            for (int i = 0; i < 16; ++i) {
+                                const float2 s2 = tab_in[k0 + 16 * h + i];
+                                const float y = lds_f32(raw + static_cast<uint32_t>(k0 + 16 * h + i) * kDensePitch + pt * 4);
                                 tc::tf32_split(fmaxf(fmaf(s2.x, y, s2.y), 0.f), hi[i], lo[i]);
                             }
                         }
-                        tc::tmem_st32_nowait(trow + k0, hi);
-                        tc::tmem_st32_nowait(trow + K1 + k0, lo);
-                    } else {
-                        for (int k1 = k0; k1 < K1; k1 += 8) {          // tail in 8-column pieces (gather only: K1 % 8 == 0)
-                            float hi[8], lo[8];
+                        tc::tmem_st16_nowait(trow + k0 + 16 * h, hi);
+                        tc::tmem_st16_nowait(trow + K1 + k0 + 16 * h, lo);
+                    }
+                } else {
+                    for (int k1 = k0; k1 < K1; k1 += 8) {          // tail in 8-column pieces (gather only: K1 % 8 == 0)
+                        float hi[8], lo[8];
 #pragma unroll
-                            for (int i = 0; i < 2; ++i) {
-                                const float4 x = lds_v4(raw + static_cast<uint32_t>(pt) * pitch + (k1 + 4 * i) * 4);
-                                tc::tf32_split(x.x, hi[4 * i], lo[4 * i]);
-                                tc::tf32_split(x.y, hi[4 * i + 1], lo[4 * i + 1]);
-                                tc::tf32_split(x.z, hi[4 * i + 2], lo[4 * i + 2]);
-                                tc::tf32_split(x.w, hi[4 * i + 3], lo[4 * i + 3]);
-                            }
-                            tc::tmem_st8_nowait(trow + k1, hi);
-                            tc::tmem_st8_nowait(trow + K1 + k1, lo);
+                        for (int i = 0; i < 2; ++i) {
+                            const float4 x = lds_v4(raw + static_cast<uint32_t>(pt) * pitch + (k1 + 4 * i) * 4);
+                            tc::tf32_split(x.x, hi[4 * i], lo[4 * i]);
+                            tc::tf32_split(x.y, hi[4 * i + 1], lo[4 * i + 1]);
+                            tc::tf32_split(x.z, hi[4 * i + 2], lo[4 * i + 2]);
+                            tc::tf32_split(x.w, hi[4 * i + 3], lo[4 * i + 3]);
                         }
+                        tc::tmem_st8_nowait(trow + k1, hi);
+                        tc::tmem_st8_nowait(trow + K1 + k1, lo);
                     }
                 }
+                tc::tmem_st_wait();
+                tc::fence_before_sync();
+                mbar_arrive(&bar_kfull[c]);
+                if (warp == kProdWarp0 && c == 0) OGC_DBG(0, u, 3);
             }
-            tc::tmem_st_wait();
-            tc::fence_before_sync();
-            mbar_arrive(&bar_a[0]);
-            named_bar_sync(kProdBar, 128);                 // every producer thread is done with the raw stage
-            if (u + 1 < n_my) issue(u + 1, j_next);
-            cp_async_commit();
+            if (warp == kProdWarp0) OGC_DBG(0, u, 4);
+            if (my_chunks > 0) {
+                named_bar_sync(pbar, 128);                     // the group's last chunk has been consumed
+                if (u + 1 < n_my) issue_chunk(u + 1, pg + 2 * (my_chunks - 1), j_next);
+                cp_async_commit();
+            }
             j_cur = j_next;
         }
     } else if (warp == kMmaWarp) {
         // ============================================ MMA issuer ============================================
-        if (lane == 0) {
-            const uint32_t d = tmem_base + colACC;
+        // warp-uniform: all lanes run the loop, one elected lane issues each MMA / commit (see tcgen05.cuh)
+        {
             for (int u = 0; u < n_my; ++u) {
                 for (int l = 0; l < nl; ++l) {
-                    mbar_wait(&bar_a[l], u & 1);
-                    if (l == 0) mbar_wait(&bar_accfree, (u & 1) ^ 1);
-                    tc::fence_after_sync();
-                    issue_layer(d, tmem_base + (l == 0 ? colA1 : colA23), l == 0 ? K1 : q.C[l - 1],
-                                smem_u32(smem + q.off_w[l]), q.C[l]);
-                    tc::mma_commit(&bar_acc[l]);
-                    if (l == 0) tc::mma_commit(&bar_a1free);
+                    if (l > 0) mbar_wait(&bar_a[l], u & 1);
+                    int buf = 0;
+                    if (single) {
+                        buf = dual ? (u & 1) : 0;
+                        mbar_wait(&bar_accfree[buf], dual ? (((u >> 1) & 1) ^ 1) : ((u & 1) ^ 1));
+                    } else {
+                        buf = (l == 0 && dual) ? 1 : 0;
+                        // region 0 was last read by the previous tile's final epilogue
+                        if (l == (dual ? 1 : 0)) mbar_wait(&bar_accfree[0], (u & 1) ^ 1);
+                    }
+                    const uint32_t d = tmem_base + q.col_acc[buf];
+                    if (l == 0) OGC_DBG(1, u, 0);
+                    if (l == 0) {
+                        // layer 1: chunk by chunk as the producer hands the operand over; each chunk is released to the
+                        // producer (for the NEXT tile) as soon as its MMAs have completed
+                        const int n = q.C[0];
+                        const uint32_t idesc = tc::make_idesc_tf32(kTile, n, 0, 0);
+                        const uint32_t blk16 = (2u * static_cast<uint32_t>(n) * 128u) >> 4, lo16 = (static_cast<uint32_t>(n) * 128u) >> 4;
+                        const uint64_t d0 = tc::make_desc_sw128(smem_u32(smem + q.off_w[0]), 16, 1024);
+                        for (int k0 = 0; k0 < K1; k0 += 32) {
+                            mbar_wait(&bar_kfull[k0 >> 5], u & 1);
+                            tc::fence_after_sync();
+                            if (k0 == 0) OGC_DBG(1, u, 1);
+                            const int ks = min(4, (K1 - k0) >> 3);
+#pragma unroll
+                            for (int s = 0; s < 4; ++s) {
+                                if (s < ks) {
+                                    const uint64_t bh = d0 + (static_cast<uint32_t>(k0 >> 5) * blk16 + static_cast<uint32_t>(s) * 2u), bl = bh + lo16;
+                                    const uint32_t ah = tmem_base + colA1 + static_cast<uint32_t>(k0 + s * 8), al = ah + static_cast<uint32_t>(K1);
+                                    tc::mma_tf32_ts_elect(d, ah, bh, idesc, (k0 | s) ? 1u : 0u);
+                                    tc::mma_tf32_ts_elect(d, ah, bl, idesc, 1u);
+                                    tc::mma_tf32_ts_elect(d, al, bh, idesc, 1u);
+                                }
+                            }
+                            tc::mma_commit_elect(&bar_kfree[k0 >> 5]);
+                        }
+                    } else {
+                        tc::fence_after_sync();
+                        issue_layer(d, tmem_base + colA23, q.C[l - 1], smem_u32(smem + q.off_w[l]), q.C[l]);
+                    }
+                    // one layer per launch with two regions: a "full" barrier per region (the issuer may run two tiles
+                    // ahead of the epilogue, which would alias the phase parity of a single barrier)
+                    tc::mma_commit_elect(&bar_acc[single ? buf : l]);
+                    OGC_DBG(1, u, 2 + l);
+                    if (q.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && l == nl - 1) {
+                        // diagnostics only: completion time of the tile's MMAs (serialises issue and execution)
+                        mbar_wait(&bar_acc[single ? buf : l], (single && dual) ? ((u >> 1) & 1) : (u & 1));
+                        OGC_DBG(1, u, 6);
+                    }
                 }
             }
         }
     } else {
         // ============================================ epilogue ============================================
-        const int et = tid, ew = warp;
-        const uint32_t trow = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
-        const int gsz = q.c_total / kGnGroups;
-        double dsum[kGnGroups] = {0.0, 0.0, 0.0, 0.0}, dsq[kGnGroups] = {0.0, 0.0, 0.0, 0.0};
+        const int eq = warp & 3, eg = warp >> 2;             // lane quadrant, column group (chunks eg, eg + 2, ...)
+        const int et = eq * 32 + lane;                       // position within the tile
+        const uint32_t trow = tmem_base + (static_cast<uint32_t>(eq * 32) << 16);
+        // GroupNorm group of every 8-channel block of the last layer, 2 bits each (c_total <= 256: 32 blocks)
+        unsigned long long gbits = 0;
+        {
+            const int gsz8 = q.c_total / (kGnGroups * 8);
+            for (int k = 0; k < q.c_total / 8; ++k) gbits |= static_cast<unsigned long long>(k / gsz8) << (2 * k);
+        }
+        float fsum[kGnGroups] = {0.f, 0.f, 0.f, 0.f}, fsq[kGnGroups] = {0.f, 0.f, 0.f, 0.f};
+        float nrx = 0.f, nry = 0.f, nrz = 0.f;
+        auto load_rel = [&](int t, int j) {
+            const float *pj = q.xyz + (static_cast<size_t>(b) * q.N + j) * 3;
+            const float *pc = q.new_xyz + (static_cast<size_t>(b) * q.M + t * 2 + (et >> 6)) * 3;
+            nrx = __ldg(pj) - __ldg(pc); nry = __ldg(pj + 1) - __ldg(pc + 1); nrz = __ldg(pj + 2) - __ldg(pc + 2);
+        };
+        if (gather && n_my > 0)
+            load_rel(blockIdx.x, __ldg(q.idx + static_cast<size_t>(b) * P + static_cast<size_t>(blockIdx.x) * kTile + et));
         for (int u = 0; u < n_my; ++u) {
             const int t = static_cast<int>(blockIdx.x) + u * static_cast<int>(gridDim.x);
             const int p0 = t * kTile;
-            float rx = 0.f, ry = 0.f, rz = 0.f;
-            if (gather) {
-                // relative coordinates of this thread's position (3 input channels kept on the CUDA cores)
-                const int j = __ldg(q.idx + static_cast<size_t>(b) * P + p0 + et);
-                const float *pj = q.xyz + (static_cast<size_t>(b) * q.N + j) * 3;
-                const float *pc = q.new_xyz + (static_cast<size_t>(b) * q.M + t * 2 + (et >> 6)) * 3;
-                rx = __ldg(pj) - __ldg(pc); ry = __ldg(pj + 1) - __ldg(pc + 1); rz = __ldg(pj + 2) - __ldg(pc + 2);
-            }
-            float fsum[kGnGroups] = {0.f, 0.f, 0.f, 0.f}, fsq[kGnGroups] = {0.f, 0.f, 0.f, 0.f};
+            // relative coordinates of this thread's position (3 input channels kept on the CUDA cores): loaded one tile
+            // ahead (index at the top of the previous tile, coordinates after its first layer)
+            const float rx = nrx, ry = nry, rz = nrz;
+            const int jn = (gather && u + 1 < n_my) ? __ldg(q.idx + static_cast<size_t>(b) * P + p0 + static_cast<int>(gridDim.x) * kTile + et) : 0;
             for (int l = 0; l < nl; ++l) {
                 const bool lastl = l == nl - 1;
                 const int n = q.C[l];
-                mbar_wait(&bar_acc[l], u & 1);
+                const int buf = single ? (dual ? (u & 1) : 0) : ((l == 0 && dual) ? 1 : 0);
+                mbar_wait(&bar_acc[single ? buf : l], (single && dual) ? ((u >> 1) & 1) : (u & 1));
                 tc::fence_after_sync();
+                if (warp == 0) OGC_DBG(2, u, 2 * l);
+                if (l == 0 && gather && u + 1 < n_my) load_rel(t + static_cast<int>(gridDim.x), jn);   // next tile's, in flight during this one
+                const uint32_t colACC = q.col_acc[buf];
                 const float2 *tss = l == 0 ? tab_ss0 : tab_ss1;
-                for (int c0 = 0; c0 < n; c0 += 32) {
+                bool released = false;
+                for (int c0 = eg * 32; c0 < n; c0 += 64) {
                     float v[32];
                     tc::tmem_ld32(trow + colACC + c0, v);
-                    if (lastl && c0 + 32 >= n) {            // accumulator drained: the next tile's layer 1 may start
+                    if (lastl && c0 + 64 >= n) {            // this warp has drained its share of the accumulator
                         tc::fence_before_sync();
-                        mbar_arrive(&bar_accfree);
+                        mbar_arrive(&bar_accfree[single ? buf : 0]);
+                        released = true;
                     }
                     if (l == 0 && gather) {
+                        const float4 *wq = tab_wx + (c0 >> 2) * 3;
+                        const float2 rx2 = make_float2(rx, rx), ry2 = make_float2(ry, ry), rz2 = make_float2(rz, rz);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float4 w = tab_wx[c0 + j];
-                            v[j] = fmaf(w.z, rz, fmaf(w.y, ry, fmaf(w.x, rx, v[j])));
+                        for (int j = 0; j < 8; ++j) {       // 4 channels: 3 broadcast LDS.128 + 6 packed FMAs
+                            const float4 wx = wq[3 * j], wy = wq[3 * j + 1], wz = wq[3 * j + 2];
+                            float2 a = make_float2(v[4 * j], v[4 * j + 1]), c = make_float2(v[4 * j + 2], v[4 * j + 3]);
+                            a = ffma2(make_float2(wx.x, wx.y), rx2, a); c = ffma2(make_float2(wx.z, wx.w), rx2, c);
+                            a = ffma2(make_float2(wy.x, wy.y), ry2, a); c = ffma2(make_float2(wy.z, wy.w), ry2, c);
+                            a = ffma2(make_float2(wz.x, wz.y), rz2, a); c = ffma2(make_float2(wz.z, wz.w), rz2, c);
+                            v[4 * j] = a.x; v[4 * j + 1] = a.y; v[4 * j + 2] = c.x; v[4 * j + 3] = c.y;
                         }
                     }
                     if (!lastl) {
-                        float hi[32], lo[32];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float2 s2 = tss[c0 + j];
-                            tc::tf32_split(fmaxf(fmaf(s2.x, v[j], s2.y), 0.f), hi[j], lo[j]);
+                        for (int h = 0; h < 2; ++h) {
+                            float hi[16], lo[16];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 s4 = *reinterpret_cast<const float4 *>(tss + c0 + 16 * h + 2 * j);
+                                tc::tf32_split(fmaxf(fmaf(s4.x, v[16 * h + 2 * j], s4.y), 0.f), hi[2 * j], lo[2 * j]);
+                                tc::tf32_split(fmaxf(fmaf(s4.z, v[16 * h + 2 * j + 1], s4.w), 0.f), hi[2 * j + 1], lo[2 * j + 1]);
+                            }
+                            tc::tmem_st16_nowait(trow + colA23 + c0 + 16 * h, hi);
+                            tc::tmem_st16_nowait(trow + colA23 + n + c0 + 16 * h, lo);
                         }
-                        tc::tmem_st32_nowait(trow + colA23 + c0, hi);
-                        tc::tmem_st32_nowait(trow + colA23 + n + c0, lo);
                         continue;
                     }
                     // ---- last computed layer: statistics, optional store, optional pooling ----
+                    const int blk0 = (c_off + c0) >> 3;                  // first 8-channel block of the chunk
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        float s = 0.f, sq = 0.f;
+                        const float2 one2 = make_float2(1.f, 1.f);
+                        const float2 p0 = make_float2(v[8 * i], v[8 * i + 1]), p1 = make_float2(v[8 * i + 2], v[8 * i + 3]);
+                        const float2 p2 = make_float2(v[8 * i + 4], v[8 * i + 5]), p3 = make_float2(v[8 * i + 6], v[8 * i + 7]);
+                        const float2 sa = ffma2(p1, one2, p0), sb = ffma2(p3, one2, p2);       // packed fp32 adds
+                        const float2 s2 = ffma2(sa, one2, sb);
+                        const float2 qa = ffma2(p1, p1, ffma2(p0, p0, make_float2(0.f, 0.f)));
+                        const float2 qb = ffma2(p3, p3, ffma2(p2, p2, qa));
+                        const float s = s2.x + s2.y, sq = qb.x + qb.y;
+                        const int g = static_cast<int>(gbits >> (2 * (blk0 + i))) & 3;   // warp-uniform
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) { s += v[8 * i + j]; sq = fmaf(v[8 * i + j], v[8 * i + j], sq); }
-                        const int g = (c_off + c0 + 8 * i) / gsz;
-#pragma unroll
-                        for (int gg = 0; gg < kGnGroups; ++gg)
-                            if (g == gg) { fsum[gg] += s; fsq[gg] += sq; }
+                        for (int gg = 0; gg < kGnGroups; ++gg) {
+                            fsum[gg] += g == gg ? s : 0.f;
+                            fsq[gg] += g == gg ? sq : 0.f;
+                        }
                     }
                     if (q.y_out) {
-                        float *yo = q.y_out + (static_cast<size_t>(b) * q.c_total + c_off + c0) * P + p0 + et;
+                        // 8 independent address registers: a single running pointer serialises the 32 stores on its
+                        // read-after-store scoreboard (measured: 21 % of all stall samples on this line)
+                        float *yo[4];
+                        yo[0] = q.y_out + (static_cast<size_t>(b) * q.c_total + c_off + c0) * P + p0 + et;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) yo[static_cast<size_t>(j) * P] = v[j];
-                    }
-                    if (q.ymax) {
-                        uint32_t kmx = 0, kmn = 0;
-                        int imx = 0, imn = 0;
+                        for (int j = 1; j < 4; ++j) yo[j] = yo[j - 1] + P;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const uint32_t key = f2key(v[j]);
-                            const uint32_t mx = __reduce_max_sync(OGC_FULL_MASK, key), mn = __reduce_min_sync(OGC_FULL_MASK, key);
-                            const uint32_t bmx = __ballot_sync(OGC_FULL_MASK, key == mx), bmn = __ballot_sync(OGC_FULL_MASK, key == mn);
-                            if (lane == j) { kmx = mx; kmn = mn; imx = __ffs(bmx) - 1; imn = __ffs(bmn) - 1; }
+                            *yo[j & 3] = v[j];
+                            if (j < 28) yo[j & 3] += static_cast<size_t>(4) * P;
                         }
-                        const size_t o = (static_cast<size_t>(b) * 2 * q.M + static_cast<size_t>(t) * 4 + ew) * q.c_total + c_off + c0 + lane;
-                        q.ymax[o] = key2f(kmx);
-                        q.ymin[o] = key2f(kmn);
-                        q.amax[o] = static_cast<unsigned char>(imx);
-                        q.amin[o] = static_cast<unsigned char>(imn);
+                    }
+                    if (q.ymax) {
+                        // max / min (+ first position) over this warp's 32 positions, 8 channels at a time through a
+                        // per-warp [8][33] transpose: lane = (channel, position quarter) scans 8 positions, two shuffle
+                        // rounds join the quarters.  (redux.sync per channel serialised on its uniform result register:
+                        // ~190 cycles per channel.)
+                        float *sc = pool_s + warp * (8 * 33);
+                        const int pch = lane >> 2, pq = lane & 3;
+#pragma unroll
+                        for (int g8 = 0; g8 < 4; ++g8) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) sc[j * 33 + lane] = v[8 * g8 + j];
+                            __syncwarp();
+                            float vmx = sc[pch * 33 + pq * 8], vmn = vmx;
+                            int imx = pq * 8, imn = imx;
+#pragma unroll
+                            for (int k = 1; k < 8; ++k) {
+                                const float x = sc[pch * 33 + pq * 8 + k];
+                                if (x > vmx) { vmx = x; imx = pq * 8 + k; }
+                                if (x < vmn) { vmn = x; imn = pq * 8 + k; }
+                            }
+#pragma unroll
+                            for (int o = 1; o <= 2; o <<= 1) {
+                                const float ox = __shfl_xor_sync(OGC_FULL_MASK, vmx, o), on = __shfl_xor_sync(OGC_FULL_MASK, vmn, o);
+                                const int oix = __shfl_xor_sync(OGC_FULL_MASK, imx, o), oin = __shfl_xor_sync(OGC_FULL_MASK, imn, o);
+                                if (ox > vmx || (ox == vmx && oix < imx)) { vmx = ox; imx = oix; }
+                                if (on < vmn || (on == vmn && oin < imn)) { vmn = on; imn = oin; }
+                            }
+                            if (pq == 0) {
+                                const size_t o = (static_cast<size_t>(b) * 2 * q.M + static_cast<size_t>(t) * 4 + eq) * q.c_total + c_off + c0 + 8 * g8 + pch;
+                                q.ymax[o] = vmx;
+                                q.ymin[o] = vmn;
+                                q.amax[o] = static_cast<unsigned char>(imx);
+                                q.amin[o] = static_cast<unsigned char>(imn);
+                            }
+                            __syncwarp();
+                        }
                     }
                 }
+                if (warp == 0) OGC_DBG(2, u, 2 * l + 1);
                 if (!lastl) {
                     tc::tmem_st_wait();
                     tc::fence_before_sync();
                     mbar_arrive(&bar_a[l + 1]);
+                } else if (!released) {                      // a column group without a chunk of this layer
+                    tc::fence_before_sync();
+                    mbar_arrive(&bar_accfree[single ? buf : 0]);
                 }
             }
+            if ((u & 3) == 3 || u + 1 == n_my) {
+                // fp32 partial sums (<= 4 tiles) -> warp sum -> fp64 in shared memory (fp64 adds are slow on this part,
+                // and 16 fp64 accumulator registers per thread do not fit next to the chunk at 17 warps)
 #pragma unroll
-            for (int g = 0; g < kGnGroups; ++g) { dsum[g] += static_cast<double>(fsum[g]); dsq[g] += static_cast<double>(fsq[g]); }
-        }
+                for (int g = 0; g < kGnGroups; ++g) {
+                    float s = fsum[g], sq = fsq[g];
 #pragma unroll
-        for (int g = 0; g < kGnGroups; ++g) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                dsum[g] += __shfl_xor_sync(OGC_FULL_MASK, dsum[g], o);
-                dsq[g] += __shfl_xor_sync(OGC_FULL_MASK, dsq[g], o);
+                    for (int o = 16; o > 0; o >>= 1) {
+                        s += __shfl_xor_sync(OGC_FULL_MASK, s, o);
+                        sq += __shfl_xor_sync(OGC_FULL_MASK, sq, o);
+                    }
+                    if (lane == 0) { atomicAdd(&gs[2 * g], static_cast<double>(s)); atomicAdd(&gs[2 * g + 1], static_cast<double>(sq)); }
+                    fsum[g] = fsq[g] = 0.f;
+                }
             }
-            if (lane == 0) { atomicAdd(&gs[2 * g], dsum[g]); atomicAdd(&gs[2 * g + 1], dsq[g]); }
         }
-        named_bar_sync(kEpiBar, 128);
+        named_bar_sync(kEpiBar, kEpi);
         if (tid < kGnGroups * 2 && n_my > 0) atomicAdd(q.sums + static_cast<size_t>(b) * kGnGroups * 2 + tid, gs[tid]);
     }
     tc::fence_before_sync();
@@ -381,7 +549,7 @@ static bool fwd_plan(FwdParams &q, const int *widths, int &nslice, size_t &smem)
     q.c_total = widths[nl - 1];
     q.raw_pitch = gather ? static_cast<uint32_t>(q.Cf) * 4u + 16u : kTile * 4u + 16u;
     const uint32_t raw_bytes = q.small ? 0u : (gather ? kTile * q.raw_pitch : static_cast<uint32_t>(q.K1) * q.raw_pitch);
-    const uint32_t tab_bytes = 3u * kMaxC * 8u + kMaxC * 16u;
+    const uint32_t tab_bytes = 3u * kMaxC * 8u + kMaxC * 16u + kEpiWarps * 8u * 33u * 4u;
     const size_t budget = static_cast<size_t>(kMaxSmemPerCta) - 2048;
     for (nslice = 1;; nslice *= 2) {
         if (nslice > 4 || (widths[nl - 1] / nslice) % 32 != 0) return false;
@@ -404,12 +572,17 @@ static bool fwd_plan(FwdParams &q, const int *widths, int &nslice, size_t &smem)
     q.off_tab = off;
     off += tab_bytes;
     smem = static_cast<size_t>(off) + 1024;
-    // tensor-memory columns: A1 (hi | lo), A2 / A3 (hi | lo), one accumulator
+    // tensor-memory columns: A1 (hi | lo), A2 / A3 (hi | lo), accumulator region 0 (+ region 1 when it fits)
     int cols = align_up(2 * q.K1, 32);
+    q.col_a23 = static_cast<uint32_t>(cols);
     if (nl > 1) cols += 2 * (nl > 2 ? (widths[0] > widths[1] ? widths[0] : widths[1]) : widths[0]);
-    int accw = 0;
-    for (int l = 0; l < nl; ++l) accw = q.C[l] > accw ? q.C[l] : accw;
-    return cols + accw <= 512;
+    int wa = 0;                                   // region 0: layers 2.. (chained) or the only layer
+    for (int l = nl > 1 ? 1 : 0; l < nl; ++l) wa = q.C[l] > wa ? q.C[l] : wa;
+    const int wb = q.C[0];                        // region 1: layer 1 (chained) / odd tiles (one layer per launch)
+    q.dual = cols + wa + wb <= 512;
+    q.col_acc[0] = static_cast<uint32_t>(cols);
+    q.col_acc[1] = static_cast<uint32_t>(q.dual ? cols + wa : cols);
+    return cols + (q.dual ? wa + wb : (wa > wb ? wa : wb)) <= 512;
 }
 
 static int fwd_shape(FwdParams &q, int m, int nsample, int cf, int gather, int nl, const int *widths) {
@@ -434,6 +607,17 @@ static int fwd_shape(FwdParams &q, int m, int nsample, int cf, int gather, int n
 
 // 1 when ogc_sa_chain_fwd can run `nl` chained layers of these widths in one launch (weights of all of them resident
 // in one SM's shared memory, operands + accumulator within the 512 tensor-memory columns), else 0.
+// Diagnostics: when set, the next launches record a per-tile timeline of CTA (0,0,0) (3 roles x 64 tiles x 8 events).
+static long long *g_chain_dbg = nullptr;
+static int g_chain_dbg_count = 0, g_chain_dbg_sel = -1;    // OGC_CHAIN_DBG_SEL = k: only the k-th launch records
+extern "C" int ogc_sa_chain_debug(long long *buf) {
+    g_chain_dbg = buf;
+    g_chain_dbg_count = 0;
+    const char *e = getenv("OGC_CHAIN_DBG_SEL");
+    g_chain_dbg_sel = e ? atoi(e) : -1;
+    return OGC_OK;
+}
+
 extern "C" int ogc_sa_chain_fits(int m, int nsample, int cf, int gather, int nl, const int *widths) {
     using namespace ogc::chain;
     if (nl < 1 || nl > 3 || !widths || cf <= 0) return 0;
@@ -480,6 +664,8 @@ extern "C" int ogc_sa_chain_fwd(int b, int n, int m, int nsample, int cf, int ga
     q.xyz = xyz; q.new_xyz = new_xyz; q.feat_pm = feat_pm; q.idx = idx; q.y_in = y_in; q.ss_in = ss_in;
     q.ss[0] = ss1; q.ss[1] = ss2; q.sums = sums; q.y_out = y_out;
     q.ymax = ymax_h; q.ymin = ymin_h; q.amax = amax_h; q.amin = amin_h;
+    q.dbg = (g_chain_dbg_sel < 0 || g_chain_dbg_count == g_chain_dbg_sel) ? g_chain_dbg : nullptr;
+    ++g_chain_dbg_count;
     int nslice = 0;
     size_t smem = 0;
     if (!fwd_plan(q, widths, nslice, smem)) return OGC_ERR_UNSUPPORTED;

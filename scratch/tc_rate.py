@@ -9,7 +9,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = ctypes.CDLL(os.path.join(ROOT, "tests", "csrc", "libogc_probe.so"))
-NAMES = {0: "ts 3xTF32", 1: "ss 3xTF32", 2: "ts single", 3: "ss single", 4: "ts 3x, 2 accumulators"}
+NAMES = {0: "ts 3xTF32", 1: "ss 3xTF32", 2: "ts single", 3: "ss single", 4: "ts 3x, 2 accumulators", 5: "ts 3x, unrolled", 6: "ts 3x + concurrent LDTM", 7: "ts 3x + concurrent STTM", 8: "ts 3x + commit every 4 k-steps"}
 
 
 def run(mode, n, k, reps, ctas):
@@ -26,7 +26,7 @@ def run(mode, n, k, reps, ctas):
     e.record()
     torch.cuda.synchronize()
     ms = s.elapsed_time(e)
-    per = 3 if mode in (0, 1, 4) else 1
+    per = 3 if mode in (0, 1, 4, 5, 6, 7, 8) else 1
     n_mma = reps * (k // 8) * per
     flops = 2.0 * 128 * n * 8 * n_mma * ctas
     return float(cyc.float().mean()) / n_mma, ms, flops / (ms * 1e-3) / 1e12
@@ -34,9 +34,9 @@ def run(mode, n, k, reps, ctas):
 
 def main():
     print("mode                      N    K  ctas  cycles/MMA  floor(N/2)  TFLOP/s(tf32, chip)")
-    for ctas in (1, 148):
-        for mode in (0, 1, 2, 3, 4):
-            for n in (32, 64, 128, 256):
+    for ctas in (148,):
+        for mode in (0, 8):
+            for n in (64, 128):
                 r = run(mode, n, 64, 400, ctas)
                 if r is None:
                     continue

@@ -6,6 +6,9 @@
 //   mode 2: A from tensor memory, ONE MMA per k-step
 //   mode 3: A from shared memory, ONE MMA per k-step
 //   mode 4: as mode 0, alternating between two accumulators per k-step
+//   mode 5: as mode 0 with the 8 k-steps' descriptors precomputed and the issue loop fully unrolled (K = 64 only)
+//   mode 8: as mode 0 with a tcgen05.commit (to a second mbarrier) after every 4 k-steps (cost of frequent commits)
+//   mode 6 / 7: as mode 0 while warps 1-3 stream tcgen05.ld / tcgen05.st on other tensor-memory columns (port contention)
 // scratch/tc_rate.py prints the table; the measured numbers are quoted in DESIGN.md.
 #include "../../ogc_b200/csrc/tcgen05.cuh"
 
@@ -14,8 +17,9 @@ namespace ogc {
 __global__ void __launch_bounds__(128)
 tc_rate_kernel(int mode, int N, int K, int reps, long long *__restrict__ cycles) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(8) uint64_t bar, bar2;
     __shared__ uint32_t tmem_base_s;
+    __shared__ volatile int done_flag;
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int tid = threadIdx.x, warp = tid >> 5;
     const uint32_t b_bytes = static_cast<uint32_t>(N) * K * 4, a_bytes = 128u * K * 4;
@@ -24,7 +28,9 @@ tc_rate_kernel(int mode, int N, int K, int reps, long long *__restrict__ cycles)
     if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
     if (tid == 0) {
         mbar_init(&bar, 1);
+        mbar_init(&bar2, 1);
         mbar_fence_init();
+        done_flag = 0;
     }
     // operand contents: small pseudo-random values (the data only matters for power)
     const uint32_t words = (2 * b_bytes + (ss ? 2 * a_bytes : 0)) / 4;
@@ -54,7 +60,31 @@ tc_rate_kernel(int mode, int N, int K, int reps, long long *__restrict__ cycles)
     if (tid == 0) {
         const uint32_t idesc = tc::make_idesc_tf32(128, N, 0, 0);
         const int ksteps = K / 8;
-        const bool three = mode == 0 || mode == 1 || mode == 4;
+        const bool three = mode == 0 || mode == 1 || mode == 4 || mode == 5 || mode >= 6;
+        if (mode == 5) {
+            uint64_t bh[8], bl[8];
+            uint32_t ah[8];
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                const uint32_t b_off = static_cast<uint32_t>(s >> 2) * (N * 128u) + static_cast<uint32_t>(s & 3) * 32u;
+                bh[s] = tc::make_desc_sw128(smem_u32(b_hi) + b_off, 16, 1024);
+                bl[s] = tc::make_desc_sw128(smem_u32(b_lo) + b_off, 16, 1024);
+                ah[s] = tmem_base + a_col + static_cast<uint32_t>(s * 8);
+            }
+            t0 = clock64();
+            for (int r = 0; r < reps; ++r) {
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    tc::mma_tf32_ts(tmem_base, ah[s], bh[s], idesc, (r | s) ? 1u : 0u);
+                    tc::mma_tf32_ts(tmem_base, ah[s], bl[s], idesc, 1u);
+                    tc::mma_tf32_ts(tmem_base, ah[s] + static_cast<uint32_t>(K), bh[s], idesc, 1u);
+                }
+            }
+            tc::mma_commit(&bar);
+            mbar_wait(&bar, 0);
+            t1 = clock64();
+            cycles[blockIdx.x] = t1 - t0;
+        } else {
         t0 = clock64();
         uint32_t acc = 0;
         for (int r = 0; r < reps; ++r) {
@@ -81,12 +111,29 @@ tc_rate_kernel(int mode, int N, int K, int reps, long long *__restrict__ cycles)
                     }
                 }
                 if (mode != 4 || (s & 1)) acc = 1;
+                if (mode == 8 && (s & 3) == 3) tc::mma_commit(&bar2);
             }
         }
         tc::mma_commit(&bar);
         mbar_wait(&bar, 0);
         t1 = clock64();
         cycles[blockIdx.x] = t1 - t0;
+        }
+        done_flag = 1;
+    } else if ((mode == 6 || mode == 7) && warp > 0) {
+        // background tensor-memory traffic on the scratch columns [2N + 2K .. ) of this warp's lane quadrant
+        const uint32_t scratch = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + a_col + 2u * K;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = static_cast<float>(tid + j);
+        float sink = 0.f;
+        while (!done_flag) {
+            for (int it = 0; it < 16; ++it) {
+                if (mode == 6) { float w[32]; tc::tmem_ld32(scratch, w); sink += w[it & 31]; }
+                else tc::tmem_st32(scratch, v);
+            }
+        }
+        if (sink == 12345.678f) cycles[0] = 0;
     }
     tc::fence_before_sync();
     __syncthreads();
@@ -102,6 +149,8 @@ extern "C" __attribute__((visibility("default"))) int ogc_tc_rate(int mode, int 
     if (n < 16 || n > 256 || n % 16 != 0 || k < 32 || k % 32 != 0 || reps < 1 || ctas < 1 || !cycles) return OGC_ERR_INVALID_ARG;
     const bool ss = mode == 1 || mode == 3;
     if (!ss && (mode == 4 ? 2 * n : n) + 2 * k > 512) return OGC_ERR_UNSUPPORTED;
+    if ((mode == 6 || mode == 7) && 2 * n + 2 * k + 32 > 512) return OGC_ERR_UNSUPPORTED;
+    if (mode == 5 && k != 64) return OGC_ERR_UNSUPPORTED;
     const size_t smem = static_cast<size_t>(2) * n * k * 4 + (ss ? static_cast<size_t>(2) * 128 * k * 4 : 0) + 1024;
     if (smem > static_cast<size_t>(kMaxSmemPerCta)) return OGC_ERR_UNSUPPORTED;
     cudaError_t e = cudaFuncSetAttribute(tc_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));

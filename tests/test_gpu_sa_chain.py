@@ -85,3 +85,20 @@ def test_chain_matches_composed_reference_expression(b200, N, M, Cf, widths):
     assert fro(f2.grad.transpose(1, 2), ref_df) < 2e-3
     for n, p in mlp.named_parameters():
         assert fro(p.grad, ref_grads[n]) < 2e-3, (n, fro(p.grad, ref_grads[n]))
+
+
+@pytest.mark.parametrize("N,M,Cf,widths", [(2048, 1024, 96, [64, 64, 128]), (1024, 512, 128, [128, 128, 256]),
+                                           (4096, 2048, 3, [32, 32, 64])])
+def test_chain_forward_many_tiles_per_cta(b200, N, M, Cf, widths):
+    """KITTI-SF sizes with 16 clouds: dozens of tiles per persistent CTA (pipeline wrap-around, barrier phases)."""
+    from ogc_b200 import sa_fused
+    xyz, new_xyz, feat_pm, idx, mlp, layers = _setup(N, M, Cf, widths, B=16)
+    outs = {}
+    for chain in (False, True):
+        sa_fused.USE_CHAIN = chain
+        try:
+            outs[chain] = sa_fused.fused_sa_mlp(xyz, new_xyz, feat_pm.clone().requires_grad_(True), idx, layers).detach()
+        finally:
+            sa_fused.USE_CHAIN = True
+    torch.cuda.synchronize()
+    assert float((outs[True] - outs[False]).abs().max()) <= 2e-5 * max(1.0, float(outs[False].abs().max()))
