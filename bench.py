@@ -1,26 +1,33 @@
 #!/usr/bin/env python
-"""bench.py -- the headline benchmark of BASELINE.json:
+"""bench.py -- the benchmarks of BASELINE.json, one JSON line per run.
 
-    point-clouds/sec for (segnet_kitti forward + UnsupervisedOGCLoss + backward + Adam) at 8192 points
+    python bench.py --gpus N --steps K --warmup W                      # headline: configs[1] at the reference's training
+                                                                       # settings (kittisf_unsup.yaml: 4 pairs x 4 views)
+    python bench.py --config train8|strong32|oa_icp|ogcdr_flow|ogcdr_flow4096|sapien_cpu ...
+    python bench.py --impl reference [--config ...] --gpus N --steps K --warmup W     # CPU arm (oracle port on the host cores)
 
-    python bench.py --gpus N --steps K --warmup W            # this repo (sm_100a kernels), N ranks via torchrun
-    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: reference-structure step on the host cores
+Headline metric: point-clouds/sec for (segnet_kitti forward + UnsupervisedOGCLoss + backward + Adam) at 8192 points.
+One "step" = one pass of `Trainer._train_it` (train_seg.py:47-86, restated in ogc_b200/train.py) over one batch:
+b = 4 KITTI-SF-like pairs per GPU with augmentation (t = 4 views) => 16 clouds x 8192 points per GPU per step,
+n_slot 10, all three loss terms active.  Weak scaling: per-GPU work fixed, ranks hold different seeded shards and
+exchange one NCCL all-reduce (grads + NaN counter).
 
-One "step" = one pass of the hot path over one batch: `Trainer._train_it` (train_seg.py:47-86) restated in
-ogc_b200/train.py.  Workload (configs[1] at the reference's own training settings,
-config/seg/kittisf/kittisf_unsup.yaml): b = 4 KITTI-SF-like pairs per GPU, augmentation on (t = 4 views) =>
-16 clouds x 8192 points per GPU per step, n_slot 10, all three loss terms active.  Weak scaling: per-GPU
-work is fixed; ranks hold different seeded shards and exchange one NCCL all-reduce (grads + NaN counter).
-
-Prints ONE JSON line (rank 0).  `value` = clouds/s with the batch already resident in HBM; `e2e` = the
-same through the public step API with pinned-host inputs copied in and the loss dict read back every step.
-`roofline` is for the dominant libogc_b200 kernel family of the step (CUDA events on the launching stream, side-stream
-overlap switched off for that pass; `traffic` = DRAM bytes per span from the committed ncu capture, profiles/ncu_traffic.json);
-`ops` lists every kernel family of ours (FPS and ball_query included, as BASELINE.json's metric asks).
-`cpu_baseline` (rank 0, N=1) times the CPU port (oracle kernels + the same torch step on the host cores)
-on a bounded sample (10 steps of one pair); `ref_cuda_ext` (N=1) times the reference's own CUDA extension under the
-reference's op sequence on the same GPU.  stdout carries exactly the JSON line (library banners go to stderr).
-With N > 1 the NCCL all-reduce, Adam and the log read-back follow the step graph eagerly.
+    value        clouds/s with the batch already resident in HBM (CUDA events, max over ranks)
+    e2e          the same through the public step API with pinned-host inputs copied in and the loss dict read back
+    roofline     the dominant libogc_b200 kernel family of the step: bound "tensor" (contractions: useful fp32-equivalent
+                 FLOP/s against the TF32 peak = half the measured bf16 cuBLAS peak; the 3xTF32 split issues 3x that work)
+                 or "hbm" (SURVEY 8d algorithmic bytes / time against the measured copy bandwidth); `traffic` = DRAM
+                 bytes per launch from the committed ncu capture; `step` = the whole-step HBM fraction of SURVEY 8d
+    ops          every kernel family of ours (FPS and ball_query GB/s included, as BASELINE.json's metric asks)
+    cpu_baseline the CPU port (oracle kernels + the same torch step, all host cores) on a bounded sample   } run in
+    ref_cuda_ext the UNMODIFIED reference Python over the reference's own CUDA extension on the same GPU,  } SUBPROCESSES:
+                 torch-default (TF32 convs) and strict-fp32 modes, >= 10 timed steps (oracle/ref_arm.py)    } the product
+                 -- the denominator of BASELINE.json's ">= 20x" target                                      } process maps
+                                                                                                            } libogc_b200 only
+Other configs (`--config`): train8 = configs[3] (8 pairs/GPU); strong32 = 32 clouds split over the ranks (strong
+scaling); oa_icp = configs[4] (64 clouds, icp_iter 20; the reference runs chunks of 4); ogcdr_flow[4096] = configs[2]
+(FlowStep3D b=16 iters=4 + flow loss + backward + Adam at 2048 / 4096 points); sapien_cpu = configs[0] (CPU plumbing).
+stdout carries exactly the JSON line (library banners go to stderr).
 """
 import argparse
 import json
@@ -38,14 +45,15 @@ import torch  # noqa: E402
 N_POINT = 8192
 N_SLOT = 10
 METRIC = "point-clouds/sec (8192 pts, segnet fwd+OGC-loss bwd)"
+ALG_BYTES_PER_CLOUD = 42.5e6          # perfectly fused units, fwd + loss + bwd
 
 
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d.get("hbm_gbs", 6650.0), d.get("hbm_gbs") is not None
-    return 6650.0, False
+        return {"hbm_gbs": d.get("hbm_gbs", 6650.0), "bf16_tflops": d.get("bf16_tflops", 1590.0), "measured": True}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "measured": False}
 
 
 class ClockSampler:
@@ -97,17 +105,49 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def build_trainer(device, world, variant_impl="b200"):
+def build_trainer(device, world, pairs):
     from ogc_b200.segnet import MaskFormer3D
     from ogc_b200.losses import build_ogc_loss, KITTISF_LOSS_CFG
     from ogc_b200.train import SegTrainer
     torch.manual_seed(10)                       # config/seg/kittisf/kittisf_unsup.yaml:3 random_seed
     net = MaskFormer3D(n_slot=N_SLOT, n_point=N_POINT, variant="kitti").to(device)
     crit = build_ogc_loss(KITTISF_LOSS_CFG)
-    return SegTrainer(net, crit, lr=1e-3, global_batch_size=4 * world, world_size=world)
+    return SegTrainer(net, crit, lr=1e-3, global_batch_size=pairs * world, world_size=world)
 
 
-def run_cpu_port(steps, warmup, pairs_per_step, threads):
+# ---------------------------------------------------------------------------------------------------------------------
+# subprocess legs (checkers / baselines never share the product process)
+# ---------------------------------------------------------------------------------------------------------------------
+def _run_json(cmd, timeout):
+    """Run a helper that prints one JSON line on stdout; {"unavailable": why} on any failure."""
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    except subprocess.TimeoutExpired:
+        return {"unavailable": f"timeout after {timeout}s: {' '.join(cmd[1:4])}"}
+    for ln in reversed(r.stdout.strip().splitlines()):
+        if ln.startswith("{"):
+            try:
+                return json.loads(ln)
+            except json.JSONDecodeError:
+                pass
+    return {"unavailable": f"rc={r.returncode}: {r.stderr.strip().splitlines()[-1][:200] if r.stderr.strip() else 'no output'}"}
+
+
+def ref_arm(*args, timeout=600):
+    """oracle/ref_arm.py: the UNMODIFIED reference Python over the reference's own CUDA extension, in a subprocess."""
+    return _run_json([sys.executable, os.path.join(ROOT, "oracle", "ref_arm.py"), *map(str, args)], timeout)
+
+
+def cpu_arm(config, steps, warmup, timeout=900):
+    """This file's --impl reference arm (CPU port), in a subprocess."""
+    return _run_json([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--config", config,
+                      "--steps", str(steps), "--warmup", str(warmup)], timeout)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm ("reference"): the oracle port on the host cores.  The only place besides tests/ and smoke() that executes oracle/.
+# ---------------------------------------------------------------------------------------------------------------------
+def run_cpu_seg(steps, warmup, pairs, aug, threads):
     """Reference-structure step on the host cores: the same torch step + the CPU oracle kernels
     (the reference itself has no CPU path: SURVEY.md 8c).  Returns (clouds/s, ms/step, clouds/step)."""
     from ogc_b200 import backend, data
@@ -116,67 +156,141 @@ def run_cpu_port(steps, warmup, pairs_per_step, threads):
     os.environ.setdefault("OMP_NUM_THREADS", str(threads))
     prev = backend.set_backend(OracleBackend())
     try:
-        trainer = build_trainer(torch.device("cpu"), 1)
-        batch = data.make_batch(1234, pairs_per_step, N_POINT, aug=False)
+        trainer = build_trainer(torch.device("cpu"), 1, pairs)
+        batch = data.make_batch(1234, pairs, N_POINT, aug=aug)
         for i in range(warmup):
-            trainer.train_step(2000 + i, batch, aug_transform=False)
+            trainer.train_step(100000 + i, batch, aug_transform=aug)
         t0 = time.perf_counter()
         for i in range(steps):
-            trainer.train_step(3000 + i, batch, aug_transform=False)
+            trainer.train_step(100100 + i, batch, aug_transform=aug)
         dt = (time.perf_counter() - t0) / max(steps, 1)
     finally:
         backend.set_backend(prev)
-    clouds = pairs_per_step * 2
+    clouds = pairs * (4 if aug else 2)
     return clouds / dt, dt * 1e3, clouds
 
 
-def run_ref_cuda_ext(device, steps, warmup, pairs, aug):
-    """The reference's OWN CUDA extension (oracle/_ref, built from /root/reference) under the reference's op
-    sequence (segnet.REFERENCE_FAITHFUL / losses.REFERENCE_FAITHFUL) on this GPU: the denominator of
-    BASELINE.json's ">= 20x the reference pointnet2 CUDA ext" target.  Returns None when the extension was not
-    built.  The reference Python itself cannot travel to the GPU box; the mirror reproduces its call sequence."""
-    from oracle import refext
-    if not refext.available():
-        return None
-    from ogc_b200 import backend, data, losses, segnet
-    prev = backend.set_backend(refext.RefExtBackend())
-    segnet.REFERENCE_FAITHFUL = losses.REFERENCE_FAITHFUL = True
+def run_cpu_sapien(steps, warmup, threads):
+    """configs[0]: one SAPIEN 512-point cloud through segnet_sapien (forward) on CPU over the oracle kernels."""
+    from ogc_b200 import backend
+    from ogc_b200.segnet import MaskFormer3D
+    from oracle.pointnet2_oracle import OracleBackend
+    import numpy as np
+    torch.set_num_threads(threads)
+    prev = backend.set_backend(OracleBackend())
     try:
-        trainer = build_trainer(device, 1)
-        batches = [tuple(x.to(device) for x in data.make_batch(500 + i, pairs, N_POINT, aug=aug)) for i in range(2)]
-        for i in range(warmup):
-            trainer.train_step(100000 + i, batches[i % 2], aug_transform=aug)
-        torch.cuda.synchronize()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        for i in range(steps):
-            trainer.train_step(100000 + i, batches[i % 2], aug_transform=aug)
-        e.record()
-        torch.cuda.synchronize()
-        ms = s.elapsed_time(e) / steps
+        torch.manual_seed(10)
+        net = MaskFormer3D(n_slot=8, n_point=512, variant="sapien")
+        net.eval()
+        pc = torch.from_numpy(np.random.default_rng(10).uniform(-0.5, 0.5, (1, 512, 3)).astype(np.float32))
+        with torch.no_grad():
+            for _ in range(warmup):
+                net(pc, pc)
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                mask = net(pc, pc)
+            dt = (time.perf_counter() - t0) / max(steps, 1)
     finally:
-        segnet.REFERENCE_FAITHFUL = losses.REFERENCE_FAITHFUL = False
         backend.set_backend(prev)
-        torch.cuda.empty_cache()
-    clouds = pairs * (4 if aug else 2)
-    return {"value": clouds / (ms * 1e-3), "unit": "clouds/s", "ms_per_step": ms, "steps": steps,
-            "what": "reference pointnet2 CUDA extension (unchanged .cu, sm_100a) + reference op sequence "
-                    "(cuDNN TF32 convs, diag_embed Kabsch, per-scale kNN, SVD nuclear norm) on the same B200"}
+    assert mask.shape == (1, 512, 8)
+    return 1.0 / dt, dt * 1e3
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--pairs", type=int, default=4, help="KITTI-SF pairs per GPU per step (reference batch_size)")
-    ap.add_argument("--no-aug", action="store_true")
-    ap.add_argument("--eager", action="store_true", help="one launch per kernel instead of CUDA-graph replay")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-ref-ext", action="store_true", help="skip timing the reference CUDA extension arm")
-    args = ap.parse_args()
+def run_cpu_icp(clouds, icp_iter, threads):
+    from ogc_b200 import backend, icp
+    from oracle.pointnet2_oracle import OracleBackend
+    torch.set_num_threads(threads)
+    prev = backend.set_backend(OracleBackend())
+    try:
+        pc1, pc2, flow, m1, m2 = icp_inputs(clouds, torch.device("cpu"))
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            icp.object_aware_icp(pc1, pc2, flow, m1, m2, icp_iter=icp_iter)
+        dt = time.perf_counter() - t0
+    finally:
+        backend.set_backend(prev)
+    return clouds / dt, dt * 1e3
 
+
+def run_cpu_flow(npoint, batch, iters, steps, threads):
+    from ogc_b200 import backend
+    from oracle.pointnet2_oracle import OracleBackend
+    torch.set_num_threads(threads)
+    prev = backend.set_backend(OracleBackend())
+    try:
+        step, _ = flow_step_fn(npoint, batch, iters, torch.device("cpu"))
+        step(0)
+        t0 = time.perf_counter()
+        for i in range(steps):
+            step(1 + i)
+        dt = (time.perf_counter() - t0) / max(steps, 1)
+    finally:
+        backend.set_backend(prev)
+    return batch / dt, dt * 1e3
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# workloads shared by the arms
+# ---------------------------------------------------------------------------------------------------------------------
+def icp_inputs(B, device, N=N_POINT, K=N_SLOT):
+    """KITTI-SF-like pairs + soft masks shaped like segnet outputs (same generator as oracle/ref_arm.py:run_oa_icp)."""
+    from ogc_b200 import data
+    batch = data.make_batch(900, B, N, aug=False)
+    pcs, segms, flows = batch[0].to(device), batch[1].to(device), batch[2].to(device)
+    torch.manual_seed(3)
+
+    def soft(seg):
+        onehot = torch.nn.functional.one_hot((seg.long() % K), K).float()
+        return torch.softmax(onehot * 4.0 + 0.3 * torch.randn_like(onehot), -1)
+    m1, m2 = soft(segms[:, 0]), soft(segms[:, 1])
+    return pcs[:, 0].contiguous(), pcs[:, 1].contiguous(), flows[:, 0].contiguous(), m1.contiguous(), m2.contiguous()
+
+
+def flow_step_fn(npoint, batch, iters, device):
+    """FlowStep3D forward (iters) + unsupervised flow loss + backward + Adam on OGC-DR-shaped synthetic pairs
+    (train_flow.py:59-92 with config/flow/ogcdr/ogcdr_unsup.yaml; generator shared with oracle/ref_arm.py)."""
+    import importlib.util
+    from ogc_b200.flownet import FlowStep3D, build_flow_loss, OGCDR_FLOW_LOSS_CFG
+    spec = importlib.util.spec_from_file_location("ogc_ref_arm_gen", os.path.join(ROOT, "oracle", "ref_arm.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)                       # only its pure-numpy batch generator is used here
+    torch.manual_seed(10)
+    net = FlowStep3D(npoint=npoint, use_instance_norm=False, loc_flow_nn=8, loc_flow_rad=0.05).to(device)
+    crit = build_flow_loss(dict(OGCDR_FLOW_LOSS_CFG, iters_w=[0.5] + [0.3] * (iters - 1)))
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    batches = [gen.flow_batch(31 + i, batch, npoint) for i in range(2)]
+    if device.type == "cuda":
+        batches = [tuple(x.pin_memory() for x in b) for b in batches]
+    net.train()
+
+    def step(i):
+        pcs = batches[i % 2][0].to(device, non_blocking=True)
+        pc1, pc2 = pcs[:, 0].contiguous(), pcs[:, 1].contiguous()
+        opt.zero_grad()
+        preds = net(pc1, pc2, pc1, pc2, iters=iters)
+        loss, d = crit(pc1, pc2, preds)
+        loss.backward()
+        opt.step()
+        return d
+    h2d = batches[0][0].numel() * 4
+    return step, h2d
+
+
+def time_cuda(fn, steps, warmup):
+    for i in range(warmup):
+        fn(i)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    out = None
+    for i in range(steps):
+        out = fn(warmup + i)
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / steps, out
+
+
+def emit_factory():
     # stdout carries exactly ONE line, the JSON: everything else any library prints there (NCCL's version banner ...)
     # is redirected to stderr at the file-descriptor level
     real_stdout = os.dup(1)
@@ -185,6 +299,27 @@ def main():
     def emit(obj):
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+    return emit
+
+
+SEG_CONFIGS = {"kittisf": 4, "train8": 8, "strong32": None}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="kittisf",
+                    choices=["kittisf", "train8", "strong32", "oa_icp", "ogcdr_flow", "ogcdr_flow4096", "sapien_cpu"])
+    ap.add_argument("--pairs", type=int, default=None, help="KITTI-SF pairs per GPU per step (default: the config's)")
+    ap.add_argument("--no-aug", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="one launch per kernel instead of CUDA-graph replay")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-ext", action="store_true", help="skip timing the reference CUDA extension arm")
+    args = ap.parse_args()
+    emit = emit_factory()
 
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -192,23 +327,57 @@ def main():
     aug = not args.no_aug
     t_views = 4 if aug else 2
     cores = os.cpu_count() or 1
-    workload = (f"kittisf_unsup step: {args.pairs} pairs/GPU x {t_views} views = {args.pairs * t_views} clouds/GPU/step, "
-                f"{N_POINT} pts, n_slot {N_SLOT}, segnet_kitti + OGC loss (dynamic+smooth+invariance) + bwd + Adam")
+    cfg = args.config
+    if cfg in SEG_CONFIGS:
+        pairs = args.pairs or SEG_CONFIGS[cfg] or max(1, 8 // world)       # strong32: 32 clouds over the ranks
+    else:
+        pairs = 0
+    seg_workload = (f"kittisf_unsup step: {pairs} pairs/GPU x {t_views} views = {pairs * t_views} clouds/GPU/step, "
+                    f"{N_POINT} pts, n_slot {N_SLOT}, segnet_kitti + OGC loss (dynamic+smooth+invariance) + bwd + Adam")
 
     # ------------------------------------------------------------------ CPU arm ("reference")
     if args.impl == "reference":
         if rank != 0:
             return
-        value, ms, clouds = run_cpu_port(args.steps, min(args.warmup, 1), 1, cores)
-        line = {"metric": METRIC, "value": value, "unit": "clouds/s", "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-                "config": {"workload": workload, "sample": "1 pair (2 clouds), no augmentation, per step"},
-                "cpu_baseline": {"value": value, "unit": "clouds/s", "cores": cores, "kind": "port",
-                                 "sample": f"{args.steps} steps x 1 pair (2 clouds x {N_POINT} pts), fwd+loss+bwd+Adam"},
-                "e2e": {"value": value, "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
+        w = min(args.warmup, 1)
+        base = {"n_gpus": args.gpus, "steps": args.steps, "warmup": w, "higher_is_better": True, "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "impl": "reference", "gpu_launches": 0}
+        if cfg in SEG_CONFIGS:
+            value, ms, clouds = run_cpu_seg(args.steps, w, pairs, aug, cores)
+            line = dict(base, metric=METRIC, value=value, unit="clouds/s", ms_per_step=ms,
+                        scaling="strong" if cfg == "strong32" else "weak",
+                        config={"workload": seg_workload, "sample": f"the same {clouds}-cloud step, {args.steps} timed steps"},
+                        cpu_baseline={"value": value, "unit": "clouds/s", "cores": cores, "kind": "port", "ms_per_step": ms,
+                                      "sample": f"{args.steps} steps (+{w} warm-up) of the full {clouds}-cloud step: oracle "
+                                                "kernels + the same torch step on the host cores"})
+        elif cfg == "sapien_cpu":
+            value, ms = run_cpu_sapien(args.steps, w, cores)
+            line = dict(base, metric="point-clouds/sec (512 pts, segnet_sapien forward, CPU plumbing)", value=value,
+                        unit="clouds/s", ms_per_step=ms, scaling="weak",
+                        config={"workload": "configs[0]: one SAPIEN 512-pt cloud, segnet_sapien forward on CPU over the oracle kernels"},
+                        cpu_baseline={"value": value, "unit": "clouds/s", "cores": cores, "kind": "port", "sample": f"{args.steps} forwards"})
+        elif cfg == "oa_icp":
+            value, ms = run_cpu_icp(4, 2, cores)
+            line = dict(base, metric="point-clouds/sec (8192 pts, object-aware ICP)", value=value * 2 / 20, unit="clouds/s",
+                        ms_per_step=ms, scaling="weak",
+                        config={"workload": "configs[4]: object_aware_icp, 8192 pts, n_slot 10",
+                                "sample": "4 clouds x 2 ICP iterations on the host cores, scaled to icp_iter 20 (cost is linear in iterations)"},
+                        cpu_baseline={"value": value * 2 / 20, "unit": "clouds/s", "cores": cores, "kind": "port",
+                                      "sample": "4 clouds x 2 iterations, scaled to 20 iterations"})
+        else:
+            npoint = 4096 if cfg == "ogcdr_flow4096" else 2048
+            value, ms = run_cpu_flow(npoint, 2, 4, max(1, min(args.steps, 2)), cores)
+            line = dict(base, metric=f"pairs/sec ({npoint} pts, FlowStep3D iters 4 fwd + flow loss bwd + Adam)", value=value,
+                        unit="pairs/s", ms_per_step=ms, scaling="weak",
+                        config={"workload": f"configs[2]: flownet_ogcdr npoint {npoint} iters 4", "sample": "batch 2 (of 16) per step"},
+                        cpu_baseline={"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": "batch 2 per step"})
+        line["e2e"] = {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
         emit(line)
+        return
+
+    if cfg == "sapien_cpu":       # configs[0] is CPU plumbing by definition: it only exists as the reference arm
+        if rank == 0:
+            emit(dict(cpu_arm("sapien_cpu", args.steps, args.warmup), note="configs[0] is a CPU-only plumbing case"))
         return
 
     # ------------------------------------------------------------------ B200 arm
@@ -221,14 +390,86 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     from ogc_b200 import backend, data
     be = backend.get_backend()
-    trainer = build_trainer(device, world)
+    peaks = measured_peaks()
+    peak_src = "MEASURED_PEAKS.json (measured)" if peaks["measured"] else "fallback 6650 GB/s / 1590 TFLOP/s"
 
+    if cfg in ("oa_icp", "ogcdr_flow", "ogcdr_flow4096"):
+        if rank != 0:                     # replicas only (no exchange step): one rank measures
+            if world > 1:
+                dist.destroy_process_group()
+            return
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        if cfg == "oa_icp":
+            from ogc_b200 import icp
+            B, IT = 64, 20
+            host = [t.pin_memory() for t in icp_inputs(B, torch.device("cpu"))]
+            dev_in = [t.to(device) for t in host]
+            l0 = be.launches
+            ms, _ = time_cuda(lambda i: icp.object_aware_icp(*dev_in, icp_iter=IT), args.steps, max(args.warmup, 3))
+            launches = (be.launches - l0) / (args.steps + max(args.warmup, 3))
+            out_host = torch.empty(B, N_POINT, 3).pin_memory()
+
+            def e2e_fn(i):
+                x = [t.to(device, non_blocking=True) for t in host]
+                out_host.copy_(icp.object_aware_icp(*x, icp_iter=IT), non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+            ms_e2e, _ = time_cuda(e2e_fn, args.steps, 1)
+            pair_evals = B * N_POINT * N_POINT * IT
+            line = {"metric": "point-clouds/sec (8192 pts, object-aware ICP, icp_iter 20)", "value": B / (ms * 1e-3),
+                    "unit": "clouds/s", "ms_per_step": ms,
+                    "config": {"workload": f"configs[4]: oa_icp.object_aware_icp, {B} clouds x {N_POINT} pts, n_slot {N_SLOT}, icp_iter {IT}",
+                               "parallelism": "replicas only", "l2": "inputs 25 MB < L2; the kernel is ALU-bound (N^2 pair evaluations), not HBM-bound"},
+                    "e2e": {"value": B / (ms_e2e * 1e-3), "unit": "clouds/s", "ms_per_step": ms_e2e,
+                            "h2d_bytes_per_step": sum(t.numel() * 4 for t in host), "d2h_bytes_per_step": out_host.numel() * 4},
+                    "roofline": {"kernel": "icp_correspond", "bound": "alu", "achieved": pair_evals / (ms * 1e-3) / 1e12,
+                                 "unit": "T pair-evaluations/s", "peak": None, "frac": None, "traffic": None,
+                                 "note": "streaming softmax over pc2 tiles in shared memory: ~14 fp32 ops + 1 ex2 per pair; "
+                                         "algorithmic HBM bytes B*(N(36+4K)+N(12+4K)) = 67 MB per call are negligible"}}
+            if not args.no_ref_ext:
+                ref = ref_arm("oa_icp", "--clouds", B, "--icp-iter", IT, "--chunk", 4, "--steps", 2, "--warmup", 1, timeout=900)
+                if "value" in ref:
+                    ref["speedup_e2e"] = line["e2e"]["value"] / ref["value"]
+                line["ref_cuda_ext"] = ref
+        else:
+            npoint = 4096 if cfg == "ogcdr_flow4096" else 2048
+            batch, iters = 16, 4
+            step, h2d = flow_step_fn(npoint, batch, iters, device)
+            l0 = be.launches
+            ms, last = time_cuda(step, args.steps, max(args.warmup, 3))
+            launches = (be.launches - l0) / (args.steps + max(args.warmup, 3))
+            line = {"metric": f"pairs/sec ({npoint} pts, FlowStep3D iters 4 fwd + flow loss bwd + Adam)", "value": batch / (ms * 1e-3),
+                    "unit": "pairs/s", "ms_per_step": ms,
+                    "config": {"workload": f"configs[2]: flownet_ogcdr.FlowStep3D npoint {npoint}, batch {batch}, iters {iters} + "
+                                           "UnsupervisedFlowStep3DLoss + backward + Adam (train_flow.py:59-92)",
+                               "parallelism": "replicas only (BatchNorm statistics are replica-local)",
+                               "l2": "launch-bound: ~25 FPS + ~30 kNN calls per forward on <= 4096 points"},
+                    "e2e": {"value": batch / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms, "h2d_bytes_per_step": h2d,
+                            "d2h_bytes_per_step": 4 * len(last)},
+                    "roofline": None, "loss": last}
+            if not args.no_ref_ext:
+                ref = ref_arm("flow", "--npoint", npoint, "--batch", batch, "--iters", iters, "--steps", 10, "--warmup", 3)
+                if "value" in ref:
+                    ref["speedup_e2e"] = line["e2e"]["value"] / ref["value"]
+                line["ref_cuda_ext"] = ref
+        line.update({"n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "higher_is_better": True,
+                     "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                     "gpu_launches": launches, "clocks": sampler.stop()})
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_arm(cfg, 2, 1).get("cpu_baseline", {"unavailable": "cpu arm failed"})
+        emit(line)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- segnet training step (kittisf / train8 / strong32) ----
+    trainer = build_trainer(device, world, pairs)
     n_batches = 4
-    batches = [data.make_batch(1000 * rank + i, args.pairs, N_POINT, aug=aug, fps_fn=be.fps, device=device)
+    batches = [data.make_batch(1000 * rank + i, pairs, N_POINT, aug=aug, fps_fn=be.fps, device=device)
                for i in range(n_batches)]
     resident = [tuple(x.to(device) for x in b) for b in batches]
     h2d = sum(x.numel() * x.element_size() for x in (batches[0][0], batches[0][2]))
-    clouds_per_step = args.pairs * t_views * world
+    clouds_per_step = pairs * t_views * world
     it0 = 100000        # past every start_step: all loss terms weighted in
 
     def barrier():
@@ -282,32 +523,49 @@ def main():
             dist.destroy_process_group()
         return
 
-    peak, measured = measured_peaks()
+    hbm_peak, tf32_peak = peaks["hbm_gbs"], peaks["bf16_tflops"] / 2.0
     op_rows = {}
     for name, d in ops.items():
         per_launch_ms = d["ms"] / d["calls"]
+        row = {"calls_per_step": d["calls"] / 2, "ms_per_step": d["ms"] / 2, "avg_ms": per_launch_ms}
+        if d.get("flops"):
+            tf = d["flops"] / d["calls"] / (per_launch_ms * 1e-3) / 1e12
+            row.update({"bound": "tensor", "useful_tflops": tf, "frac_of_tf32_peak": tf / tf32_peak,
+                        "frac_of_tf32_peak_3xtf32_work": 3 * tf / tf32_peak})
         gbs = d["bytes"] / d["calls"] / (per_launch_ms * 1e-3) / 1e9
-        op_rows[name] = {"calls_per_step": d["calls"] / 2, "ms_per_step": d["ms"] / 2, "avg_ms": per_launch_ms,
-                         "alg_gbs": gbs, "frac_of_hbm_peak": gbs / peak}
+        row.update({"alg_gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak})
+        op_rows[name] = row
     top = max(op_rows, key=lambda k: op_rows[k]["ms_per_step"]) if op_rows else None
     roofline = None
     if top:
-        # DRAM bytes per launch of that kernel family from the committed `ncu --set full` capture (profiles/)
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(top, {}).get("dram_bytes_per_launch")
-        roofline = {"kernel": top, "bound": "hbm", "achieved": op_rows[top]["alg_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": op_rows[top]["alg_gbs"] / peak, "traffic": traffic,
-                    "alg_bytes_per_launch": ops[top]["bytes"] / ops[top]["calls"],
-                    "peak_source": "MEASURED_PEAKS.json (measured)" if measured else "fallback 6650 GB/s",
-                    "share_of_step": op_rows[top]["ms_per_step"] / ms_step,
-                    "note": "algorithmic bytes per launch / CUDA-event duration; see DESIGN.md for the byte formulas"}
+        r = op_rows[top]
+        alg = ops[top]["bytes"] / ops[top]["calls"]
+        if r.get("bound") == "tensor":
+            roofline = {"kernel": top, "bound": "tensor", "achieved": r["useful_tflops"], "peak": tf32_peak, "unit": "TFLOP/s",
+                        "frac": r["useful_tflops"] / tf32_peak, "tensor_work_frac_3xtf32": 3 * r["useful_tflops"] / tf32_peak,
+                        "peak_how": "TF32 dense = half the measured bf16 cuBLAS burst peak; " + peak_src,
+                        "note": "useful fp32-equivalent FLOPs (2*Cin*Cout per position) per launch / CUDA-event duration; the "
+                                "3xTF32 split issues three times that tensor work"}
+        else:
+            roofline = {"kernel": top, "bound": "hbm", "achieved": r["alg_gbs"], "peak": hbm_peak, "unit": "GB/s",
+                        "frac": r["alg_gbs"] / hbm_peak, "peak_how": peak_src,
+                        "note": "algorithmic bytes per launch / CUDA-event duration (DESIGN.md byte formulas)"}
+        roofline.update({"traffic": traffic, "alg_bytes_per_launch": alg,
+                         "waste_ratio": (traffic / alg) if traffic and alg else None,
+                         "share_of_step": r["ms_per_step"] / ms_step})
+        value = clouds_per_step / (ms_step * 1e-3)
+        roofline["step"] = {"alg_bytes_per_cloud": ALG_BYTES_PER_CLOUD, "bound": "hbm",
+                            "frac": value / world * ALG_BYTES_PER_CLOUD / (hbm_peak * 1e9),
+                            "note": "whole step against SURVEY 8d's perfectly-fused 42.5 MB per cloud"}
 
     line = {"metric": METRIC, "value": clouds_per_step / (ms_step * 1e-3), "unit": "clouds/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "parallelism": f"dp{world}",
+            "scaling": "strong" if cfg == "strong32" else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": seg_workload, "name": cfg, "parallelism": f"dp{world}",
                        "launch": "eager" if args.eager else "one CUDA graph per step",
                        "l2": "per-step working set (GBs of activations) >> 126 MB L2; inputs cycle over 4 distinct batches"},
             "e2e": {"value": clouds_per_step / (ms_e2e * 1e-3), "unit": "clouds/s", "ms_per_step": ms_e2e,
@@ -315,20 +573,27 @@ def main():
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "ops": op_rows,
             "loss": last_dict}
 
-    if world == 1 and not args.no_ref_ext:
-        ref = run_ref_cuda_ext(device, 2, 1, args.pairs, aug)
-        if ref is not None:
-            ref["speedup_e2e"] = line["e2e"]["value"] / ref["value"]
-            line["ref_cuda_ext"] = ref
-    if world == 1 and not args.no_cpu_baseline:
-        cpu_steps = 10                      # ~10-15 s of CPU work on the box's host cores
-        v, ms, clouds = run_cpu_port(cpu_steps, 1, 1, cores)
-        line["cpu_baseline"] = {"value": v, "unit": "clouds/s", "cores": cores, "kind": "port", "ms_per_step": ms,
-                                "sample": f"{cpu_steps} steps (+1 warm-up) x 1 pair ({clouds} clouds x {N_POINT} pts, no aug): "
-                                          "oracle kernels + the same torch step on the host cores"}
-    emit(line)
     if world > 1:
         dist.destroy_process_group()
+    # free this process's GPU memory before the subprocess legs (the reference arm needs ~19 GB)
+    del trainer, resident, batches
+    torch.cuda.empty_cache()
+    if world == 1 and not args.no_ref_ext:
+        refs = {}
+        for mode, flag in (("tf32_default", []), ("strict_fp32", ["--fp32"])):
+            refs[mode] = ref_arm("kittisf", "--steps", 10, "--warmup", 3, "--pairs", pairs, *(["--no-aug"] if not aug else []), *flag)
+        main_ref = refs["tf32_default"]
+        ref = dict(main_ref)
+        if "value" in ref:
+            ref["speedup_e2e"] = line["e2e"]["value"] / ref["value"]
+        if "value" in refs["strict_fp32"]:
+            ref["strict_fp32"] = {k: refs["strict_fp32"][k] for k in ("value", "ms_per_step", "steps", "precision")}
+            ref["speedup_e2e_vs_strict_fp32"] = line["e2e"]["value"] / refs["strict_fp32"]["value"]
+        line["ref_cuda_ext"] = ref
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_arm(cfg, 2, 1)                    # 2 steps (+1 warm-up) of the SAME 16-cloud step: ~25 s of CPU work
+        line["cpu_baseline"] = cpu.get("cpu_baseline", cpu)
+    emit(line)
 
 
 if __name__ == "__main__":

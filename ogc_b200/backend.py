@@ -50,10 +50,10 @@ class OpTimer:
     def __init__(self):
         self.enabled = False
         self.detail = False   # per-shape span names (profiling scripts)
-        self.records = []  # (name, start_event, end_event, algorithmic_bytes)
+        self.records = []  # (name, start_event, end_event, algorithmic_bytes, useful_flops)
 
     @contextmanager
-    def span(self, name, nbytes):
+    def span(self, name, nbytes, flops=0):
         if not self.enabled:
             yield
             return
@@ -62,16 +62,18 @@ class OpTimer:
         s.record()
         yield
         e.record()
-        self.records.append((name, s, e, nbytes))
+        self.records.append((name, s, e, nbytes, flops))
 
     def summary(self):
-        """{name: {"calls", "ms", "bytes"}} -- call after torch.cuda.synchronize()."""
+        """{name: {"calls", "ms", "bytes", "flops"}} -- call after torch.cuda.synchronize().  `flops` = useful
+        fp32-equivalent FLOPs of a contraction kernel (0 for data-movement kernels)."""
         out = {}
-        for name, s, e, nb in self.records:
-            d = out.setdefault(name, {"calls": 0, "ms": 0.0, "bytes": 0})
+        for name, s, e, nb, fl in self.records:
+            d = out.setdefault(name, {"calls": 0, "ms": 0.0, "bytes": 0, "flops": 0})
             d["calls"] += 1
             d["ms"] += s.elapsed_time(e)
             d["bytes"] += nb
+            d["flops"] += fl
         return out
 
     def reset(self):

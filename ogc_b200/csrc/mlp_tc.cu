@@ -245,7 +245,10 @@ mlp_fwd_tc_kernel(MlpTcParams q) {
         }
     } else if (warp == kTcMmaWarp) {
         // ================================ MMA issuer ================================
-        if (lane == 0) {
+        // warp-uniform: all lanes run the loop, one elected lane issues each MMA / commit.  (Inside `if (lane == 0)`
+        // every operand went through vector registers + R2UR, ~12 dependent instructions per MMA: THAT, not the tensor
+        // pipe, was the ~140 cycles per instruction seen in the round-1 source-level profile.)
+        {
             const uint32_t idesc = tc::make_idesc_tf32(kTcM, kTcNT, 0, 0), idesc2 = tc::make_idesc_tf32(kTcM, 2 * kTcNT, 0, 0);
             for (int u = 0; u < n_my; ++u) {
                 const int ob = u % n_op, tb = u & 1;
@@ -253,18 +256,18 @@ mlp_fwd_tc_kernel(MlpTcParams q) {
                 mbar_wait(&bar_tempty[tb], ((u >> 1) & 1) ^ 1);
                 tc::fence_after_sync();
                 const uint32_t d = tmem_base + static_cast<uint32_t>(tb * kTcAccCols);
-                const uint32_t bh0 = smem_u32(op_hi(ob));
-                uint32_t acc = 0;
-                for (int s = 0; s < KB * 4; ++s) {
-                    const uint32_t bo = static_cast<uint32_t>(s >> 2) * (2u * kTcNT * 128u) + static_cast<uint32_t>(s & 3) * 32u;
-                    const uint64_t bd = tc::make_desc_sw128(bh0 + bo, 16, 1024);     // rows 0-63 hi, 64-127 lo
-                    const uint32_t wh = tmem_base + kTcWCol + static_cast<uint32_t>(s * 8), wl = wh + Kp;
-                    tc::mma_tf32_ts(d, wh, bd, idesc2, acc);     // cols [0,64) (+)= W_hi a_hi, [64,128) (+)= W_hi a_lo
-                    tc::mma_tf32_ts(d, wl, bd, idesc, 1);        // cols [0,64) += W_lo a_hi
-                    acc = 1;
+                const uint64_t bd0 = tc::make_desc_sw128(smem_u32(op_hi(ob)), 16, 1024);     // rows 0-63 hi, 64-127 lo
+                for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+                    for (int s4 = 0; s4 < 4; ++s4) {
+                        const uint64_t bd = bd0 + (static_cast<uint32_t>(kb) * ((2u * kTcNT * 128u) >> 4) + static_cast<uint32_t>(s4) * 2u);
+                        const uint32_t wh = tmem_base + kTcWCol + static_cast<uint32_t>((kb * 4 + s4) * 8), wl = wh + Kp;
+                        tc::mma_tf32_ts_elect(d, wh, bd, idesc2, (kb | s4) ? 1u : 0u);   // cols [0,64) (+)= W_hi a_hi, [64,128) (+)= W_hi a_lo
+                        tc::mma_tf32_ts_elect(d, wl, bd, idesc, 1);                      // cols [0,64) += W_lo a_hi
+                    }
                 }
-                tc::mma_commit(&bar_empty[ob]);    // operand buffer may be overwritten
-                tc::mma_commit(&bar_tfull[tb]);    // accumulator ready
+                tc::mma_commit_elect(&bar_empty[ob]);    // operand buffer may be overwritten
+                tc::mma_commit_elect(&bar_tfull[tb]);    // accumulator ready
             }
         }
     } else {

@@ -200,7 +200,8 @@ mlp_dx_tc_kernel(MlpDxTcParams q) {
             mbar_arrive(&bar_full[ob]);
         }
     } else if (warp == kTbMmaWarp) {
-        if (lane == 0) {
+        // warp-uniform issue (see mlp_tc.cu): all lanes run the loop, one elected lane issues
+        {
             const uint32_t idesc = tc::make_idesc_tf32(kTbM, kTbNT, 0, 0);
             for (int u = 0; u < n_my; ++u) {
                 const int ob = u % n_op, tb = u & 1;
@@ -208,20 +209,20 @@ mlp_dx_tc_kernel(MlpDxTcParams q) {
                 mbar_wait(&bar_tempty[tb], ((u >> 1) & 1) ^ 1);
                 tc::fence_after_sync();
                 const uint32_t d = tmem_base + static_cast<uint32_t>(tb * kTbNT);
-                const uint32_t bh0 = smem_u32(op_hi(ob)), bl0 = bh0 + a_bytes;
-                uint32_t acc = 0;
-                for (int s = 0; s < KB * 4; ++s) {
-                    const uint32_t bo = static_cast<uint32_t>(s >> 2) * (kTbNT * 128u) + static_cast<uint32_t>(s & 3) * 32u;
-                    const uint64_t bhd = tc::make_desc_sw128(bh0 + bo, 16, 1024);
-                    const uint64_t bld = tc::make_desc_sw128(bl0 + bo, 16, 1024);
-                    const uint32_t wh = tmem_base + kTbWCol + static_cast<uint32_t>(s * 8), wl = wh + Kp;
-                    tc::mma_tf32_ts(d, wh, bhd, idesc, acc);
-                    tc::mma_tf32_ts(d, wh, bld, idesc, 1);
-                    tc::mma_tf32_ts(d, wl, bhd, idesc, 1);
-                    acc = 1;
+                const uint64_t bh0 = tc::make_desc_sw128(smem_u32(op_hi(ob)), 16, 1024);
+                const uint64_t bl0 = bh0 + (a_bytes >> 4);
+                for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+                    for (int s4 = 0; s4 < 4; ++s4) {
+                        const uint32_t off16 = static_cast<uint32_t>(kb) * ((kTbNT * 128u) >> 4) + static_cast<uint32_t>(s4) * 2u;
+                        const uint32_t wh = tmem_base + kTbWCol + static_cast<uint32_t>((kb * 4 + s4) * 8), wl = wh + Kp;
+                        tc::mma_tf32_ts_elect(d, wh, bh0 + off16, idesc, (kb | s4) ? 1u : 0u);
+                        tc::mma_tf32_ts_elect(d, wh, bl0 + off16, idesc, 1);
+                        tc::mma_tf32_ts_elect(d, wl, bh0 + off16, idesc, 1);
+                    }
                 }
-                tc::mma_commit(&bar_empty[ob]);
-                tc::mma_commit(&bar_tfull[tb]);
+                tc::mma_commit_elect(&bar_empty[ob]);
+                tc::mma_commit_elect(&bar_tfull[tb]);
             }
         }
     } else {
@@ -592,26 +593,26 @@ mlp_dw_tc_kernel(MlpDwTcParams q) {
             sg = sgn;
         }
     } else if (warp == kTbMmaWarp) {
-        if (lane == 0) {
+        {
             const uint32_t idesc = tc::make_idesc_tf32(kTbM, n_mma, 0, 0);
             uint32_t acc = 0;
             for (int u = 0; u < n_my; ++u) {
                 const int ob = u & 1;
                 mbar_wait(&bar_full[ob], (u >> 1) & 1);
                 tc::fence_after_sync();
-                const uint32_t ah0 = smem_u32(a_hi(ob)), al0 = ah0 + a_bytes;
+                const uint64_t ahd0 = tc::make_desc_sw128(smem_u32(a_hi(ob)), 16, 1024);
+                const uint64_t ald0 = ahd0 + (a_bytes >> 4);
                 const uint32_t dh0 = tmem_base + kDwAccCols + ob * 64, dl0 = dh0 + 32;
+#pragma unroll
                 for (int s = 0; s < kDwTile / 8; ++s) {     // 32 positions = 4 K-steps: 32 B of every a row, 8 dY columns
-                    const uint64_t ahd = tc::make_desc_sw128(ah0 + s * 32, 16, 1024);
-                    const uint64_t ald = tc::make_desc_sw128(al0 + s * 32, 16, 1024);
-                    tc::mma_tf32_ts(tmem_base, dh0 + s * 8, ahd, idesc, acc);
-                    tc::mma_tf32_ts(tmem_base, dh0 + s * 8, ald, idesc, 1);
-                    tc::mma_tf32_ts(tmem_base, dl0 + s * 8, ahd, idesc, 1);
+                    tc::mma_tf32_ts_elect(tmem_base, dh0 + s * 8, ahd0 + static_cast<uint32_t>(s * 2), idesc, acc);
+                    tc::mma_tf32_ts_elect(tmem_base, dh0 + s * 8, ald0 + static_cast<uint32_t>(s * 2), idesc, 1);
+                    tc::mma_tf32_ts_elect(tmem_base, dl0 + s * 8, ahd0 + static_cast<uint32_t>(s * 2), idesc, 1);
                     acc = 1;
                 }
-                tc::mma_commit(&bar_empty[ob]);
+                tc::mma_commit_elect(&bar_empty[ob]);
             }
-            tc::mma_commit(&bar_done);
+            tc::mma_commit_elect(&bar_done);
         }
     } else {
         // epilogue: wait for every MMA of this CTA, then lane = output channel adds its row of dW

@@ -48,7 +48,9 @@ def _tc_dx_ok(S, cout, rows, scatter):
 
 
 STORE_Y = True      # stage 1: keep the pre-norm tensors for the per-layer backward kernels
-USE_CHAIN = True    # round-2 kernels (csrc/sa_chain_*.cu): positions on the MMA's M axis, layers chained through TMEM
+USE_CHAIN = False   # round-2 kernels (csrc/sa_chain_*.cu): positions on the MMA's M axis, layers chained through TMEM.
+                    # Correct (tests/test_gpu_sa_chain.py) but not yet faster than the per-layer kernels at KITTI-SF sizes
+                    # (profiles/README.md, round 2): kept behind this switch
 
 
 def _chain_plan(M, S, Cf, widths):
@@ -107,7 +109,9 @@ class _FusedSAMLP(Function):
                 sums = torch.zeros(B, 4, 2, dtype=torch.float64, device=dev)
                 pool = (_p(hx), _p(hn), _p(ax), _p(an)) if last else (None, None, None, None)
                 with TIMER.span(f"sa_chain_fwd[{plan}:{l + 1}/{L}>{widths[l]}]" if TIMER.detail else "sa_chain_fwd",
-                                B * (12 * N + 4 * N * Cf + 4 * P)):
+                                B * (12 * N + 4 * N * Cf + 4 * P),
+                                2 * B * P * sum(a * c for a, c in zip([Cf + 3] + widths[:l], widths[:l + 1]))
+                                if plan == "full" else 2 * B * P * ((Cf + 3) if l == 0 else widths[l - 1]) * widths[l]):
                     if plan == "full":
                         arr = (ctypes.c_int * 3)(*(widths[:l + 1] + [0, 0])[:3])
                         _lib.check(lib.ogc_sa_chain_fwd(
@@ -162,7 +166,7 @@ class _FusedSAMLP(Function):
             use_nw = l > 0 and _narrow_ok(S, cin, cout)
             use_tc = not use_nw and _tc_ok(S, cin, cout, l == 0)
             tag = "sa_mlp_fwd_nw" if use_nw else "sa_mlp_fwd_tc" if use_tc else "sa_mlp_fwd"
-            with TIMER.span(f"{tag}[{cin}>{cout}]" if TIMER.detail else tag, flops_bytes):
+            with TIMER.span(f"{tag}[{cin}>{cout}]" if TIMER.detail else tag, flops_bytes, 2 * B * P * cin * cout):
                 if use_nw:
                     w2d = W.detach().reshape(cout, cin).contiguous()
                     _lib.check(lib.ogc_sa_mlp_narrow_fwd(
@@ -240,12 +244,12 @@ class _FusedSAMLP(Function):
             dw_tc = not dw_nw and _tc_dw_ok(S, cin, cout)
             dw_fn, dw_tag = (lib.ogc_sa_mlp_layer_dw_tc, "sa_mlp_dw_tc") if dw_tc else (lib.ogc_sa_mlp_layer_dw, "sa_mlp_dw")
             if dw_nw:
-                with TIMER.span(f"sa_mlp_dw_nw[{cin}>{cout}]" if TIMER.detail else "sa_mlp_dw_nw", B * P * 4 * (2 * cout + cin)):
+                with TIMER.span(f"sa_mlp_dw_nw[{cin}>{cout}]" if TIMER.detail else "sa_mlp_dw_nw", B * P * 4 * (2 * cout + cin), 2 * B * P * cin * cout):
                     _lib.check(lib.ogc_sa_mlp_narrow_dw(
                         B, M, S, cout, cin, _p(dz), _p(go), cL, 0, _p(sel), _p(ys[l]), _p(coef), _p(ys[l - 1]),
                         _p(sss[l - 1]), _p(dW), _st()), "ogc_sa_mlp_narrow_dw")
             else:
-                with TIMER.span(f"{dw_tag}[{cin}>{cout}]" if TIMER.detail else dw_tag, B * P * 4 * (2 * cout + cin)):
+                with TIMER.span(f"{dw_tag}[{cin}>{cout}]" if TIMER.detail else dw_tag, B * P * 4 * (2 * cout + cin), 2 * B * P * cin * cout):
                     _lib.check(dw_fn(
                         B, N, M, S, cout, cin, int(gather), _p(dz), _p(go), cL, 0, _p(sel), _p(ys[l]), _p(coef),
                         _p(ys[l - 1]) if l else None, _p(sss[l - 1]) if l else None,
@@ -262,13 +266,13 @@ class _FusedSAMLP(Function):
                 dx_tc = not dx_nw and _tc_dx_ok(S, cout, cprev, False)
                 dx_fn, dx_tag = (lib.ogc_sa_mlp_layer_dx_tc, "sa_mlp_dx_tc") if dx_tc else (lib.ogc_sa_mlp_layer_dx, "sa_mlp_dx")
                 if dx_nw:
-                    with TIMER.span(f"sa_mlp_dx_nw[{cout}>{cprev}]" if TIMER.detail else "sa_mlp_dx_nw", B * P * 4 * (2 * cout + 2 * cprev)):
+                    with TIMER.span(f"sa_mlp_dx_nw[{cout}>{cprev}]" if TIMER.detail else "sa_mlp_dx_nw", B * P * 4 * (2 * cout + 2 * cprev), 2 * B * P * cout * cprev):
                         _lib.check(lib.ogc_sa_mlp_narrow_dx(
                             B, M, S, cout, cprev, _p(dz), _p(go), cL, 0, _p(sel), _p(ys[l]), _p(coef), _p(w2d),
                             _p(ys[l - 1]), _p(sss[l - 1]), _p(mrs[l - 1]), _p(params[3 * (l - 1) + 1]), _p(dz_prev),
                             _p(ab_prev), _p(dgamma_prev), _p(dbeta_prev), _st()), "ogc_sa_mlp_narrow_dx")
                 else:
-                    with TIMER.span(f"{dx_tag}[{cout}>{cprev}]" if TIMER.detail else dx_tag, B * P * 4 * (2 * cout + 2 * cprev)):
+                    with TIMER.span(f"{dx_tag}[{cout}>{cprev}]" if TIMER.detail else dx_tag, B * P * 4 * (2 * cout + 2 * cprev), 2 * B * P * cout * cprev):
                         _lib.check(dx_fn(
                             B, N, M, S, cout, cin, 0, cprev, _p(dz), _p(go), cL, 0, _p(sel), _p(ys[l]), _p(coef), _p(w2d),
                             _p(ys[l - 1]), _p(sss[l - 1]), _p(mrs[l - 1]), _p(params[3 * (l - 1) + 1]), _p(dz_prev),
@@ -281,7 +285,7 @@ class _FusedSAMLP(Function):
                     rows = min(128, Cf - off)
                     dx_tc = _tc_dx_ok(S, cout, rows, True)
                     dx_fn, dx_tag = (lib.ogc_sa_mlp_layer_dx_tc, "sa_mlp_dx_tc") if dx_tc else (lib.ogc_sa_mlp_layer_dx, "sa_mlp_dx")
-                    with TIMER.span(f"{dx_tag}[{cout}>scatter{rows}]" if TIMER.detail else dx_tag, B * P * 4 * (2 * cout + rows)):
+                    with TIMER.span(f"{dx_tag}[{cout}>scatter{rows}]" if TIMER.detail else dx_tag, B * P * 4 * (2 * cout + rows), 2 * B * P * cout * rows):
                         _lib.check(dx_fn(
                             B, N, M, S, cout, cin, 3 + off, rows, _p(dz), _p(go), cL, 0, _p(sel), _p(ys[l]), _p(coef),
                             _p(w2d), None, None, None, None, None, None, None, None, _p(idx), _p(dfeat_pm), Cf, off,

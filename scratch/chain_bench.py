@@ -19,7 +19,7 @@ cfgs = [("SA1a", 8192, 2048, 3, [32, 32, 32]), ("SA1b", 8192, 2048, 3, [32, 32, 
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 if os.environ.get("CFGS"):
     cfgs = [c for c in cfgs if c[0] in os.environ["CFGS"].split(",")]
-sa_fused.USE_CHAIN = os.environ.get("CHAIN", "1") == "1"
+sa_fused.USE_CHAIN = os.environ.get("CHAIN", "1") == "1"       # default here: the chained kernels
 sa_fused.STORE_Y = os.environ.get("STORE_Y", "1") == "1"
 fwd_only = os.environ.get("FWD_ONLY", "0") == "1"
 for name, N, M, Cf, w in cfgs:

@@ -12,9 +12,9 @@ pytestmark = pytest.mark.gpu
 def per_layer_kernels():
     """The round-1 per-layer kernels (fallback for shapes the chained kernels do not cover) compared among themselves."""
     from ogc_b200 import sa_fused
-    sa_fused.USE_CHAIN = False
+    prev, sa_fused.USE_CHAIN = sa_fused.USE_CHAIN, False
     yield
-    sa_fused.USE_CHAIN = True
+    sa_fused.USE_CHAIN = prev
 
 
 def rel_err(a, b):

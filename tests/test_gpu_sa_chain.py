@@ -41,14 +41,18 @@ def _setup(N, M, Cf, widths, B=3):
 def test_chain_forward_matches_per_layer_kernels(b200, N, M, Cf, widths):
     from ogc_b200 import sa_fused
     xyz, new_xyz, feat_pm, idx, mlp, layers = _setup(N, M, Cf, widths)
-    assert sa_fused._chain_plan(M, 64, Cf, widths) is not None
+    sa_fused.USE_CHAIN = True
+    try:
+        assert sa_fused._chain_plan(M, 64, Cf, widths) is not None
+    finally:
+        sa_fused.USE_CHAIN = False
     saved = {}
     for chain in (False, True):
         sa_fused.USE_CHAIN, sa_fused.STORE_Y = chain, True
         try:
             out = sa_fused.fused_sa_mlp(xyz, new_xyz, feat_pm.clone().requires_grad_(True), idx, layers)
         finally:
-            sa_fused.USE_CHAIN = True
+            sa_fused.USE_CHAIN = False
         saved[chain] = [out.detach().clone()] + [t.clone() for t in out.grad_fn.saved_tensors[4:]]
     assert len(saved[False]) == len(saved[True])
     for a, b in zip(saved[False], saved[True]):
@@ -75,9 +79,14 @@ def test_chain_matches_composed_reference_expression(b200, N, M, Cf, widths):
     ref_df = f1.grad.clone()
     mlp.zero_grad()
     f2 = feat_pm.clone().requires_grad_(True)
-    out = fused_sa_mlp(xyz, new_xyz, f2, idx, layers)
-    (out * probe).sum().backward()
-    err = float((out - ref).abs().max() / ref.abs().max())
+    from ogc_b200 import sa_fused
+    sa_fused.USE_CHAIN = True
+    try:
+        out = fused_sa_mlp(xyz, new_xyz, f2, idx, layers)
+        (out * probe).sum().backward()
+    finally:
+        sa_fused.USE_CHAIN = False
+    err = float((out.detach() - ref.detach()).abs().max() / ref.detach().abs().max())
     assert err < 2e-5, err
 
     def fro(a, b):
@@ -99,6 +108,6 @@ def test_chain_forward_many_tiles_per_cta(b200, N, M, Cf, widths):
         try:
             outs[chain] = sa_fused.fused_sa_mlp(xyz, new_xyz, feat_pm.clone().requires_grad_(True), idx, layers).detach()
         finally:
-            sa_fused.USE_CHAIN = True
+            sa_fused.USE_CHAIN = False
     torch.cuda.synchronize()
     assert float((outs[True] - outs[False]).abs().max()) <= 2e-5 * max(1.0, float(outs[False].abs().max()))
