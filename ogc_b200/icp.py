@@ -10,13 +10,13 @@ import torch
 
 import pointnet2.pointnet2 as ops
 from ogc_b200 import backend as _backend_mod
-from ogc_b200.losses import _use_fused, fit_motion_svd_batch, interpolate_mask_by_flow, match_mask_by_iou, \
+from ogc_b200.losses import MAX_FUSED_K_ICP, _use_fused, fit_motion_svd_batch, interpolate_mask_by_flow, match_mask_by_iou, \
     match_indices_by_iou
 
 
 def weighted_kabsch(pc, flow, mask):
     """pc, flow (B,N,3), mask (B,N,K) -> flow (B,N,3) projected on per-object rigid motions (oa_icp.py:16-38)."""
-    if _use_fused(pc, flow, mask):
+    if _use_fused(pc, flow, mask, k=mask.shape[-1]):
         be = _backend_mod.get_backend()
         pc, flow, mask = pc.contiguous(), flow.contiguous(), mask.contiguous()
         Rt = be.weighted_kabsch(pc, flow, mask, second_is_flow=True)
@@ -31,7 +31,7 @@ def weighted_kabsch(pc, flow, mask):
 
 def object_aware_icp(pc1, pc2, flow, mask1, mask2, icp_iter=10, temperature=0.01):
     """oa_icp.py:41-84.  pc1, pc2, flow (B,N,3), mask1, mask2 (B,N,K) -> refined flow (B,N,3)."""
-    fused = _use_fused(pc1, pc2, flow, mask1, mask2)
+    fused = _use_fused(pc1, pc2, flow, mask1, mask2, k=mask1.shape[-1], k_max=MAX_FUSED_K_ICP)
     # align the slot order of frame 2 to frame 1 (:52-54)
     mask2_interp = interpolate_mask_by_flow(pc1, pc2, mask1, flow)
     if fused:

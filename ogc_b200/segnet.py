@@ -28,10 +28,6 @@ from ogc_b200 import backend as _backend_mod
 from ogc_b200 import fp_fused, sa_fused
 
 FORCE_COMPOSED = False   # tests: run the torch-composed SA path on the GPU to compare with the fused kernels
-# bench.py's "reference CUDA extension" arm: reproduce the reference's op sequence as written -- nn.Conv
-# through cuDNN (TF32 allowed, torch's default), the k-NN of a multi-scale level recomputed per scale --
-# so that the timing is the one a user of the reference gets on this GPU.
-REFERENCE_FAITHFUL = False
 
 GN_GROUPS = 4  # models/segnet_kitti.py:8  BN_CONFIG = GroupNorm, 4 groups
 
@@ -88,10 +84,7 @@ class ConvGNReLU(nn.Module):
         self.act = act
 
     def forward(self, x):
-        if REFERENCE_FAITHFUL:
-            y = (F.conv2d if x.dim() == 4 else F.conv1d)(x, self.conv.weight, self.conv.bias)
-        else:
-            y = _pointwise_linear(self.conv.weight, x, self.conv.bias)
+        y = _pointwise_linear(self.conv.weight, x, self.conv.bias)
         if self.normlayer is not None:
             gn = self.normlayer.gn
             y = F.group_norm(y, GN_GROUPS, gn.weight, gn.bias, gn.eps)
@@ -131,7 +124,7 @@ class SetAbstraction(nn.Module):
         `new_xyz`: this level's centres when they were sampled ahead of time."""
         if new_xyz is None:
             new_xyz = self.sample(xyz)
-        fused = (not FORCE_COMPOSED and not REFERENCE_FAITHFUL and xyz.is_cuda and getattr(_backend_mod.get_backend(), "name", "") == "b200"
+        fused = (not FORCE_COMPOSED and xyz.is_cuda and getattr(_backend_mod.get_backend(), "name", "") == "b200"
                  and all(sa_fused.supported(ns, [m.layer0.conv.weight.shape[1]] +
                                             [getattr(m, f"layer{i}").conv.weight.shape[0] for i in range(m.n_layers)])
                          for ns, m in zip(self.nsamples, self.mlps)))
@@ -143,7 +136,7 @@ class SetAbstraction(nn.Module):
         outs = []
         knn_cache = {}
         for radius, nsample, mlp in zip(self.radii, self.nsamples, self.mlps):
-            if nsample not in knn_cache or REFERENCE_FAITHFUL:   # identical k-NN for every scale with the same k
+            if nsample not in knn_cache:   # identical k-NN for every scale with the same k
                 same_k = [r for r, ns in zip(self.radii, self.nsamples) if ns == nsample]
                 if fused and all(r is not None for r in same_k):
                     # every scale replaces neighbours beyond its radius by the nearest one: nothing farther than the
@@ -174,7 +167,7 @@ class FeaturePropagation(nn.Module):
         `nn`: (dist2, idx) of three_nn(unknown, known) when computed ahead of time (fused path only)."""
         widths = [self.mlp.layer0.conv.weight.shape[1]] + [getattr(self.mlp, f"layer{i}").conv.weight.shape[0]
                                                            for i in range(self.mlp.n_layers)]
-        if (not FORCE_COMPOSED and not REFERENCE_FAITHFUL and unknown.is_cuda and fp_fused.supported(widths)
+        if (not FORCE_COMPOSED and unknown.is_cuda and fp_fused.supported(widths)
                 and getattr(_backend_mod.get_backend(), "name", "") == "b200"):
             layers = [(getattr(self.mlp, f"layer{i}").conv.weight, getattr(self.mlp, f"layer{i}").normlayer.gn.weight,
                        getattr(self.mlp, f"layer{i}").normlayer.gn.bias) for i in range(self.mlp.n_layers)]
@@ -348,7 +341,7 @@ class MaskFormer3D(nn.Module):
             l_feats[i] = self.FP_modules[i](l_pc[i], l_pc[i + 1], l_feats[i], l_feats[i + 1], None if fp_nn is None else fp_nn[i])
         slot = self.MF_head(l_feats[-1].transpose(1, 2))                      # (B,K,D)
         slot = self.object_mlp(slot.transpose(1, 2))                          # (B,64,K)
-        if (not FORCE_COMPOSED and not REFERENCE_FAITHFUL and pc.is_cuda and l_feats[0].shape[1] == 64 and slot.shape[2] <= 16
+        if (not FORCE_COMPOSED and pc.is_cuda and l_feats[0].shape[1] == 64 and slot.shape[2] <= 16
                 and getattr(_backend_mod.get_backend(), "name", "") == "b200"):
             return _MaskHeadFn.apply(l_feats[0], F.normalize(slot, dim=1), 1.0 / 0.05)
         logits = torch.einsum("bdn,bdk->bnk", F.normalize(l_feats[0], dim=1), F.normalize(slot, dim=1)) / 0.05

@@ -61,10 +61,10 @@ class FlatAdam:
         self.flat_g_ext.zero_()
 
     def step(self, lr_scale=1.0, grad_scale=1.0):
-        self.t += 1
         if self.lib is None:      # CPU arm of bench.py (--impl reference): same arithmetic in torch
             if bool(torch.isnan(self.flat_g).any()):
-                return
+                return            # skipped step: the bias-correction counter does not advance (train_seg.py:81-85)
+            self.t += 1
             g = self.flat_g * grad_scale
             if self.weight_decay:
                 g = g + self.weight_decay * self.flat_p
@@ -74,6 +74,7 @@ class FlatAdam:
             denom = self.v.sqrt() / (1 - b2 ** self.t) ** 0.5 + self.eps
             self.flat_p.addcdiv_(self.m, denom, value=-self.lr * lr_scale / (1 - b1 ** self.t))
             return
+        self.t += 1
         self.set_lr(self.lr * lr_scale)
         self.launch_step(grad_scale)
 
@@ -111,9 +112,32 @@ class SegTrainer:
         self.sched = dict(lr=lr, lr_decay=lr_decay, decay_step=decay_step, lr_clip=lr_clip)
         self.global_batch_size, self.world_size = global_batch_size, world_size
         self.device = self.opt.flat_p.device
+        if world_size > 1:
+            self.sync_replicas()
         self.overlap_geometry = True      # FPS chain on a side stream under the loss neighbourhoods
         self._geo_stream = None
         self._geo_stream2 = None
+
+    def sync_replicas(self, src=0):
+        """Data-parallel replicas must start from (and resume with) identical weights and optimiser state: broadcast
+        rank `src`'s flat parameter / moment buffers and step counter.  Called at construction; call it again after
+        loading a checkpoint on one rank.  (The per-step all-reduce only keeps EQUAL replicas equal.)"""
+        if self.world_size <= 1 or not dist.is_initialized():
+            return
+        for buf in (self.opt.flat_p, self.opt.m, self.opt.v):
+            dist.broadcast(buf, src=src)
+        if self.opt.lib is not None:
+            dist.broadcast(self.opt.state, src=src)
+        t = torch.tensor([float(self.opt.t)], device=self.device)
+        dist.broadcast(t, src=src)
+        self.opt.t = int(t.item())
+        # cheap divergence check: every rank must now hold the same parameter checksum
+        chk = self.opt.flat_p.double().sum().reshape(1)
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        if float(hi - lo) != 0.0:
+            raise RuntimeError("ogc_b200: replicas disagree on the parameters after the start-up broadcast")
 
     def _step_body(self, pcs, flows, it, aug_transform, defer, allreduce=True):
         """zero_grad -> forward -> loss -> backward -> NaN count -> all-reduce -> Adam launch (no host sync when
@@ -146,7 +170,7 @@ class SegTrainer:
         with stream events, so it is captured into the step's CUDA graph as two parallel branches."""
         from . import losses
         be = get_backend()
-        if getattr(be, "name", "") != "b200" or losses.FORCE_COMPOSED or losses.REFERENCE_FAITHFUL:
+        if getattr(be, "name", "") != "b200" or losses.FORCE_COMPOSED:
             return None, None
         main = torch.cuda.current_stream()
         if self._geo_stream is None:
@@ -156,7 +180,7 @@ class SegTrainer:
         from . import segnet as _segnet
         third = None
         with torch.cuda.stream(side):
-            if _segnet.FORCE_COMPOSED or _segnet.REFERENCE_FAITHFUL:
+            if _segnet.FORCE_COMPOSED:
                 centres, fp_nn = self.segnet.sample_chain(flat), None
             else:
                 # the three_nn of the finest FP level (8192 <- 2048, the only sizeable one) needs the first level's
@@ -180,8 +204,9 @@ class SegTrainer:
         losses.NEIGHBOUR_CACHE.clear()
         if specs:
             for pc in pcs_l:
+                handle = losses.tag_cloud(pc)
                 for kind, k, radius in specs:
-                    losses.NEIGHBOUR_CACHE[(pc.data_ptr(), kind, k, radius)] = losses.neighbourhood(be, kind, k, radius, pc)
+                    losses.NEIGHBOUR_CACHE[(handle, kind, k, radius)] = losses.neighbourhood(be, kind, k, radius, pc)
         main.wait_stream(side)
         if third is not None:
             main.wait_stream(third)
@@ -220,7 +245,9 @@ class SegTrainer:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):                      # warm-up on a side stream (allocator, cuBLAS, NCCL)
             for _ in range(2):
-                self._step_body(g["pcs"], g["flows"], it, aug_transform, defer=True)
+                # no collective in the warm-up: a rank-local re-capture (e.g. a ragged last batch on one rank) must not
+                # change the number of all-reduces the ranks issue
+                self._step_body(g["pcs"], g["flows"], it, aug_transform, defer=True, allreduce=False)
                 opt.launch_step(1.0 / self.world_size)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
@@ -242,7 +269,11 @@ class SegTrainer:
                 g["host"].copy_(d["_values"], non_blocking=True)       # captured D2H of the logged scalars
         g["launches"] = get_backend().launches - launches0
         g["graph"] = graph
+        # keep ONLY the current key: the start_steps schedule and the augmentation switch are monotone, so an old
+        # graph (multi-GB private activation pool + static inputs) is never replayed again
+        self._graphs.clear()
         self._graphs[key] = g
+        torch.cuda.empty_cache()
         return g
 
     def train_step_graphed(self, it, batch, aug_transform=False):

@@ -58,3 +58,16 @@ def test_product_path_refuses_cpu_tensors():
         be.fps(torch.zeros(1, 8, 3), 2)
     with pytest.raises(RuntimeError, match="CUDA tensor"):
         be.knn(2, torch.zeros(1, 8, 3), torch.zeros(1, 8, 3))
+
+
+def test_pointnet2_cuda_shim_exports_the_reference_wrappers():
+    """INTEGRATION.md option B: the shim module carries the ten names of pointnet2/src/pointnet2_api.cpp:10-25."""
+    import importlib.util
+    path = os.path.join(ROOT, "ogc_b200", "shim", "pointnet2_cuda.py")
+    spec = importlib.util.spec_from_file_location("pointnet2_cuda_shim_check", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    for name in ["ball_query_wrapper", "group_points_wrapper", "group_points_grad_wrapper", "gather_points_wrapper",
+                 "gather_points_grad_wrapper", "furthest_point_sampling_wrapper", "knn_wrapper", "three_nn_wrapper",
+                 "three_interpolate_wrapper", "three_interpolate_grad_wrapper"]:
+        assert callable(getattr(mod, name)), name

@@ -16,11 +16,11 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _build(world):
+def _build(world, seed=10):
     from ogc_b200 import losses
     from ogc_b200.segnet import MaskFormer3D
     from ogc_b200.train import SegTrainer
-    torch.manual_seed(10)
+    torch.manual_seed(seed)
     net = MaskFormer3D(n_slot=6, n_point=256, variant="sapien")
     cfg = {**losses.KITTISF_LOSS_CFG, "start_steps": [0, 0, 0],
            "smooth_loss_params": {"w_knn": 3.0, "w_ball_q": 1.0,
@@ -42,7 +42,9 @@ def _worker(rank, world, port, out):
     from ogc_b200 import backend
     from oracle.pointnet2_oracle import OracleBackend
     backend.set_backend(OracleBackend())
-    tr = _build(world)
+    # rank 1 initialises from a DIFFERENT seed: SegTrainer must broadcast rank 0's weights at start-up (ADVICE r1:
+    # replicas that only ever all-reduce gradients silently train different models otherwise)
+    tr = _build(world, seed=10 + 7 * rank)
     full = _batch()
     shard = tuple(x[rank:rank + 1] for x in full)
     d = tr.train_step(5000, shard, aug_transform=True)
@@ -86,6 +88,7 @@ def test_nan_gradient_skips_update_on_every_rank():
     before = opt.flat_p.clone()
     opt.step()
     assert torch.equal(opt.flat_p, before)
+    assert opt.t == 0          # a skipped step does not advance the bias correction (the reference never calls step())
     opt.zero_grad()
     p.grad.fill_(1.0)
     opt.step()
