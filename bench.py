@@ -530,8 +530,10 @@ def main():
         row = {"calls_per_step": d["calls"] / 2, "ms_per_step": d["ms"] / 2, "avg_ms": per_launch_ms}
         if d.get("flops"):
             tf = d["flops"] / d["calls"] / (per_launch_ms * 1e-3) / 1e12
-            row.update({"bound": "tensor", "useful_tflops": tf, "frac_of_tf32_peak": tf / tf32_peak,
-                        "frac_of_tf32_peak_3xtf32_work": 3 * tf / tf32_peak})
+            row["useful_tflops"] = tf
+            if "_tc" in name or "chain" in name:          # tcgen05 kernels; the narrow / SIMT ones are HBM-bound fp32 FFMA
+                row.update({"bound": "tensor", "frac_of_tf32_peak": tf / tf32_peak,
+                            "frac_of_tf32_peak_3xtf32_work": 3 * tf / tf32_peak})
         gbs = d["bytes"] / d["calls"] / (per_launch_ms * 1e-3) / 1e9
         row.update({"alg_gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak})
         op_rows[name] = row
