@@ -247,6 +247,23 @@ OGC_API int ogc_sa_mlp_layer_dw(int b, int n, int m, int nsample, int cout, int 
                                 const float *xyz, const float *new_xyz, const float *feat_pm, const int *idx,
                                 float *dw, void *stream);
 
+/* ---- Uniform-grid acceleration of the radius-bounded searches (csrc/grid.cu) -------------------------------------------
+ * ogc_grid_build counting-sorts every cloud xyz (b,m,3) into a grid whose cells are >= radius wide (at most
+ * 32 x 8 x 32 cells): sorted (b,m,4) fp32 records (x, y, z, original index as int bits), cell_start
+ * (ogc_grid_table_bytes(b) bytes), params (b,16) fp32.  ogc_knn_grid / ogc_ball_query_grid then visit only the 27
+ * cells around a query and return EXACTLY what ogc_knn_bounded / ogc_ball_query return (interpolate_gpu.cu:9-57 order
+ * rule (distance, index); ball_query_gpu.cu:9-45 first-nsample-in-index-order rule), for max_dist / radius <= the
+ * radius the grid was built with.  unknown / new_xyz == NULL: the queries are the cloud itself (n == m). */
+OGC_API long long ogc_grid_sorted_bytes(int b, int m);
+OGC_API long long ogc_grid_table_bytes(int b);
+OGC_API long long ogc_grid_params_bytes(int b);
+OGC_API int ogc_grid_build(int b, int m, float radius, const float *xyz, void *sorted, int *cell_start, float *params,
+                           void *stream);
+OGC_API int ogc_knn_grid(int b, int n, int m, int k, float max_dist, const float *unknown, const void *sorted,
+                         const int *cell_start, const float *params, float *dist, int *idx, void *stream);
+OGC_API int ogc_ball_query_grid(int b, int n, int m, float radius, int nsample, const float *new_xyz, const void *sorted,
+                                const int *cell_start, const float *params, int *idx, void *stream);
+
 /* ---- Chained set-abstraction MLP (round 2; csrc/sa_chain_fwd.cu) ----------------------------------------------------
  * Replaces, for one grouper of a PointNet++ SA level, grouping_operation x2 + concat + (conv1x1, GroupNorm(4), ReLU) x L
  * (+ max over nsample) of utils/pointnet2_util.py:33-44 / pointnet2/pointnet2.py:283-294 / utils/nn_util.py:151-168

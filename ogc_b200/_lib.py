@@ -44,6 +44,9 @@ SIGNATURES = {
     "ogc_gn_bwd_coef": [_I, _I, _LL, _P, _P, _P, _P, _P],
     "ogc_sa_mlp_layer_dx": [_I] * 8 + [_P, _P, _I, _I] + [_P] * 14 + [_I, _I, _P],
     "ogc_sa_mlp_layer_dw": [_I] * 7 + [_P, _P, _I, _I] + [_P] * 11,
+    "ogc_grid_build": [_I, _I, _F, _P, _P, _P, _P, _P],
+    "ogc_knn_grid": [_I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P],
+    "ogc_ball_query_grid": [_I, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P],
     "ogc_sa_chain_debug": [_P],
     "ogc_sa_chain_fits": [_I] * 5 + [_P],
     "ogc_sa_chain_fwd": [_I] * 7 + [_P] * 19,
@@ -92,6 +95,10 @@ def load():
         fn.restype = _I
     lib.ogc_version.restype = ctypes.c_char_p
     lib.ogc_version.argtypes = []
+    for name, argtypes in (("ogc_grid_sorted_bytes", [_I, _I]), ("ogc_grid_table_bytes", [_I]), ("ogc_grid_params_bytes", [_I])):
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = _LL
     _lib = lib
     return lib
 

@@ -116,6 +116,27 @@ class B200Backend:
         self.launches += 1
         return d, idx
 
+    # ---- uniform-grid acceleration of the radius-bounded searches (csrc/grid.cu) ----------------
+    USE_GRID = True          # tests flip this to compare with the brute-force kernels
+    GRID_MIN_POINTS = 1024   # below this the brute-force kernels are already cheap
+
+    def _grid(self, xyz, radius):
+        """Counting-sort every cloud of xyz (B,m,3) into a grid with cells >= radius -> (sorted, cell_start, params)."""
+        B, m, _ = xyz.shape
+        dev = xyz.device
+        sorted_ = torch.empty(B, m, 4, dtype=torch.float32, device=dev)
+        table = torch.empty(self.lib.ogc_grid_table_bytes(B) // 4, dtype=torch.int32, device=dev)
+        params = torch.empty(B, 16, dtype=torch.float32, device=dev)
+        with TIMER.span("grid_build", B * m * 28):
+            _lib.check(self.lib.ogc_grid_build(B, m, float(radius), _ptr(xyz), _ptr(sorted_), _ptr(table), _ptr(params),
+                                               _stream()), "ogc_grid_build")
+        self.launches += 1
+        return sorted_, table, params
+
+    @staticmethod
+    def _same(a, b):
+        return a.data_ptr() == b.data_ptr() and a.shape == b.shape
+
     def knn_bounded(self, k, unknown, known, max_dist):
         """k-NN among candidates within max_dist (dist = sqrt, +inf / idx 0 for unfilled slots); see the header."""
         _chk_f32(unknown, "unknown")
@@ -124,6 +145,14 @@ class B200Backend:
         m = known.shape[1]
         d = torch.empty(B, n, k, dtype=torch.float32, device=unknown.device)
         idx = torch.empty(B, n, k, dtype=torch.int32, device=unknown.device)
+        if self.USE_GRID and m >= self.GRID_MIN_POINTS and max_dist > 0:
+            sorted_, table, params = self._grid(known, max_dist)
+            with TIMER.span("knn", B * (12 * (n + m) + 8 * n * k)):
+                _lib.check(self.lib.ogc_knn_grid(B, n, m, k, float(max_dist), None if self._same(unknown, known) else _ptr(unknown),
+                                                 _ptr(sorted_), _ptr(table), _ptr(params), _ptr(d), _ptr(idx), _stream()),
+                           "ogc_knn_grid")
+            self.launches += 1
+            return d, idx
         with TIMER.span("knn", B * (12 * (n + m) + 8 * n * k)):
             _lib.check(self.lib.ogc_knn_bounded(B, n, m, k, float(max_dist), _ptr(unknown), _ptr(known), _ptr(d),
                                                 _ptr(idx), _stream()), "ogc_knn_bounded")
@@ -224,6 +253,14 @@ class B200Backend:
         B, N, _ = xyz.shape
         M = new_xyz.shape[1]
         idx = torch.empty(B, M, nsample, dtype=torch.int32, device=xyz.device)
+        if self.USE_GRID and self.GRID_MIN_POINTS <= N <= 32768 and radius > 0:
+            sorted_, table, params = self._grid(xyz, radius)
+            with TIMER.span("ball_query", B * (12 * (N + M) + 4 * M * nsample)):
+                _lib.check(self.lib.ogc_ball_query_grid(B, M, N, float(radius), nsample,
+                                                        None if self._same(new_xyz, xyz) else _ptr(new_xyz), _ptr(sorted_),
+                                                        _ptr(table), _ptr(params), _ptr(idx), _stream()), "ogc_ball_query_grid")
+            self.launches += 1
+            return idx
         with TIMER.span("ball_query", B * (12 * (N + M) + 4 * M * nsample)):
             _lib.check(self.lib.ogc_ball_query(B, N, M, float(radius), nsample, _ptr(new_xyz), _ptr(xyz), _ptr(idx),
                                                _stream()), "ogc_ball_query")

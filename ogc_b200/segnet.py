@@ -124,6 +124,7 @@ class SetAbstraction(nn.Module):
         `new_xyz`: this level's centres when they were sampled ahead of time."""
         if new_xyz is None:
             new_xyz = self.sample(xyz)
+        wait_ready(new_xyz)
         fused = (not FORCE_COMPOSED and xyz.is_cuda and getattr(_backend_mod.get_backend(), "name", "") == "b200"
                  and all(sa_fused.supported(ns, [m.layer0.conv.weight.shape[1]] +
                                             [getattr(m, f"layer{i}").conv.weight.shape[0] for i in range(m.n_layers)])
@@ -157,6 +158,15 @@ class SetAbstraction(nn.Module):
         return new_xyz, torch.cat(outs, dim=1)
 
 
+def wait_ready(t):
+    """Tensors produced ahead of time on a side stream (train.SegTrainer._prefetch_geometry) carry the event they become
+    ready at; the consumer's stream waits for it here (a no-op for ordinary tensors)."""
+    ev = getattr(t, "_ogc_ready", None)
+    if ev is not None:
+        torch.cuda.current_stream().wait_event(ev)
+    return t
+
+
 class FeaturePropagation(nn.Module):
     def __init__(self, channels):
         super().__init__()
@@ -171,6 +181,8 @@ class FeaturePropagation(nn.Module):
                 and getattr(_backend_mod.get_backend(), "name", "") == "b200"):
             layers = [(getattr(self.mlp, f"layer{i}").conv.weight, getattr(self.mlp, f"layer{i}").normlayer.gn.weight,
                        getattr(self.mlp, f"layer{i}").normlayer.gn.bias) for i in range(self.mlp.n_layers)]
+            if nn is not None:
+                wait_ready(nn[0])
             return fp_fused.fused_fp(unknown, known, unknown_feats, known_feats, layers, nn)
         dist, idx = ops.three_nn(unknown.contiguous(), known.contiguous())
         recip = 1.0 / (dist + 1e-8)

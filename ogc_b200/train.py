@@ -149,6 +149,13 @@ class SegTrainer:
         pcs_l = [pcs[:, i].contiguous() for i in range(t)]
         centres, fp_nn = self._prefetch_geometry(flat, pcs_l) if self.overlap_geometry and flat.is_cuda else (None, None)
         masks = self.segnet(flat, flat, centres, fp_nn).view(b, t, n, -1)
+        if centres is not None and getattr(self, "_geo_join", None):
+            # every side-stream product has been consumed through its event; join the streams themselves as well so
+            # that a stream capture sees no unjoined branch
+            for st in self._geo_join:
+                if st is not None:
+                    torch.cuda.current_stream().wait_stream(st)
+            self._geo_join = None
         masks_l = [masks[:, i].contiguous() for i in range(t)]
         flows_l = [flows[:, i].contiguous() for i in range(t)]
         self.criterion.defer_logging = defer
@@ -189,17 +196,26 @@ class SegTrainer:
                     self._geo_stream2 = torch.cuda.Stream()
                 third = self._geo_stream2
                 sa = self.segnet.SA_modules
-                centres = [sa[0].sample(flat)]
-                first_done = torch.cuda.Event()
-                first_done.record(side)
+                # every product carries the event it becomes ready at (`_ogc_ready`): the main stream waits per
+                # CONSUMER (level-1 centres before SA1, ... -- segnet.wait_ready), not for the whole chain, so that
+                # only the first FPS (1.27 ms of the 1.77 ms chain) sits on the critical path
+                def ready(t, stream):
+                    t._ogc_ready = torch.cuda.Event()
+                    t._ogc_ready.record(stream)
+                    return t
+                centres = [ready(sa[0].sample(flat), side)]
                 with torch.cuda.stream(third):
-                    third.wait_event(first_done)
+                    third.wait_event(centres[0]._ogc_ready)
                     nn0 = be.three_nn(flat.contiguous(), centres[0])
+                    ready(nn0[0], third)
                 for m in sa[1:]:
-                    centres.append(m.sample(centres[-1]))
+                    centres.append(ready(m.sample(centres[-1]), side))
                 l_pc = [flat] + centres
-                fp_nn = [nn0] + [be.three_nn(l_pc[i].contiguous(), l_pc[i + 1].contiguous())
-                                 for i in range(1, len(self.segnet.FP_modules))]
+                fp_nn = [nn0]
+                for i in range(1, len(self.segnet.FP_modules)):
+                    nn_i = be.three_nn(l_pc[i].contiguous(), l_pc[i + 1].contiguous())
+                    ready(nn_i[0], side)
+                    fp_nn.append(nn_i)
         specs = losses.smooth_specs(self.criterion.smooth_loss) if hasattr(self.criterion, "smooth_loss") else None
         losses.NEIGHBOUR_CACHE.clear()
         if specs:
@@ -207,9 +223,9 @@ class SegTrainer:
                 handle = losses.tag_cloud(pc)
                 for kind, k, radius in specs:
                     losses.NEIGHBOUR_CACHE[(handle, kind, k, radius)] = losses.neighbourhood(be, kind, k, radius, pc)
-        main.wait_stream(side)
-        if third is not None:
-            main.wait_stream(third)
+        if third is None:                 # composed path: plain join
+            main.wait_stream(side)
+        self._geo_join = (side, third)
         return centres, fp_nn
 
     def train_step(self, it, batch, aug_transform=False):
