@@ -37,6 +37,17 @@ CASES = {
 }
 
 
+# BASELINE.json configs[1] at its OWN size: one KITTI-SF-like pair (2 clouds x 8192 points, the
+# synthetic road scene of ogc_b200/data.py), n_slot 10, through the unmodified reference on CPU
+CASES["segnet_kitti_8192"] = {"kind": "segnet", "variant": "kitti", "n_slot": 10, "n_point": 8192, "B": 2, "seed": 31,
+                              "scene": "kittisf",
+                              "grad_params": ["SA_modules.0.mlps.0.layer0.conv.weight", "SA_modules.1.mlps.0.layer1.conv.weight",
+                                              "SA_modules.2.mlps.0.layer2.conv.weight", "FP_modules.0.mlp.layer1.conv.weight",
+                                              "MF_head.transformer_layers.1.cross_attn.in_proj_weight", "object_mlp.1.conv.bias"]}
+CASES["ogc_loss_8192_aug"] = {"kind": "ogc_loss", "B": 1, "N": 8192, "K": 10, "seed": 32, "aug": True, "it": 100000,
+                              "scene": "kittisf", "loss_cfg": KITTI_LOSS}
+
+
 FLOW_LOSS = {   # config/flow/ogcdr/ogcdr_unsup.yaml:37-52 with 3 unrolled iterations
     "weights": [0.75, 0.25], "iters_w": [0.5, 0.3, 0.3],
     "chamfer_loss_params": {"loss_norm": 2},
@@ -87,6 +98,23 @@ def make_inputs(case):
             e = np.exp(lg - lg.max(-1, keepdims=True))
             masks.append((e / e.sum(-1, keepdims=True))[:, rng.permutation(K)])
         return {"pc": f32(pc), "mask": f32(np.stack(masks)), "flows": f32(flows)}
+    if case["kind"] == "segnet" and case.get("scene") == "kittisf":
+        from ogc_b200 import data
+        pcs = data.make_batch(case["seed"], case["B"] // 2, case["n_point"], aug=False)[0]          # (b,2,N,3)
+        pc = pcs.reshape(case["B"], case["n_point"], 3).clone()
+        probe = f32(rng.normal(size=(case["B"], case["n_point"], case["n_slot"])))
+        return {"pc": pc, "probe": probe}
+    if case["kind"] == "ogc_loss" and case.get("scene") == "kittisf":
+        from ogc_b200 import data
+        pcs, segms, flows, _ = data.make_batch(case["seed"], case["B"], case["N"], aug=case["aug"])   # (b,V,N,3)
+        V, K = pcs.shape[1], case["K"]
+        logits = []
+        for v in range(V):
+            lg = rng.normal(size=(case["B"], case["N"], K)) * 0.5
+            seg = segms[:, v].numpy() % K
+            lg[np.arange(case["B"])[:, None], np.arange(case["N"])[None, :], seg] += 2.0
+            logits.append(f32(lg))
+        return {"pcs": [pcs[:, v].clone() for v in range(V)], "flows": [flows[:, v].clone() for v in range(V)], "logits": logits}
     if case["kind"] == "segnet":
         pc = f32(rng.uniform(-1, 1, size=(case["B"], case["n_point"], 3)) * case["scale"])
         probe = f32(rng.normal(size=(case["B"], case["n_point"], case["n_slot"])))

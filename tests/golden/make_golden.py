@@ -3,7 +3,7 @@
 repo's operator layer bound to the CPU oracle.  Run in the build container only (the reference tree
 does not travel to the GPU box); the produced .npz files are committed.
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [case names ...]
 
 Inputs are seeded; network weights come from `torch.manual_seed(10)` + this repo's MaskFormer3D
 constructor and are loaded into the reference model through `load_state_dict` (identical parameter
@@ -33,7 +33,10 @@ def main():
     import importlib
     from losses import seg_loss_unsup as ref_loss
 
+    only = set(sys.argv[1:])
     for name, case in CASES.items():
+        if only and name not in only:
+            continue
         out = {}
         inp = make_inputs(case)
         if case["kind"] == "segnet":

@@ -68,15 +68,109 @@ def test_fused_sa_mlp_matches_composed(b200, N, M, Cf, widths):
 
     assert out.shape == ref.shape
     assert rel_err(out, ref) < 2e-5, rel_err(out, ref)
-    # Gradients: a single ReLU decision (z ~ 0) or arg-max among the 64 samples can flip under a 1e-6 change of
-    # the forward values (different summation order / 3xTF32), which toggles one O(1) contribution in the sums
-    # behind a weight gradient (measured: all saved forward tensors agree to 1e-6, one flipped element moves one
-    # channel's gradient by ~3e-3 of the tensor's max).  So: Frobenius-relative error tight, max error loose.
+    # Gradients against a fp32 torch evaluation: both sides take their own ReLU / arg-max decisions, and one flipped
+    # decision moves a whole channel's gradient (test_gradients_match_fp64_given_identical_decisions below holds the
+    # decisions fixed and requires 1e-4; it also counts the flips).  Here only the aggregate is bounded.
     def fro_err(a, b):
         return float((a - b).norm() / b.norm().clamp_min(1e-12))
-    assert fro_err(f2.grad, ref_df) < 2e-3 and rel_err(f2.grad, ref_df) < 3e-2, (fro_err(f2.grad, ref_df), rel_err(f2.grad, ref_df))
+    assert fro_err(f2.grad, ref_df) < 2e-3, fro_err(f2.grad, ref_df)
     for n, p in mlp.named_parameters():
-        assert fro_err(p.grad, ref_grads[n]) < 2e-3 and rel_err(p.grad, ref_grads[n]) < 3e-2, (n, fro_err(p.grad, ref_grads[n]))
+        assert fro_err(p.grad, ref_grads[n]) < 2e-3, (n, fro_err(p.grad, ref_grads[n]))
+
+
+def _forced_decision_reference(xyz, new_xyz, feat_pm, idx, layers, probe, sel, ys, sss):
+    """float64 evaluation of the reference expression (group -> (conv1x1, GroupNorm(4), ReLU) x L -> max over nsample;
+    utils/pointnet2_util.py:33-44) with the ReLU masks and arg-max positions of the FUSED forward forced in.  Returns
+    (pooled output, gradients, number of ReLU decisions and arg-max positions that differ from the natural fp64 ones)."""
+    B, M, S = idx.shape
+    L = len(layers)
+    f64 = feat_pm.double().transpose(1, 2).contiguous().requires_grad_(True)
+    gi = idx.long()
+
+    def group(t):
+        C = t.shape[1]
+        return torch.gather(t.unsqueeze(2).expand(B, C, M, t.shape[2]), 3, gi.unsqueeze(1).expand(B, C, M, S))
+    a = torch.cat([group(xyz.double().transpose(1, 2).contiguous()) - new_xyz.double().transpose(1, 2).unsqueeze(-1),
+                   group(f64)], 1)
+    params64 = [[t.detach().double().requires_grad_(True) for t in lay] for lay in layers]
+    relu_flips = 0
+    for l in range(L):
+        W, gm, bt = params64[l]
+        y = torch.einsum("oc,bcms->boms", W.reshape(W.shape[0], -1), a)
+        C = y.shape[1]
+        yg = y.reshape(B, 4, -1)
+        mu, var = yg.mean(2, keepdim=True), yg.var(2, unbiased=False, keepdim=True)
+        z = ((yg - mu) / torch.sqrt(var + 1e-5)).reshape_as(y) * gm.view(1, -1, 1, 1) + bt.view(1, -1, 1, 1)
+        m_ours = (sss[l][..., 0].double().view(B, C, 1) * ys[l].double() + sss[l][..., 1].double().view(B, C, 1) > 0).reshape_as(y)
+        flipped = (z > 0) != m_ours
+        relu_flips += int(flipped.sum())
+        assert float(z.detach()[flipped].abs().max()) < 1e-4 if flipped.any() else True     # only decisions at ~0 may differ
+        a = z * m_ours
+    pooled = torch.gather(a, 3, sel.long().clamp(max=S - 1).unsqueeze(-1)).squeeze(-1) * (sel != 255)
+    nat = a.detach().max(dim=3)
+    arg_flips = (nat.indices != sel.long()) & (sel != 255)
+    if arg_flips.any():            # a different arg-max is only acceptable at a tie (to fp32 resolution)
+        assert float((nat.values - pooled.detach())[arg_flips].abs().max()) < 1e-4
+    (pooled * probe.double()).sum().backward()
+    grads = {"dfeat": f64.grad.transpose(1, 2)}
+    for i in range(L):
+        for j, nm in enumerate(("W", "gamma", "beta")):
+            grads[f"{nm}{i}"] = params64[i][j].grad
+    return pooled.detach(), grads, relu_flips, int(arg_flips.sum())
+
+
+@pytest.mark.parametrize("N,M,Cf,widths", [
+    (4096, 1024, 3, [32, 32, 32]), (4096, 1024, 3, [32, 32, 64]),     # SA1 (gathered SIMT layer + narrow kernels)
+    (2048, 1024, 96, [64, 64, 128]),                                   # SA2 (tcgen05 3xTF32 kernels) at its KITTI-SF size
+    (1024, 512, 128, [128, 128, 256]),                                 # SA3
+    (256, 64, 192, [128, 128, 256]),                                   # sapien SA2
+])
+def test_gradients_match_fp64_given_identical_decisions(b200, N, M, Cf, widths):
+    """Flip-aware gradient parity.  The fused forward fixes every data-dependent DECISION of the
+    block -- ReLU masks (from its stored pre-norm tensors) and max-pool winners (`sel`).  A float64 evaluation of the
+    reference expression with those decisions forced in must then agree with the fused backward to fp32 accuracy:
+    1e-4 in the Frobenius norm and 3e-4 of the largest entry for every gradient (measured: <= 3.5e-5 / 1.1e-4 on the
+    tensor-core kernels, ~4e-7 on the fp32 SIMT kernels).  Decisions that differ from the natural float64 ones are
+    counted and must sit at a tie: |pre-activation| < 1e-4, pooled margin < 1e-4 (measured: 0-5 per 10^8 activations)."""
+    from ogc_b200 import segnet, sa_fused
+    import pointnet2.pointnet2 as ops
+    torch.manual_seed(N + Cf)
+    B = 4
+    xyz = torch.randn(B, N, 3, device="cuda")
+    new_xyz = xyz[:, :M].contiguous()
+    feat_pm = torch.randn(B, N, Cf, device="cuda")
+    mlp = segnet.SharedMLP([Cf + 3] + widths).cuda()
+    with torch.no_grad():
+        for n_, p_ in mlp.named_parameters():
+            if "gn.weight" in n_:
+                p_.copy_(torch.randn_like(p_) * 0.5 + 0.8)
+            if "gn.bias" in n_:
+                p_.copy_(torch.randn_like(p_) * 0.3)
+    dist, idx = ops.knn(64, new_xyz, xyz)
+    idx = ops.clip_neighbours_by_radius(dist, idx, 1.2)
+    L = len(widths)
+    layers = [(getattr(mlp, f"layer{i}").conv.weight, getattr(mlp, f"layer{i}").normlayer.gn.weight,
+               getattr(mlp, f"layer{i}").normlayer.gn.bias) for i in range(L)]
+    probe = torch.randn(B, widths[-1], M, device="cuda")
+    f2 = feat_pm.clone().requires_grad_(True)
+    out = sa_fused.fused_sa_mlp(xyz, new_xyz, f2, idx, layers)
+    saved = out.grad_fn.saved_tensors
+    sel, ys, sss = saved[4], saved[6:6 + L], saved[6 + L:6 + 2 * L]
+    (out * probe).sum().backward()
+    mine = {"dfeat": f2.grad}
+    for i in range(L):
+        for j, nm in enumerate(("W", "gamma", "beta")):
+            mine[f"{nm}{i}"] = layers[i][j].grad
+    ref_out, ref, relu_flips, arg_flips = _forced_decision_reference(xyz, new_xyz, feat_pm, idx, layers, probe, sel, ys, sss)
+    n_act = sum(B * w * M * 64 for w in widths)
+    print(f"decisions differing from fp64: ReLU {relu_flips} of {n_act}, arg-max {arg_flips} of {B * widths[-1] * M}")
+    assert relu_flips <= 1e-6 * n_act + 8 and arg_flips <= 1e-5 * B * widths[-1] * M + 4
+    assert float((out.detach().double() - ref_out).abs().max()) <= 2e-5 * float(ref_out.abs().max())
+    for k in mine:
+        d = (mine[k].double().reshape(ref[k].shape) - ref[k]).abs()
+        fro = float(d.norm() / ref[k].norm().clamp_min(1e-300))
+        mx = float(d.max() / ref[k].abs().max().clamp_min(1e-300))
+        assert fro <= 1e-4 and mx <= 3e-4, (k, fro, mx)
 
 
 @pytest.mark.parametrize("N,M,Cf,widths", [(400, 100, 96, [64, 64, 128]), (300, 70, 128, [128, 128, 256])])
