@@ -28,6 +28,15 @@ from ogc_b200 import backend as _backend_mod
 from ogc_b200 import fp_fused, sa_fused
 
 FORCE_COMPOSED = False   # tests: run the torch-composed SA path on the GPU to compare with the fused kernels
+HEAD_SIDE_STREAM = True  # slot transformer + object MLP on a side stream underneath the feature-propagation chain
+_HEAD_STREAMS = {}
+
+
+def _head_stream(device):
+    key = (device.type, device.index)
+    if key not in _HEAD_STREAMS:
+        _HEAD_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _HEAD_STREAMS[key]
 
 GN_GROUPS = 4  # models/segnet_kitti.py:8  BN_CONFIG = GroupNorm, 4 groups
 
@@ -317,6 +326,7 @@ class MaskFormer3D(nn.Module):
             raise NotImplementedError("only the configurations the reference ships (config/seg/*.yaml) are mirrored")
         spec = SEGNET_SPECS[variant]
         self.variant = variant
+        self.n_slot = n_slot
         self.SA_modules = nn.ModuleList(
             SetAbstraction(int(n_point / div), radii, nsamples, [list(m) for m in mlps])
             for div, radii, nsamples, mlps in spec["sa"])
@@ -349,12 +359,31 @@ class MaskFormer3D(nn.Module):
             new_pc, new_feats = sa(l_pc[-1], l_feats[-1], None if centres is None else centres[i])
             l_pc.append(new_pc)
             l_feats.append(new_feats)
+        fused_head = (not FORCE_COMPOSED and pc.is_cuda and self.n_slot <= 16
+                      and getattr(_backend_mod.get_backend(), "name", "") == "b200")
+        side = None
+        if fused_head and HEAD_SIDE_STREAM:
+            # The slot transformer + object MLP (~60 tiny kernels forward, ~150 backward, K = 10 slots) only need the
+            # coarsest features, the feature-propagation chain only the set-abstraction outputs: two independent
+            # branches.  The head runs on a side stream underneath the FP kernels; autograd replays every node on the
+            # stream of its forward, so its backward overlaps the FP / SA backward the same way (and a stream capture
+            # records the fork / join as parallel graph branches).
+            main = torch.cuda.current_stream()
+            side = _head_stream(pc.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                slot = self.object_mlp(self.MF_head(l_feats[-1].transpose(1, 2)).transpose(1, 2))
+                slot_hat = F.normalize(slot, dim=1)
         for i in range(len(self.FP_modules) - 1, -1, -1):     # coarse -> fine; FP_modules[i] lifts level i+1 to i
             l_feats[i] = self.FP_modules[i](l_pc[i], l_pc[i + 1], l_feats[i], l_feats[i + 1], None if fp_nn is None else fp_nn[i])
-        slot = self.MF_head(l_feats[-1].transpose(1, 2))                      # (B,K,D)
-        slot = self.object_mlp(slot.transpose(1, 2))                          # (B,64,K)
-        if (not FORCE_COMPOSED and pc.is_cuda and l_feats[0].shape[1] == 64 and slot.shape[2] <= 16
-                and getattr(_backend_mod.get_backend(), "name", "") == "b200"):
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+            if l_feats[0].shape[1] == 64:
+                return _MaskHeadFn.apply(l_feats[0], slot_hat, 1.0 / 0.05)
+        else:
+            slot = self.MF_head(l_feats[-1].transpose(1, 2))                      # (B,K,D)
+            slot = self.object_mlp(slot.transpose(1, 2))                          # (B,64,K)
+        if fused_head and l_feats[0].shape[1] == 64:
             return _MaskHeadFn.apply(l_feats[0], F.normalize(slot, dim=1), 1.0 / 0.05)
         logits = torch.einsum("bdn,bdk->bnk", F.normalize(l_feats[0], dim=1), F.normalize(slot, dim=1)) / 0.05
         return logits.softmax(dim=-1)
