@@ -247,31 +247,26 @@ def icp_inputs(B, device, N=N_POINT, K=N_SLOT):
 
 
 def flow_step_fn(npoint, batch, iters, device):
-    """FlowStep3D forward (iters) + unsupervised flow loss + backward + Adam on OGC-DR-shaped synthetic pairs
-    (train_flow.py:59-92 with config/flow/ogcdr/ogcdr_unsup.yaml; generator shared with oracle/ref_arm.py)."""
+    """FlowStep3D forward (iters) + unsupervised flow loss + backward + NaN guard + Adam on OGC-DR-shaped synthetic pairs
+    (train_flow.py:59-92 with config/flow/ogcdr/ogcdr_unsup.yaml; generator shared with oracle/ref_arm.py).
+    On the GPU the step is ogc_b200.train.FlowTrainer's single CUDA-graph launch."""
     import importlib.util
     from ogc_b200.flownet import FlowStep3D, build_flow_loss, OGCDR_FLOW_LOSS_CFG
+    from ogc_b200.train import FlowTrainer
     spec = importlib.util.spec_from_file_location("ogc_ref_arm_gen", os.path.join(ROOT, "oracle", "ref_arm.py"))
     gen = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(gen)                       # only its pure-numpy batch generator is used here
     torch.manual_seed(10)
     net = FlowStep3D(npoint=npoint, use_instance_norm=False, loc_flow_nn=8, loc_flow_rad=0.05).to(device)
     crit = build_flow_loss(dict(OGCDR_FLOW_LOSS_CFG, iters_w=[0.5] + [0.3] * (iters - 1)))
-    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    trainer = FlowTrainer(net, crit, iters, lr=1e-3)
     batches = [gen.flow_batch(31 + i, batch, npoint) for i in range(2)]
     if device.type == "cuda":
         batches = [tuple(x.pin_memory() for x in b) for b in batches]
-    net.train()
+    graphed = device.type == "cuda" and os.environ.get("OGC_FLOW_EAGER", "0") != "1"
 
     def step(i):
-        pcs = batches[i % 2][0].to(device, non_blocking=True)
-        pc1, pc2 = pcs[:, 0].contiguous(), pcs[:, 1].contiguous()
-        opt.zero_grad()
-        preds = net(pc1, pc2, pc1, pc2, iters=iters)
-        loss, d = crit(pc1, pc2, preds)
-        loss.backward()
-        opt.step()
-        return d
+        return trainer.train_step_graphed(batches[i % 2]) if graphed else trainer.train_step(batches[i % 2])
     h2d = batches[0][0].numel() * 4
     return step, h2d
 

@@ -52,13 +52,15 @@ class FlowSA(nn.Module):
         xyz = xyz.contiguous()
         xyz_t = xyz.transpose(1, 2).contiguous()
         if fps_idx is None:
-            key = (xyz.data_ptr(), tuple(xyz.shape), self.npoint)
-            if fps_cache is not None and key in fps_cache:
+            # memo keyed by the tensor OBJECT (the entry holds a reference, so the id cannot be recycled while the
+            # memo lives: one forward pass); the callers pass the same level tensors again and again
+            key = (id(xyz), self.npoint)
+            if fps_cache is not None and key in fps_cache and fps_cache[key][1] is xyz:
                 fps_idx = fps_cache[key][0]
             else:
                 fps_idx = ops.furthest_point_sample(xyz_t, self.npoint)
                 if fps_cache is not None:
-                    fps_cache[key] = (fps_idx, xyz)      # holding xyz keeps its address from being reused
+                    fps_cache[key] = (fps_idx, xyz)
         new_xyz = ops.gather_operation(xyz, fps_idx)
         new_xyz_t = new_xyz.transpose(1, 2).contiguous()
         _, idx = ops.knn(self.nsample, new_xyz_t, xyz_t)
@@ -249,6 +251,7 @@ class UnsupervisedFlowStep3DLoss(nn.Module):
         self.chamfer_loss, self.smooth_loss = chamfer_loss, smooth_loss
         self.w_chamfer, self.w_smooth = weights
         self.iters_w = iters_w
+        self.defer_logging = False       # True: return the logged scalars as ONE device tensor (no host sync: capturable)
 
     def forward(self, pc1, pc2, flow_preds):
         assert len(flow_preds) == len(self.iters_w)
@@ -261,8 +264,10 @@ class UnsupervisedFlowStep3DLoss(nn.Module):
         loss = sum(terms)
         logged["sum"] = loss
         keys = list(logged)
-        vals = torch.stack([logged[k].detach().float().reshape(()) for k in keys]).tolist()   # one D2H, not 2*iters+1
-        return loss, dict(zip(keys, vals))
+        stacked = torch.stack([logged[k].detach().float().reshape(()) for k in keys])
+        if self.defer_logging:
+            return loss, {"_keys": keys, "_values": stacked}
+        return loss, dict(zip(keys, stacked.tolist()))                                        # one D2H, not 2*iters+1
 
 
 OGCDR_FLOW_LOSS_CFG = {   # config/flow/ogcdr/ogcdr_unsup.yaml:37-52

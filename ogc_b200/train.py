@@ -314,3 +314,76 @@ class SegTrainer:
         out = dict(zip(g["keys"], g["host"].tolist()))
         out.setdefault("invariance", 0)
         return out
+
+
+class FlowTrainer:
+    """`Trainer._train_it` of train_flow.py:59-92 (FlowStep3D forward over `iters` GRU iterations, unsupervised flow loss,
+    backward, NaN guard, Adam) with the same device-side machinery as SegTrainer: flat Adam with the NaN-skip decided on
+    the device, and the whole step replayed as ONE CUDA graph (`train_step_graphed`) -- the reference's step is ~3000
+    small launches and is bound by the host, not the GPU.  Replicas only across GPUs (BatchNorm statistics are local)."""
+
+    def __init__(self, flownet, criterion, iters, lr=1e-3, weight_decay=0.0):
+        self.net, self.criterion, self.iters = flownet, criterion, iters
+        self.opt = FlatAdam(flownet.parameters(), lr=lr, weight_decay=weight_decay)
+        self.device = self.opt.flat_p.device
+        self._graph = None
+
+    def _body(self, pcs, defer):
+        self.net.train()
+        self.opt.zero_grad()
+        pc1, pc2 = pcs[:, 0].contiguous(), pcs[:, 1].contiguous()
+        preds = self.net(pc1, pc2, pc1, pc2, iters=self.iters)
+        self.criterion.defer_logging = defer
+        try:
+            loss, d = self.criterion(pc1, pc2, preds)
+        finally:
+            self.criterion.defer_logging = False
+        loss.backward()
+        self.opt.count_nan()
+        return d
+
+    def train_step(self, batch):
+        pcs = batch[0].to(self.device, non_blocking=True)
+        d = self._body(pcs, defer=False)
+        self.opt.step()
+        return d
+
+    def train_step_graphed(self, batch):
+        pcs = batch[0]
+        if self._graph is None or self._graph["pcs"].shape != pcs.shape:
+            g = {"pcs": torch.zeros(pcs.shape, dtype=torch.float32, device=self.device)}
+            g["pcs"].copy_(pcs)
+            opt = self.opt
+            snap = [x.clone() for x in (opt.flat_p, opt.m, opt.v, opt.state)]
+            bn = [(m, m.running_mean.clone(), m.running_var.clone(), m.num_batches_tracked.clone())
+                  for m in self.net.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm)]
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                      # warm-up (allocator, cuBLAS handles) on a side stream
+                for _ in range(2):
+                    self._body(g["pcs"], defer=True)
+                    opt.launch_step(1.0)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            for dst, src in zip((opt.flat_p, opt.m, opt.v, opt.state), snap):        # the warm-up must not train
+                dst.copy_(src)
+            for m, a, b_, c in bn:
+                m.running_mean.copy_(a); m.running_var.copy_(b_); m.num_batches_tracked.copy_(c)
+            host = torch.zeros(32, dtype=torch.float32).pin_memory()
+            l0 = get_backend().launches
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                d = self._body(g["pcs"], defer=True)
+                opt.launch_step(1.0)
+                g["keys"], g["host"] = d["_keys"], host[:len(d["_keys"])]
+                g["host"].copy_(d["_values"], non_blocking=True)
+            g["launches"] = get_backend().launches - l0
+            g["graph"] = graph
+            self._graph = g
+        g = self._graph
+        g["pcs"].copy_(pcs, non_blocking=True)
+        self.opt.set_lr(self.opt.lr)
+        g["graph"].replay()
+        get_backend().launches += g["launches"]
+        torch.cuda.current_stream().synchronize()
+        return dict(zip(g["keys"], g["host"].tolist()))

@@ -67,3 +67,33 @@ def test_flownet_gpu_matches_reference(b200):
     med = float(np.median(np.abs(preds[2] - G["flow2"])))
     print(f"third iteration: median |diff| {med:.2e}")
     assert np.isfinite(preds[2]).all() and med < 2e-2
+
+
+@pytest.mark.gpu
+def test_flow_trainer_graph_replay_equals_eager(b200):
+    """ogc_b200.train.FlowTrainer: the CUDA-graph replay of the step (train_flow.py:59-92) must train like the eager
+    step -- same logged losses, same parameters after 3 steps (BatchNorm running statistics included), up to the fp32
+    summation order of the atomically accumulated gradients (which differs from run to run in the reference too)."""
+    from ogc_b200.flownet import FlowStep3D, build_flow_loss, OGCDR_FLOW_LOSS_CFG
+    from ogc_b200.train import FlowTrainer
+
+    def run(graphed):
+        torch.manual_seed(10)
+        net = FlowStep3D(npoint=512, loc_flow_nn=8, loc_flow_rad=0.05).cuda()
+        tr = FlowTrainer(net, build_flow_loss(dict(OGCDR_FLOW_LOSS_CFG, iters_w=[0.5, 0.3, 0.3])), iters=3)
+        g = torch.Generator().manual_seed(4)
+        pc1 = torch.rand(4, 512, 3, generator=g) - 0.5
+        pcs = torch.stack([pc1, pc1 + 0.02 + 0.003 * torch.randn(4, 512, 3, generator=g)], 1)
+        batch = (pcs.pin_memory(), None, None, None)
+        logs = [(tr.train_step_graphed if graphed else tr.train_step)(batch) for _ in range(3)]
+        torch.cuda.synchronize()
+        bn = torch.cat([m.running_var.flatten() for m in net.modules() if isinstance(m, torch.nn.BatchNorm2d)])
+        return logs, tr.opt.flat_p.clone(), bn.clone()
+
+    le, pe, be_ = run(False)
+    lg, pg, bg = run(True)
+    for a, b in zip(le, lg):
+        for k in a:
+            assert abs(a[k] - b[k]) <= 1e-4 * max(1.0, abs(a[k])), (k, a[k], b[k])
+    assert float((pe - pg).abs().max()) <= 1e-4
+    assert float((be_ - bg).abs().max()) <= 1e-4 * float(be_.abs().max())
