@@ -47,6 +47,15 @@ def _tc_dx_ok(S, cout, rows, scatter):
     return USE_TC and S == 64 and 32 <= cout <= (128 if scatter else 256) and rows <= 128 and (scatter or rows % 16 == 0)
 
 
+USE_CHAIN_DX = False  # input-gradient kernel in the round-2 orientation (csrc/sa_chain_bwd.cu): on par with the per-layer
+                      # kernel for dense / scatter layers, slower for the synthesised last layer -> off by default
+
+
+def _chain_dx_ok(S, M, cout, rows, scatter):
+    return (USE_TC and USE_CHAIN_DX and S == 64 and M % 2 == 0 and cout % 32 == 0 and cout <= 256 and rows <= 128
+            and rows % (16 if scatter else 32) == 0 and 8 * rows * cout <= 180 * 1024)   # resident W^T (hi + lo) fits one SM
+
+
 STORE_Y = True      # stage 1: keep the pre-norm tensors for the per-layer backward kernels
 USE_CHAIN = False   # round-2 kernels (csrc/sa_chain_*.cu): positions on the MMA's M axis, layers chained through TMEM.
                     # Correct (tests/test_gpu_sa_chain.py) but not yet faster than the per-layer kernels at KITTI-SF sizes
@@ -271,6 +280,14 @@ class _FusedSAMLP(Function):
                             B, M, S, cout, cprev, _p(dz), _p(go), cL, 0, _p(sel), _p(ys[l]), _p(coef), _p(w2d),
                             _p(ys[l - 1]), _p(sss[l - 1]), _p(mrs[l - 1]), _p(params[3 * (l - 1) + 1]), _p(dz_prev),
                             _p(ab_prev), _p(dgamma_prev), _p(dbeta_prev), _st()), "ogc_sa_mlp_narrow_dx")
+                elif _chain_dx_ok(S, M, cout, cprev, False):
+                    chan_sums = torch.zeros(B, cprev, 2, **f32)
+                    with TIMER.span(f"sa_chain_dx[{cout}>{cprev}]" if TIMER.detail else "sa_chain_dx", B * P * 4 * (2 * cout + 2 * cprev), 2 * B * P * cout * cprev):
+                        _lib.check(lib.ogc_sa_chain_dx(
+                            B, N, M, S, cout, cin, 0, cprev, _p(dz), _p(go), cL, 0, _p(sel), _p(ys[l]), _p(coef), _p(w2d),
+                            _p(ys[l - 1]), _p(sss[l - 1]), _p(mrs[l - 1]), _p(params[3 * (l - 1) + 1]), _p(dz_prev),
+                            _p(ab_prev), _p(dgamma_prev), _p(dbeta_prev), None, None, 0, 0, _p(chan_sums), _st()), "ogc_sa_chain_dx")
+                    be.launches += 1      # + dx_finalize_kernel
                 else:
                     with TIMER.span(f"{dx_tag}[{cout}>{cprev}]" if TIMER.detail else dx_tag, B * P * 4 * (2 * cout + 2 * cprev), 2 * B * P * cout * cprev):
                         _lib.check(dx_fn(
@@ -283,6 +300,14 @@ class _FusedSAMLP(Function):
                 dfeat_pm = torch.zeros(B, N, Cf, **f32)
                 for off in range(0, Cf, 128):
                     rows = min(128, Cf - off)
+                    if _chain_dx_ok(S, M, cout, rows, True):
+                        with TIMER.span(f"sa_chain_dx[{cout}>scatter{rows}]" if TIMER.detail else "sa_chain_dx", B * P * 4 * (2 * cout + rows), 2 * B * P * cout * rows):
+                            _lib.check(lib.ogc_sa_chain_dx(
+                                B, N, M, S, cout, cin, 3 + off, rows, _p(dz), _p(go), cL, 0, _p(sel), _p(ys[l]), _p(coef),
+                                _p(w2d), None, None, None, None, None, None, None, None, _p(idx), _p(dfeat_pm), Cf, off,
+                                None, _st()), "ogc_sa_chain_dx")
+                        be.launches += 1
+                        continue
                     dx_tc = _tc_dx_ok(S, cout, rows, True)
                     dx_fn, dx_tag = (lib.ogc_sa_mlp_layer_dx_tc, "sa_mlp_dx_tc") if dx_tc else (lib.ogc_sa_mlp_layer_dx, "sa_mlp_dx")
                     with TIMER.span(f"{dx_tag}[{cout}>scatter{rows}]" if TIMER.detail else dx_tag, B * P * 4 * (2 * cout + rows), 2 * B * P * cout * rows):

@@ -21,6 +21,7 @@ if os.environ.get("CFGS"):
     cfgs = [c for c in cfgs if c[0] in os.environ["CFGS"].split(",")]
 sa_fused.USE_CHAIN = os.environ.get("CHAIN", "1") == "1"       # default here: the chained kernels
 sa_fused.STORE_Y = os.environ.get("STORE_Y", "1") == "1"
+sa_fused.USE_CHAIN_DX = os.environ.get("CHAIN_DX", "1") == "1"
 fwd_only = os.environ.get("FWD_ONLY", "0") == "1"
 for name, N, M, Cf, w in cfgs:
     xyz = (torch.rand(B, N, 3, device="cuda") - 0.5) * 40

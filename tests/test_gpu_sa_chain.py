@@ -111,3 +111,34 @@ def test_chain_forward_many_tiles_per_cta(b200, N, M, Cf, widths):
             sa_fused.USE_CHAIN = False
     torch.cuda.synchronize()
     assert float((outs[True] - outs[False]).abs().max()) <= 2e-5 * max(1.0, float(outs[False].abs().max()))
+
+
+DX_SHAPES = [
+    (400, 100, 96, [64, 64, 128]),        # SA2: dense 128 -> 64 (synthesised dz), 64 -> 64, scatter 96
+    (300, 70, 128, [128, 128, 128]),      # SA3-like: 128 -> 128 (the 256-wide layer's weights exceed one SM: falls back)
+    (256, 64, 32, [32, 96, 160]),         # group sizes 8 / 24 inside a 16-column piece; scatter 32
+    (256, 64, 160, [64, 64]),             # scatter in two row blocks (128 + 32)
+]
+
+
+@pytest.mark.parametrize("N,M,Cf,widths", DX_SHAPES)
+def test_chain_dx_matches_per_layer_kernels(b200, N, M, Cf, widths):
+    """ogc_sa_chain_dx against ogc_sa_mlp_layer_dx_tc / ogc_sa_mlp_layer_dx: every gradient of the block."""
+    from ogc_b200 import sa_fused
+    xyz, new_xyz, feat_pm, idx, mlp, layers = _setup(N, M, Cf, widths)
+    probe = torch.randn(3, widths[-1], M, device="cuda")
+    res = {}
+    for chain_dx in (False, True):
+        sa_fused.USE_CHAIN_DX = chain_dx
+        try:
+            f = feat_pm.clone().requires_grad_(True)
+            mlp.zero_grad()
+            out = sa_fused.fused_sa_mlp(xyz, new_xyz, f, idx, layers)
+            (out * probe).sum().backward()
+        finally:
+            sa_fused.USE_CHAIN_DX = False
+        res[chain_dx] = [f.grad.clone()] + [p.grad.clone() for p in mlp.parameters()]
+    for a, b in zip(res[False], res[True]):
+        rel = float((a - b).norm() / a.norm().clamp_min(1e-30))
+        assert rel <= 2e-5, rel
+        assert float((a - b).abs().max()) <= 1e-4 * float(a.abs().max()), float((a - b).abs().max())
