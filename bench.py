@@ -265,8 +265,11 @@ def flow_step_fn(npoint, batch, iters, device):
         batches = [tuple(x.pin_memory() for x in b) for b in batches]
     graphed = device.type == "cuda" and os.environ.get("OGC_FLOW_EAGER", "0") != "1"
 
-    def step(i):
-        return trainer.train_step_graphed(batches[i % 2]) if graphed else trainer.train_step(batches[i % 2])
+    resident = [tuple(x.to(device) for x in b) for b in batches]
+
+    def step(i, host_inputs=True):
+        b = (batches if host_inputs else resident)[i % 2]
+        return trainer.train_step_graphed(b) if graphed else trainer.train_step(b)
     h2d = batches[0][0].numel() * 4
     return step, h2d
 
@@ -431,15 +434,16 @@ def main():
             batch, iters = 16, 4
             step, h2d = flow_step_fn(npoint, batch, iters, device)
             l0 = be.launches
-            ms, last = time_cuda(step, args.steps, max(args.warmup, 3))
+            ms, last = time_cuda(lambda i: step(i, host_inputs=False), args.steps, max(args.warmup, 3))
             launches = (be.launches - l0) / (args.steps + max(args.warmup, 3))
+            ms_e2e, last = time_cuda(step, args.steps, 1)        # pinned host inputs copied every step + loss read-back
             line = {"metric": f"pairs/sec ({npoint} pts, FlowStep3D iters 4 fwd + flow loss bwd + Adam)", "value": batch / (ms * 1e-3),
                     "unit": "pairs/s", "ms_per_step": ms,
                     "config": {"workload": f"configs[2]: flownet_ogcdr.FlowStep3D npoint {npoint}, batch {batch}, iters {iters} + "
                                            "UnsupervisedFlowStep3DLoss + backward + Adam (train_flow.py:59-92)",
                                "parallelism": "replicas only (BatchNorm statistics are replica-local)",
                                "l2": "launch-bound: ~25 FPS + ~30 kNN calls per forward on <= 4096 points"},
-                    "e2e": {"value": batch / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms, "h2d_bytes_per_step": h2d,
+                    "e2e": {"value": batch / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                             "d2h_bytes_per_step": 4 * len(last)},
                     "roofline": None, "loss": last}
             if not args.no_ref_ext:

@@ -345,6 +345,9 @@ OGC_API int ogc_sa_chain_dx(int b, int n, int m, int nsample, int cout, int cin_
                             const float *ss_prev, const float *mean_rstd_prev, const float *gamma_prev,
                             float *dz_prev, double *ab_prev, float *dgamma_prev, float *dbeta_prev, const int *idx,
                             float *dfeat_pm, int dfeat_stride, int dfeat_off, float *chan_sums, void *stream);
+/* Diagnostics for ogc_sa_chain_dx: a device buffer of 8 x 32 int64; the k-th launch after this call fills
+ * slot k with per-role cycle sums of one CTA; NULL = off. */
+OGC_API int ogc_sa_chain_dx_debug(long long *buf);
 OGC_API int ogc_sa_mlp_layer_dw_tc(int b, int n, int m, int nsample, int cout, int cin, int gather, const float *dz,
                                    const float *go, int go_ctotal, int go_coff, const unsigned char *sel,
                                    const float *y, const float *coef, const float *y_prev, const float *ss_prev,

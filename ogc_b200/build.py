@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libogc_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-         "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr"]
+         "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr"] + os.environ.get("OGC_NVCC_FLAGS", "").split()
 
 
 def sources():

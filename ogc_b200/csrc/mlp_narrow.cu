@@ -47,44 +47,6 @@ __device__ __forceinline__ float ord2f(uint32_t k) {
     return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu));
 }
 
-// v[c] (c < 32) per lane  ->  returns sum over the 32 lanes of v[lane]  (31 shuffles instead of 160)
-__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const bool up = lane & 16;
-        const float send = up ? v[i] : v[i + 16];
-        const float keep = up ? v[i + 16] : v[i];
-        v[i] = keep + __shfl_xor_sync(OGC_FULL_MASK, send, 16);
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const bool up = lane & 8;
-        const float send = up ? v[i] : v[i + 8];
-        const float keep = up ? v[i + 8] : v[i];
-        v[i] = keep + __shfl_xor_sync(OGC_FULL_MASK, send, 8);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const bool up = lane & 4;
-        const float send = up ? v[i] : v[i + 4];
-        const float keep = up ? v[i + 4] : v[i];
-        v[i] = keep + __shfl_xor_sync(OGC_FULL_MASK, send, 4);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const bool up = lane & 2;
-        const float send = up ? v[i] : v[i + 2];
-        const float keep = up ? v[i + 2] : v[i];
-        v[i] = keep + __shfl_xor_sync(OGC_FULL_MASK, send, 2);
-    }
-    {
-        const bool up = lane & 1;
-        const float send = up ? v[0] : v[1];
-        const float keep = up ? v[1] : v[0];
-        v[0] = keep + __shfl_xor_sync(OGC_FULL_MASK, send, 1);
-    }
-    return v[0];
-}
 
 // ------------------------------------------------------------------------------------------ forward
 struct NarrowFwdParams {

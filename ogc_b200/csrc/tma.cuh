@@ -1,0 +1,61 @@
+// Tensor-map TMA (cp.async.bulk.tensor, SASS UTMALDG) helpers: 2-D fp32 tiles global -> shared with mbarrier completion.
+// One instruction moves a whole [box_outer][box_inner] tile; a 1-D cp.async.bulk (UBLKCP) of one 512-byte row costs the
+// copy engine about as much as a whole tile (measured: ~50-70 cycles per operation per SM), which capped row-by-row
+// staging at ~9 B/clk/SM.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace ogc {
+namespace tma {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// The driver entry point is resolved through the runtime (no link-time dependency on libcuda).
+static inline EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// Row-major fp32 matrix (outer rows of `inner` elements, contiguous), tiles of [box_outer][box_inner], no swizzle:
+// the tile lands in shared memory row-major, box_inner * 4 bytes per row.  inner * 4 must be a multiple of 16 and
+// `base` 16-byte aligned.  Returns false when the driver refuses.
+static inline bool make_2d_f32(CUtensorMap *map, const void *base, uint64_t inner, uint64_t outer, uint32_t box_inner,
+                               uint32_t box_outer) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {inner, outer};
+    const cuuint64_t strides[1] = {inner * 4};
+    const cuuint32_t box[2] = {box_inner, box_outer};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+#ifdef __CUDACC__
+// One thread: tile whose first element is (row y, column x) -> dst (128-byte aligned); completes `bar` with the tile's bytes.
+__device__ __forceinline__ void load_2d(void *dst_smem, const CUtensorMap *map, int x, int y, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            static_cast<uint32_t>(__cvta_generic_to_shared(dst_smem))),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(static_cast<uint32_t>(__cvta_generic_to_shared(bar)))
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_map(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+#endif
+
+}  // namespace tma
+}  // namespace ogc

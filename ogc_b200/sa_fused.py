@@ -52,7 +52,9 @@ USE_CHAIN_DX = False  # input-gradient kernel in the round-2 orientation (csrc/s
 
 
 def _chain_dx_ok(S, M, cout, rows, scatter):
-    return (USE_TC and USE_CHAIN_DX and S == 64 and M % 2 == 0 and cout % 32 == 0 and cout <= 256 and rows <= 128
+    if USE_CHAIN_DX in ("dense", "scatter") and USE_CHAIN_DX != ("scatter" if scatter else "dense"):
+        return False        # diagnostics: only one of the two modes
+    return (USE_TC and bool(USE_CHAIN_DX) and S == 64 and M % 2 == 0 and cout % 32 == 0 and cout <= 256 and rows <= 128
             and rows % (16 if scatter else 32) == 0 and 8 * rows * cout <= 180 * 1024)   # resident W^T (hi + lo) fits one SM
 
 

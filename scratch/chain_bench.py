@@ -21,7 +21,7 @@ if os.environ.get("CFGS"):
     cfgs = [c for c in cfgs if c[0] in os.environ["CFGS"].split(",")]
 sa_fused.USE_CHAIN = os.environ.get("CHAIN", "1") == "1"       # default here: the chained kernels
 sa_fused.STORE_Y = os.environ.get("STORE_Y", "1") == "1"
-sa_fused.USE_CHAIN_DX = os.environ.get("CHAIN_DX", "1") == "1"
+sa_fused.USE_CHAIN_DX = {"0": False, "1": True}.get(os.environ.get("CHAIN_DX", "1"), os.environ.get("CHAIN_DX"))
 fwd_only = os.environ.get("FWD_ONLY", "0") == "1"
 for name, N, M, Cf, w in cfgs:
     xyz = (torch.rand(B, N, 3, device="cuda") - 0.5) * 40
@@ -38,6 +38,8 @@ for name, N, M, Cf, w in cfgs:
         out = fused_sa_mlp(xyz, new_xyz, feat, idx, layers)
         if not fwd_only:
             (out * probe).sum().backward()
+        if os.environ.get("VERBOSE"):
+            torch.cuda.synchronize(); print("rep", r, "done", flush=True)
     torch.cuda.synchronize(); backend.TIMER.enabled = False
     P = M * 64
     print(f"== {name}: N={N} M={M} P={P} Cin={Cf + 3} widths={w} chain={sa_fused.USE_CHAIN}")

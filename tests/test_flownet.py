@@ -91,9 +91,21 @@ def test_flow_trainer_graph_replay_equals_eager(b200):
         return logs, tr.opt.flat_p.clone(), bn.clone()
 
     le, pe, be_ = run(False)
+    le2, pe2, be2 = run(False)
     lg, pg, bg = run(True)
-    for a, b in zip(le, lg):
-        for k in a:
-            assert abs(a[k] - b[k]) <= 1e-4 * max(1.0, abs(a[k])), (k, a[k], b[k])
-    assert float((pe - pg).abs().max()) <= 1e-4
-    assert float((be_ - bg).abs().max()) <= 1e-4 * float(be_.abs().max())
+    # step 0 starts from identical parameters: the logged losses must agree to fp32 summation order
+    for k in le[0]:
+        assert abs(le[0][k] - lg[0][k]) <= 2e-5 * max(1.0, abs(le[0][k])), (k, le[0][k], lg[0][k])
+    # later steps: Adam's first updates are sign-like (lr * g / (|g| + eps)), so gradient entries at the noise level of
+    # the atomically ordered sums move their parameter by +-lr in either run; the yardstick is therefore the deviation
+    # between two EAGER runs, not zero
+    dev = lambda la, lb: max(abs(a[k] - b[k]) / max(1.0, abs(a[k])) for a, b in zip(la, lb) for k in a)
+    noise_l, noise_p = dev(le, le2), float((pe - pe2).abs().max())
+    noise_b = float((be_ - be2).abs().max()) / float(be_.abs().max())
+    print(f"eager vs eager: logs {noise_l:.2e} params {noise_p:.2e} bn {noise_b:.2e}; "
+          f"graph vs eager: logs {dev(le, lg):.2e} params {float((pe - pg).abs().max()):.2e} "
+          f"bn {float((be_ - bg).abs().max()) / float(be_.abs().max()):.2e}")
+    assert dev(le, lg) <= 5 * noise_l + 1e-4
+    assert float((pe - pg).abs().max()) <= 5 * noise_p + 1e-4
+    assert float((pe - pg).abs().mean()) <= 5 * float((pe - pe2).abs().mean()) + 1e-6
+    assert float((be_ - bg).abs().max()) / float(be_.abs().max()) <= 5 * noise_b + 1e-4
