@@ -336,7 +336,9 @@ OGC_API int ogc_sa_mlp_layer_dx_tc(int b, int n, int m, int nsample, int cout, i
                                    int dfeat_off, void *stream);
 /* ogc_sa_mlp_layer_dx_tc in the round-2 orientation (csrc/sa_chain_bwd.cu: positions on the MMA's M axis, dY built
  * straight from global memory into tensor memory, no shared-memory staging of activations).  Same arguments and
- * results; dense mode additionally needs `chan_sums`, a caller-ZEROED (b, rows, 2) fp32 workspace.
+ * results; dense mode additionally needs `chan_sums`, a caller-ZEROED (b, prev_total, 2) fp32 workspace, and may cover
+ * a slice [prev_off, prev_off + rows) of a layer of prev_total channels (0, 0 = the whole layer; w column = row_off + k,
+ * y_prev / dz_prev / ss_prev / gamma_prev / dgamma_prev / dbeta_prev are those of the whole layer).
  * nsample == 64, m even, cout % 32 == 0 (<= 256), rows % 16 == 0 (<= 128; dense mode: % 32 == 0), else
  * OGC_ERR_UNSUPPORTED.  Replaces utils/nn_util.py:151-168 + pointnet2/pointnet2.py:283-294 backward (autograd). */
 OGC_API int ogc_sa_chain_dx(int b, int n, int m, int nsample, int cout, int cin_full, int row_off, int rows,
@@ -344,7 +346,8 @@ OGC_API int ogc_sa_chain_dx(int b, int n, int m, int nsample, int cout, int cin_
                             const float *y, const float *coef, const float *w, const float *y_prev,
                             const float *ss_prev, const float *mean_rstd_prev, const float *gamma_prev,
                             float *dz_prev, double *ab_prev, float *dgamma_prev, float *dbeta_prev, const int *idx,
-                            float *dfeat_pm, int dfeat_stride, int dfeat_off, float *chan_sums, void *stream);
+                            float *dfeat_pm, int dfeat_stride, int dfeat_off, float *chan_sums, int prev_total, int prev_off,
+                            void *stream);
 /* Diagnostics for ogc_sa_chain_dx: a device buffer of 8 x 32 int64; the k-th launch after this call fills
  * slot k with per-role cycle sums of one CTA; NULL = off. */
 OGC_API int ogc_sa_chain_dx_debug(long long *buf);

@@ -54,7 +54,7 @@ SIGNATURES = {
     "ogc_sa_mlp_layer_fwd_tc": [_I] * 8 + [_P] * 14,
     "ogc_sa_mlp_layer_dx_tc": [_I] * 8 + [_P, _P, _I, _I] + [_P] * 14 + [_I, _I, _P],
     "ogc_sa_chain_dx_debug": [_P],
-    "ogc_sa_chain_dx": [_I] * 8 + [_P, _P, _I, _I] + [_P] * 14 + [_I, _I, _P, _P],
+    "ogc_sa_chain_dx": [_I] * 8 + [_P, _P, _I, _I] + [_P] * 14 + [_I, _I, _P, _I, _I, _P],
     "ogc_sa_mlp_layer_dw_tc": [_I] * 7 + [_P, _P, _I, _I] + [_P] * 11,
     "ogc_icp_correspond": [_I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P],
     "ogc_mask_match": [_I, _I, _P, _P, _P, _P],

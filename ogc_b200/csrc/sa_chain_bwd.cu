@@ -45,6 +45,7 @@ struct DxParams {
     const int *idx;                                     // scatter: (B,M,64)
     float *dfeat_pm;
     int N, dfeat_stride, dfeat_off;
+    int prev_total, prev_off;      // dense mode on a slice of a wider layer: channels [prev_off, prev_off + rows) of prev_total
     uint32_t off_w, off_tab, off_scr, off_pring, off_ering;
     uint32_t col_acc[2];
     long long *dbg;                // optional: per-role cycle accumulators of CTA (0,0), see ogc_sa_chain_dx_debug
@@ -101,8 +102,8 @@ sa_dx_kernel(const __grid_constant__ DxParams q, const __grid_constant__ CUtenso
         tab_cf[c] = __ldg(reinterpret_cast<const float4 *>(q.dy.coef) + static_cast<size_t>(b) * C + c);
     if (!SCATTER) {
         for (int c = tid; c < rows; c += kDxThreads) {
-            const float2 s2 = __ldg(reinterpret_cast<const float2 *>(q.ss_prev) + static_cast<size_t>(b) * rows + c);
-            const int g = c / (rows / kGnGroups);
+            const float2 s2 = __ldg(reinterpret_cast<const float2 *>(q.ss_prev) + static_cast<size_t>(b) * q.prev_total + q.prev_off + c);
+            const int g = (q.prev_off + c) / (q.prev_total / kGnGroups);
             tab_ss[c] = make_float4(s2.x, s2.y, __ldg(q.mean_rstd_prev + (b * kGnGroups + g) * 2),
                                     __ldg(q.mean_rstd_prev + (b * kGnGroups + g) * 2 + 1));
         }
@@ -152,7 +153,7 @@ sa_dx_kernel(const __grid_constant__ DxParams q, const __grid_constant__ CUtenso
                     mbar_wait(&bar_efree[stage], (((eseq / ES) & 1) ^ 1));
                     if (lane == 0) {
                         mbar_arrive_expect_tx(&bar_efull[stage], kEStageBytes);
-                        tma::load_2d(ering + static_cast<size_t>(stage) * kEStageBytes, &tm_yp, pos0, b * rows + 32 * i, &bar_efull[stage]);
+                        tma::load_2d(ering + static_cast<size_t>(stage) * kEStageBytes, &tm_yp, pos0, b * q.prev_total + q.prev_off + 32 * i, &bar_efull[stage]);
                     }
                     __syncwarp();
                 }
@@ -168,61 +169,91 @@ sa_dx_kernel(const __grid_constant__ DxParams q, const __grid_constant__ CUtenso
         const uint32_t trow = tmem_base + (static_cast<uint32_t>(pw * 32) << 16);
         const bool rec = kRec && q.dbg && blockIdx.x == 0 && blockIdx.y == 0 && warp == kProdWarp0 && lane == 0;
         long long a_kfree = 0, a_pfull = 0, a_work = 0, t_begin = clock64(), t0 = 0, t1 = 0;
-        for (int u = 0; u < n_my; ++u) {
-            const int t = tile_of(u);
-            const int m = t * 2 + (pt >> 6), s_own = pt & 63;
-            for (int c = 0; c < nchunks; ++c) {
-                const int chunk_seq = u * nchunks + c;             // position in the CTA's chunk sequence
-                const int slot = chunk_seq % ring;
-                const uint32_t use = static_cast<uint32_t>(chunk_seq / ring);      // how many times the slot was used before
-                int sel_l = 0;
-                float go_l = 0.f;
-                if (SYNTH) {      // lane j: arg-max slot and pooled gradient of channel 32 c + j at this warp's centre
-                    sel_l = __ldg(q.dy.sel + (static_cast<size_t>(b) * C + 32 * c + lane) * M + m);
-                    go_l = __ldg(q.dy.go + (static_cast<size_t>(b) * q.dy.go_ctotal + q.dy.go_coff + 32 * c + lane) * M + m);
-                }
+        const int s_own = pt & 63;
+        // one 32-channel chunk: wait for the tensor-memory slot, then the two half-chunk stages
+        auto do_chunk = [&](int u, int c, int sel_l, float go_l) {
+            const int chunk_seq = u * nchunks + c;             // position in the CTA's chunk sequence
+            const int slot = chunk_seq % ring;
+            const uint32_t use = static_cast<uint32_t>(chunk_seq / ring);      // how many times the slot was used before
+            if (rec) t0 = clock64();
+            mbar_wait(&bar_kfree[slot], (use & 1) ^ 1);
+            tc::fence_after_sync();
+            if (rec) { t1 = clock64(); a_kfree += t1 - t0; }
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int hseq = chunk_seq * 2 + hh;
+                const int stage = hseq % PS;
                 if (rec) t0 = clock64();
-                mbar_wait(&bar_kfree[slot], (use & 1) ^ 1);
-                tc::fence_after_sync();
-                if (rec) { t1 = clock64(); a_kfree += t1 - t0; }
+                mbar_wait(&bar_pfull[stage], (hseq / PS) & 1);
+                if (rec) { t1 = clock64(); a_pfull += t1 - t0; }
+                const float *st_y = reinterpret_cast<const float *>(pring + static_cast<size_t>(stage) * kPStageBytes) + (8 * pg) * kTile + pt;
+                float yv[8], zv[8];
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    const int hseq = chunk_seq * 2 + hh;
-                    const int stage = hseq % PS;
-                    if (rec) t0 = clock64();
-                    mbar_wait(&bar_pfull[stage], (hseq / PS) & 1);
-                    if (rec) { t1 = clock64(); a_pfull += t1 - t0; }
-                    const float *st_y = reinterpret_cast<const float *>(pring + static_cast<size_t>(stage) * kPStageBytes) + (8 * pg) * kTile + pt;
-                    float yv[8], zv[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) yv[j] = st_y[j * kTile];
-                    if (SYNTH) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int sl = __shfl_sync(OGC_FULL_MASK, sel_l, 16 * hh + 8 * pg + j);
-                            const float g = __shfl_sync(OGC_FULL_MASK, go_l, 16 * hh + 8 * pg + j);
-                            zv[j] = sl == s_own ? g : 0.f;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) zv[j] = st_y[(16 + j) * kTile];
-                    }
-                    mbar_arrive(&bar_pfree[stage]);        // values are in registers: the stage may be refilled
-                    float hi[8], lo[8];
+                for (int j = 0; j < 8; ++j) yv[j] = st_y[j * kTile];
+                if (SYNTH) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const float4 cf = tab_cf[32 * c + 16 * hh + 8 * pg + j];
-                        const float v = fmaf(cf.x, zv[j], -cf.y) - (yv[j] - cf.w) * cf.z;
-                        tc::tf32_split(v, hi[j], lo[j]);
+                        const int sl = __shfl_sync(OGC_FULL_MASK, sel_l, 16 * hh + 8 * pg + j);
+                        const float g = __shfl_sync(OGC_FULL_MASK, go_l, 16 * hh + 8 * pg + j);
+                        zv[j] = sl == s_own ? g : 0.f;
                     }
-                    tc::tmem_st8_nowait(trow + slot * 64 + 16 * hh + 8 * pg, hi);
-                    tc::tmem_st8_nowait(trow + slot * 64 + 32 + 16 * hh + 8 * pg, lo);
-                    if (rec) a_work += clock64() - t1;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) zv[j] = st_y[(16 + j) * kTile];
                 }
-                tc::tmem_st_wait();
-                tc::fence_before_sync();
-                mbar_arrive(&bar_kfull[slot]);
+                float hi[8], lo[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 cf = tab_cf[32 * c + 16 * hh + 8 * pg + j];
+                    const float v = fmaf(cf.x, zv[j], -cf.y) - (yv[j] - cf.w) * cf.z;
+                    tc::tf32_split(v, hi[j], lo[j]);
+                }
+                // release the stage only after the loaded values have been CONSUMED: an arrive issued right behind the
+                // shared-memory loads is not ordered behind their completion (measured: the next TMA tile overwrote rows
+                // a warp was still reading, once per few hundred launches)
+                mbar_arrive(&bar_pfree[stage]);
+                tc::tmem_st8_nowait(trow + slot * 64 + 16 * hh + 8 * pg, hi);
+                tc::tmem_st8_nowait(trow + slot * 64 + 32 + 16 * hh + 8 * pg, lo);
+                if (rec) a_work += clock64() - t1;
             }
+            tc::tmem_st_wait();
+            tc::fence_before_sync();
+            mbar_arrive(&bar_kfull[slot]);
+        };
+        if (SYNTH) {
+            // lane j of chunk c: arg-max slot and pooled gradient of channel 32 c + j at this warp's centre.  The values of
+            // a chunk are reloaded for the NEXT tile as soon as they are used: a whole tile of prefetch distance.
+            const unsigned char *selb = q.dy.sel + (static_cast<size_t>(b) * C + lane) * M + (pt >> 6);
+            const float *gob = q.dy.go + (static_cast<size_t>(b) * q.dy.go_ctotal + q.dy.go_coff + lane) * M + (pt >> 6);
+            int sel_a[kMaxC / 32];
+            float go_a[kMaxC / 32];
+#pragma unroll
+            for (int c = 0; c < kMaxC / 32; ++c) {
+                sel_a[c] = 255; go_a[c] = 0.f;
+                if (c < nchunks && n_my > 0) {
+                    sel_a[c] = __ldg(selb + static_cast<size_t>(32 * c) * M + 2 * tile_of(0));
+                    go_a[c] = __ldg(gob + static_cast<size_t>(32 * c) * M + 2 * tile_of(0));
+                }
+            }
+            for (int u = 0; u < n_my; ++u) {
+                const bool more = u + 1 < n_my;
+                const int m_next = 2 * tile_of(more ? u + 1 : u);
+#pragma unroll
+                for (int c = 0; c < kMaxC / 32; ++c) {
+                    if (c < nchunks) {
+                        const int sl = sel_a[c];
+                        const float g = go_a[c];
+                        if (more) {
+                            sel_a[c] = __ldg(selb + static_cast<size_t>(32 * c) * M + m_next);
+                            go_a[c] = __ldg(gob + static_cast<size_t>(32 * c) * M + m_next);
+                        }
+                        do_chunk(u, c, sl, g);
+                    }
+                }
+            }
+        } else {
+            for (int u = 0; u < n_my; ++u)
+                for (int c = 0; c < nchunks; ++c) do_chunk(u, c, 0, 0.f);
         }
         if (rec) { q.dbg[0] = a_pfull; q.dbg[1] = a_kfree; q.dbg[2] = a_work; q.dbg[3] = clock64() - t_begin; }
     } else if (warp == kMmaWarp) {
@@ -322,7 +353,6 @@ sa_dx_kernel(const __grid_constant__ DxParams q, const __grid_constant__ CUtenso
                 float yp[16], v[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) yp[j] = blk[j * kTile + lane];
-                mbar_arrive(&bar_efree[stage]);            // values are in registers: the stage may be refilled
                 if (i == 0) {
                     if (rec) t0 = clock64();
                     mbar_wait(&bar_acc[buf], (u >> 1) & 1);
@@ -343,8 +373,9 @@ sa_dx_kernel(const __grid_constant__ DxParams q, const __grid_constant__ CUtenso
                     v[j] = gz;
                     yp[j] = gz * ((yp[j] - s4.z) * s4.w);      // dz_prev * xhat_prev
                 }
+                mbar_arrive(&bar_efree[stage]);            // the loaded values have been consumed: the stage may be refilled
                 {
-                    float *dzp = q.dz_prev + (static_cast<size_t>(b) * rows + c0) * P + pos;
+                    float *dzp = q.dz_prev + (static_cast<size_t>(b) * q.prev_total + q.prev_off + c0) * P + pos;
                     float *yo[4] = {dzp, dzp + P, dzp + 2 * static_cast<size_t>(P), dzp + 3 * static_cast<size_t>(P)};
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
@@ -372,7 +403,7 @@ sa_dx_kernel(const __grid_constant__ DxParams q, const __grid_constant__ CUtenso
             __syncwarp();
             for (int e = lane; e < rows; e += 32) {        // e = (piece i, channel within the piece, which sum)
                 const int ch = 32 * (e >> 5) + 16 * eg + ((e >> 1) & 15);
-                atomicAdd(q.chan_sums + (static_cast<size_t>(b) * rows + ch) * 2 + (e & 1), wsum[e]);
+                atomicAdd(q.chan_sums + (static_cast<size_t>(b) * q.prev_total + q.prev_off + ch) * 2 + (e & 1), wsum[e]);
             }
         }
     }
@@ -382,15 +413,16 @@ sa_dx_kernel(const __grid_constant__ DxParams q, const __grid_constant__ CUtenso
 }
 
 // chan_sums (B,rows,2) -> dgamma / dbeta (+=), ab (B,4,2) (+=): the inputs of ogc_gn_bwd_coef for layer l-1
-__global__ void dx_finalize_kernel(int B, int rows, const float *__restrict__ chan_sums, const float *__restrict__ gamma,
-                                   double *__restrict__ ab, float *__restrict__ dgamma, float *__restrict__ dbeta) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= rows) return;
-    const int g = c / (rows / kGnGroups);
+__global__ void dx_finalize_kernel(int B, int rows, int prev_total, int prev_off, const float *__restrict__ chan_sums,
+                                   const float *__restrict__ gamma, double *__restrict__ ab, float *__restrict__ dgamma,
+                                   float *__restrict__ dbeta) {
+    const int c = prev_off + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= prev_off + rows) return;
+    const int g = c / (prev_total / kGnGroups);
     const double gm = static_cast<double>(gamma[c]);
     float sb = 0.f, sg = 0.f;
     for (int b = 0; b < B; ++b) {
-        const float s0 = chan_sums[(static_cast<size_t>(b) * rows + c) * 2], s1 = chan_sums[(static_cast<size_t>(b) * rows + c) * 2 + 1];
+        const float s0 = chan_sums[(static_cast<size_t>(b) * prev_total + c) * 2], s1 = chan_sums[(static_cast<size_t>(b) * prev_total + c) * 2 + 1];
         sb += s0; sg += s1;
         atomicAdd(ab + (b * kGnGroups + g) * 2, gm * s0);
         atomicAdd(ab + (b * kGnGroups + g) * 2 + 1, gm * s1);
@@ -414,14 +446,17 @@ extern "C" int ogc_sa_chain_dx_debug(long long *buf) {
 }
 
 // Drop-in replacement of ogc_sa_mlp_layer_dx_tc (same arguments, same outputs) in the positions-on-M orientation, plus
-// `chan_sums`: a caller-zeroed (b, rows, 2) fp32 workspace (dense mode).  nsample == 64, m even, cout a multiple of 32
+// `chan_sums`: a caller-zeroed (b, prev_total, 2) fp32 workspace (dense mode), and `prev_total` / `prev_off`: the launch
+// covers channels [prev_off, prev_off + rows) of a layer of prev_total channels (0 / 0 = the whole layer; a 256 -> 128
+// layer whose resident weights exceed one SM runs as two 64-row launches).  nsample == 64, m even, cout a multiple of 32
 // (<= 256), rows a multiple of 16 (<= 128; dense: a multiple of 32).  OGC_ERR_UNSUPPORTED otherwise.
 extern "C" int ogc_sa_chain_dx(int b, int n, int m, int nsample, int cout, int cin_full, int row_off, int rows,
                                const float *dz, const float *go, int go_ctotal, int go_coff, const unsigned char *sel,
                                const float *y, const float *coef, const float *w, const float *y_prev,
                                const float *ss_prev, const float *mean_rstd_prev, const float *gamma_prev,
                                float *dz_prev, double *ab_prev, float *dgamma_prev, float *dbeta_prev, const int *idx,
-                               float *dfeat_pm, int dfeat_stride, int dfeat_off, float *chan_sums, void *stream) {
+                               float *dfeat_pm, int dfeat_stride, int dfeat_off, float *chan_sums, int prev_total, int prev_off,
+                               void *stream) {
     using namespace ogc;
     using namespace ogc::chain;
     if (b < 0 || m <= 0 || cout <= 0 || rows <= 0 || row_off < 0 || row_off + rows > cin_full || !w) return OGC_ERR_INVALID_ARG;
@@ -442,6 +477,9 @@ extern "C" int ogc_sa_chain_dx(int b, int n, int m, int nsample, int cout, int c
     q.cin_full = cin_full; q.row_off = row_off; q.rows = rows; q.W = w;
     q.y_prev = y_prev; q.ss_prev = ss_prev; q.mean_rstd_prev = mean_rstd_prev; q.dz_prev = dz_prev; q.chan_sums = chan_sums;
     q.idx = idx; q.dfeat_pm = dfeat_pm; q.N = n; q.dfeat_stride = dfeat_stride; q.dfeat_off = dfeat_off;
+    if (prev_total <= 0) { prev_total = rows; prev_off = 0; }
+    if (!scatter && (prev_off < 0 || prev_off + rows > prev_total || prev_total % kGnGroups != 0)) return OGC_ERR_INVALID_ARG;
+    q.prev_total = prev_total; q.prev_off = prev_off;
     // shared memory: W^T tile | tables | scatter transpose scratch | dY-input ring | mask-input ring
     const bool synth = dz == nullptr;
     const uint32_t w_bytes = w_tile_bytes(rows, cout);
@@ -482,7 +520,7 @@ extern "C" int ogc_sa_chain_dx(int b, int n, int m, int nsample, int cout, int c
     const uint64_t p64 = static_cast<uint64_t>(m) * nsample;
     bool ok = tma::make_2d_f32(&tm_y, y, p64, static_cast<uint64_t>(b) * cout, kTile, 16);
     if (ok && !synth) ok = tma::make_2d_f32(&tm_dz, dz, p64, static_cast<uint64_t>(b) * cout, kTile, 16);
-    if (ok && !scatter) ok = tma::make_2d_f32(&tm_yp, y_prev, p64, static_cast<uint64_t>(b) * rows, kTile, 32);
+    if (ok && !scatter) ok = tma::make_2d_f32(&tm_yp, y_prev, p64, static_cast<uint64_t>(b) * prev_total, kTile, 32);
     if (!ok) return OGC_ERR_UNSUPPORTED;
 #define OGC_DX_LAUNCH(S, SC)                                                                                          \
     do {                                                                                                              \
@@ -499,7 +537,8 @@ extern "C" int ogc_sa_chain_dx(int b, int n, int m, int nsample, int cout, int c
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return static_cast<int>(e);
     if (!scatter) {
-        dx_finalize_kernel<<<(rows + 127) / 128, 128, 0, st>>>(b, rows, chan_sums, gamma_prev, ab_prev, dgamma_prev, dbeta_prev);
+        dx_finalize_kernel<<<(rows + 127) / 128, 128, 0, st>>>(b, rows, prev_total, prev_off, chan_sums, gamma_prev, ab_prev, dgamma_prev,
+                                                               dbeta_prev);
     }
     OGC_RETURN_LAUNCH_STATUS();
 }

@@ -47,8 +47,8 @@ def _tc_dx_ok(S, cout, rows, scatter):
     return USE_TC and S == 64 and 32 <= cout <= (128 if scatter else 256) and rows <= 128 and (scatter or rows % 16 == 0)
 
 
-USE_CHAIN_DX = False  # input-gradient kernel in the round-2 orientation (csrc/sa_chain_bwd.cu): on par with the per-layer
-                      # kernel for dense / scatter layers, slower for the synthesised last layer -> off by default
+USE_CHAIN_DX = True   # input-gradient kernel in the round-2 orientation (csrc/sa_chain_bwd.cu: positions on the MMA's M axis,
+                      # operands staged by tensor-map TMA): 1.2-2.2x the per-layer kernel at KITTI-SF sizes
 
 
 def _chain_dx_ok(S, M, cout, rows, scatter):
@@ -58,6 +58,7 @@ def _chain_dx_ok(S, M, cout, rows, scatter):
             and rows % (16 if scatter else 32) == 0 and 8 * rows * cout <= 180 * 1024)   # resident W^T (hi + lo) fits one SM
 
 
+DEBUG_KEEP = None     # diagnostics: a list that collects (layer, dz_prev, ab_prev, coef) of every backward
 STORE_Y = True      # stage 1: keep the pre-norm tensors for the per-layer backward kernels
 USE_CHAIN = False   # round-2 kernels (csrc/sa_chain_*.cu): positions on the MMA's M axis, layers chained through TMEM.
                     # Correct (tests/test_gpu_sa_chain.py) but not yet faster than the per-layer kernels at KITTI-SF sizes
@@ -282,14 +283,19 @@ class _FusedSAMLP(Function):
                             B, M, S, cout, cprev, _p(dz), _p(go), cL, 0, _p(sel), _p(ys[l]), _p(coef), _p(w2d),
                             _p(ys[l - 1]), _p(sss[l - 1]), _p(mrs[l - 1]), _p(params[3 * (l - 1) + 1]), _p(dz_prev),
                             _p(ab_prev), _p(dgamma_prev), _p(dbeta_prev), _st()), "ogc_sa_mlp_narrow_dx")
-                elif _chain_dx_ok(S, M, cout, cprev, False):
+                elif _chain_dx_ok(S, M, cout, cprev, False) or (cprev % 64 == 0 and _chain_dx_ok(S, M, cout, cprev // 2, False)):
+                    # a layer whose resident W^T (hi + lo) exceeds one SM runs as two launches of half the output channels
+                    nblk = 1 if _chain_dx_ok(S, M, cout, cprev, False) else 2
+                    rows = cprev // nblk
                     chan_sums = torch.zeros(B, cprev, 2, **f32)
                     with TIMER.span(f"sa_chain_dx[{cout}>{cprev}]" if TIMER.detail else "sa_chain_dx", B * P * 4 * (2 * cout + 2 * cprev), 2 * B * P * cout * cprev):
-                        _lib.check(lib.ogc_sa_chain_dx(
-                            B, N, M, S, cout, cin, 0, cprev, _p(dz), _p(go), cL, 0, _p(sel), _p(ys[l]), _p(coef), _p(w2d),
-                            _p(ys[l - 1]), _p(sss[l - 1]), _p(mrs[l - 1]), _p(params[3 * (l - 1) + 1]), _p(dz_prev),
-                            _p(ab_prev), _p(dgamma_prev), _p(dbeta_prev), None, None, 0, 0, _p(chan_sums), _st()), "ogc_sa_chain_dx")
-                    be.launches += 1      # + dx_finalize_kernel
+                        for off in range(0, cprev, rows):
+                            _lib.check(lib.ogc_sa_chain_dx(
+                                B, N, M, S, cout, cin, off, rows, _p(dz), _p(go), cL, 0, _p(sel), _p(ys[l]), _p(coef), _p(w2d),
+                                _p(ys[l - 1]), _p(sss[l - 1]), _p(mrs[l - 1]), _p(params[3 * (l - 1) + 1]), _p(dz_prev),
+                                _p(ab_prev), _p(dgamma_prev), _p(dbeta_prev), None, None, 0, 0, _p(chan_sums), cprev, off,
+                                _st()), "ogc_sa_chain_dx")
+                    be.launches += 2 * nblk - 1      # + dx_finalize_kernel per launch
                 else:
                     with TIMER.span(f"{dx_tag}[{cout}>{cprev}]" if TIMER.detail else dx_tag, B * P * 4 * (2 * cout + 2 * cprev), 2 * B * P * cout * cprev):
                         _lib.check(dx_fn(
@@ -297,6 +303,8 @@ class _FusedSAMLP(Function):
                             _p(ys[l - 1]), _p(sss[l - 1]), _p(mrs[l - 1]), _p(params[3 * (l - 1) + 1]), _p(dz_prev),
                             _p(ab_prev), _p(dgamma_prev), _p(dbeta_prev), None, None, 0, 0, _st()), "ogc_sa_mlp_layer_dx")
                 be.launches += 1
+                if DEBUG_KEEP is not None:
+                    DEBUG_KEEP.append((l, dz_prev, ab_prev, coef))
                 dz, ab, dgamma, dbeta = dz_prev, ab_prev, dgamma_prev, dbeta_prev
             elif ctx.feat_needs_grad:
                 dfeat_pm = torch.zeros(B, N, Cf, **f32)
@@ -307,7 +315,7 @@ class _FusedSAMLP(Function):
                             _lib.check(lib.ogc_sa_chain_dx(
                                 B, N, M, S, cout, cin, 3 + off, rows, _p(dz), _p(go), cL, 0, _p(sel), _p(ys[l]), _p(coef),
                                 _p(w2d), None, None, None, None, None, None, None, None, _p(idx), _p(dfeat_pm), Cf, off,
-                                None, _st()), "ogc_sa_chain_dx")
+                                None, 0, 0, _st()), "ogc_sa_chain_dx")
                         be.launches += 1
                         continue
                     dx_tc = _tc_dx_ok(S, cout, rows, True)

@@ -13,8 +13,9 @@ def per_layer_kernels():
     """The round-1 per-layer kernels (fallback for shapes the chained kernels do not cover) compared among themselves."""
     from ogc_b200 import sa_fused
     prev, sa_fused.USE_CHAIN = sa_fused.USE_CHAIN, False
+    prev_dx, sa_fused.USE_CHAIN_DX = sa_fused.USE_CHAIN_DX, False
     yield
-    sa_fused.USE_CHAIN = prev
+    sa_fused.USE_CHAIN, sa_fused.USE_CHAIN_DX = prev, prev_dx
 
 
 def rel_err(a, b):
