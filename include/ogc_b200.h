@@ -428,6 +428,14 @@ OGC_API int ogc_sa_mlp_narrow_dw(int b, int m, int nsample, int cout, int cin, c
                                  const float *coef, const float *y_prev, const float *ss_prev, float *dw,
                                  void *stream);
 
+/* Weight gradient of a DENSE SharedMLP layer with tensor-map TMA staging (csrc/sa_dw_tma.cu): the stored (b,c,p) tensors
+ * land in shared memory as 128-byte-swizzled K-major tcgen05 operands, are turned into dY / relu(GN(y_prev)) and their
+ * TF32 residuals in place, and contracted over positions on the tensor cores (3xTF32).  Same arguments and result as
+ * ogc_sa_mlp_narrow_dw.  nsample == 64, m even, cout % 32 == 0 (<= 256), cin % 32 == 0 (<= 128). */
+OGC_API int ogc_sa_dw_tma(int b, int m, int nsample, int cout, int cin, const float *dz, const float *go, int go_ctotal,
+                          int go_coff, const unsigned char *sel, const float *y, const float *coef, const float *y_prev,
+                          const float *ss_prev, float *dw, void *stream);
+
 /* =====================================================================================
  * Mask head (csrc/mask_head.cu) -- replaces models/segnet_kitti.py:85-88:
  *   mask (b,n,k) = softmax_k( <feats[:,n]/max(|feats[:,n]|,1e-12), slots_hat[:,k]> * inv_temperature )

@@ -28,10 +28,11 @@ static inline EncodeTiledFn encode_fn() {
 }
 
 // Row-major fp32 matrix (outer rows of `inner` elements, contiguous), tiles of [box_outer][box_inner], no swizzle:
-// the tile lands in shared memory row-major, box_inner * 4 bytes per row.  inner * 4 must be a multiple of 16 and
+// the tile lands in shared memory row-major, box_inner * 4 bytes per row; with swizzle128 (box_inner * 4 == 128, destination
+// 1024-byte aligned) in the 128-byte-swizzled K-major layout a tcgen05 shared-memory descriptor reads directly.  inner * 4 must be a multiple of 16 and
 // `base` 16-byte aligned.  Returns false when the driver refuses.
 static inline bool make_2d_f32(CUtensorMap *map, const void *base, uint64_t inner, uint64_t outer, uint32_t box_inner,
-                               uint32_t box_outer) {
+                               uint32_t box_outer, bool swizzle128 = false) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     const cuuint64_t dims[2] = {inner, outer};
@@ -39,7 +40,8 @@ static inline bool make_2d_f32(CUtensorMap *map, const void *base, uint64_t inne
     const cuuint32_t box[2] = {box_inner, box_outer};
     const cuuint32_t estr[2] = {1, 1};
     return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 

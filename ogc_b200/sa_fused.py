@@ -58,6 +58,15 @@ def _chain_dx_ok(S, M, cout, rows, scatter):
             and rows % (16 if scatter else 32) == 0 and 8 * rows * cout <= 180 * 1024)   # resident W^T (hi + lo) fits one SM
 
 
+USE_DW_TMA = True     # dense-layer weight gradient with TMA-staged operands (csrc/sa_dw_tma.cu)
+DW_TMA_NARROW = False # ... also for SA level 1's 32 -> 32 layers (measured: the warp-per-centre kernel is faster there)
+
+
+def _dw_tma_ok(S, M, cin, cout):
+    return (USE_TC and USE_DW_TMA and S == 64 and M % 2 == 0 and cout % 32 == 0 and cout <= 256 and cin % 32 == 0 and cin <= 128
+            and (DW_TMA_NARROW or cin >= 64 or cout >= 64))
+
+
 DEBUG_KEEP = None     # diagnostics: a list that collects (layer, dz_prev, ab_prev, coef) of every backward
 STORE_Y = True      # stage 1: keep the pre-norm tensors for the per-layer backward kernels
 USE_CHAIN = False   # round-2 kernels (csrc/sa_chain_*.cu): positions on the MMA's M axis, layers chained through TMEM.
@@ -255,7 +264,12 @@ class _FusedSAMLP(Function):
             dw_nw = not gather and _narrow_ok(S, cin, cout)
             dw_tc = not dw_nw and _tc_dw_ok(S, cin, cout)
             dw_fn, dw_tag = (lib.ogc_sa_mlp_layer_dw_tc, "sa_mlp_dw_tc") if dw_tc else (lib.ogc_sa_mlp_layer_dw, "sa_mlp_dw")
-            if dw_nw:
+            if not gather and _dw_tma_ok(S, M, cin, cout):
+                with TIMER.span(f"sa_dw_tma[{cin}>{cout}]" if TIMER.detail else "sa_dw_tma", B * P * 4 * (2 * cout + cin), 2 * B * P * cin * cout):
+                    _lib.check(lib.ogc_sa_dw_tma(
+                        B, M, S, cout, cin, _p(dz), _p(go), cL, 0, _p(sel), _p(ys[l]), _p(coef), _p(ys[l - 1]),
+                        _p(sss[l - 1]), _p(dW), _st()), "ogc_sa_dw_tma")
+            elif dw_nw:
                 with TIMER.span(f"sa_mlp_dw_nw[{cin}>{cout}]" if TIMER.detail else "sa_mlp_dw_nw", B * P * 4 * (2 * cout + cin), 2 * B * P * cin * cout):
                     _lib.check(lib.ogc_sa_mlp_narrow_dw(
                         B, M, S, cout, cin, _p(dz), _p(go), cL, 0, _p(sel), _p(ys[l]), _p(coef), _p(ys[l - 1]),

@@ -22,6 +22,8 @@ if os.environ.get("CFGS"):
 sa_fused.USE_CHAIN = os.environ.get("CHAIN", "1") == "1"       # default here: the chained kernels
 sa_fused.STORE_Y = os.environ.get("STORE_Y", "1") == "1"
 sa_fused.USE_CHAIN_DX = {"0": False, "1": True}.get(os.environ.get("CHAIN_DX", "1"), os.environ.get("CHAIN_DX"))
+sa_fused.USE_DW_TMA = os.environ.get("DW_TMA", "1") == "1"
+sa_fused.DW_TMA_NARROW = os.environ.get("DW_TMA_NARROW", "0") == "1"
 fwd_only = os.environ.get("FWD_ONLY", "0") == "1"
 for name, N, M, Cf, w in cfgs:
     xyz = (torch.rand(B, N, 3, device="cuda") - 0.5) * 40

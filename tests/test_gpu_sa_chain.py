@@ -146,3 +146,37 @@ def test_chain_dx_matches_per_layer_kernels(b200, N, M, Cf, widths):
         rel = float((a - b).norm() / a.norm().clamp_min(1e-30))
         assert rel <= 2e-5, (name, rel)
         assert float((a - b).abs().max()) <= 1e-4 * float(a.abs().max()), (name, float((a - b).abs().max()))
+
+
+DW_SHAPES = [
+    (400, 100, 96, [64, 64, 128], False),       # SA2: 64 -> 128 (synthesised dz, one M block), 64 -> 64
+    (300, 70, 128, [128, 128, 256], False),     # SA3: 128 -> 256 (two M blocks, two stages), 128 -> 128
+    (1024, 512, 128, [128, 128, 128], False),   # many tiles per CTA
+    (512, 128, 3, [32, 32, 64], True),          # SA1's narrow layers through the same kernel (padded M)
+    (256, 64, 40, [32, 96, 160], False),        # 32 -> 96 dense, 96 -> 160 synthesised
+]
+
+
+@pytest.mark.parametrize("N,M,Cf,widths,narrow", DW_SHAPES)
+def test_dw_tma_matches_per_layer_kernels(b200, N, M, Cf, widths, narrow):
+    """ogc_sa_dw_tma against ogc_sa_mlp_layer_dw_tc / ogc_sa_mlp_narrow_dw: ONE forward, two backward passes.  The
+    operands' hi parts are truncated (by the tensor core) instead of rounded: products carry 2^-20 instead of 2^-22."""
+    from ogc_b200 import sa_fused
+    xyz, new_xyz, feat_pm, idx, mlp, layers = _setup(N, M, Cf, widths)
+    probe = torch.randn(3, widths[-1], M, device="cuda")
+    f = feat_pm.clone().requires_grad_(True)
+    out = sa_fused.fused_sa_mlp(xyz, new_xyz, f, idx, layers)
+    loss = (out * probe).sum()
+    wrt = [f] + list(mlp.parameters())
+    res, default, default_n = {}, sa_fused.USE_DW_TMA, sa_fused.DW_TMA_NARROW
+    for tma in (False, True):
+        sa_fused.USE_DW_TMA, sa_fused.DW_TMA_NARROW = tma, narrow
+        try:
+            res[tma] = [g.clone() for g in torch.autograd.grad(loss, wrt, retain_graph=True)]
+        finally:
+            sa_fused.USE_DW_TMA, sa_fused.DW_TMA_NARROW = default, default_n
+    names = ["dfeat"] + [n for n, _ in mlp.named_parameters()]
+    for name, a, b in zip(names, res[False], res[True]):
+        rel = float((a - b).norm() / a.norm().clamp_min(1e-30))
+        assert rel <= 2e-5, (name, rel)
+        assert float((a - b).abs().max()) <= 1e-4 * float(a.abs().max()), (name, float((a - b).abs().max()))

@@ -67,3 +67,21 @@ def test_a_operand_from_tensor_memory(n, k):
     e3 = float((run(2, n, k, 1, a, b).double() - ref).abs().max())
     e32 = float(((a @ b.t()).double() - ref).abs().max())
     assert e3 < 4 * e32 + 1e-6, (e3, e32)
+
+
+def test_tf32_operands_are_truncated():
+    """tcgen05.mma kind::tf32 ignores the 13 low mantissa bits of an fp32 operand (truncation toward zero) on every
+    operand path (shared-memory A, shared-memory B, tensor-memory A).  csrc/sa_dw_tma.cu relies on it: the raw fp32
+    value serves as the 'hi' operand and x - trunc(x) as the exact 'lo' operand of the 3xTF32 split."""
+    n, k = 32, 32
+    u = 2.0 ** -10
+    fr = torch.tensor([0.0, 0.25, 0.49, 0.5, 0.51, 0.75, 0.999], device="cuda")
+    for sign in (1.0, -1.0):
+        vals = sign * (1.0 + fr * u)
+        a = torch.zeros(128, k, device="cuda"); a[:len(fr), 0] = vals
+        b = torch.zeros(n, k, device="cuda"); b[0, 0] = 1.0
+        assert torch.equal(run(0, n, k, 0, a, b)[:len(fr), 0], torch.full_like(fr, sign))
+        assert torch.equal(run(2, n, k, 0, a, b)[:len(fr), 0], torch.full_like(fr, sign))
+        a2 = torch.zeros(128, k, device="cuda"); a2[0, 0] = 1.0
+        b2 = torch.zeros(n, k, device="cuda"); b2[:len(fr), 0] = vals
+        assert torch.equal(run(0, n, k, 0, a2, b2)[0, :len(fr)], torch.full_like(fr, sign))
