@@ -428,6 +428,14 @@ OGC_API int ogc_sa_mlp_narrow_dw(int b, int m, int nsample, int cout, int cin, c
                                  const float *coef, const float *y_prev, const float *ss_prev, float *dw,
                                  void *stream);
 
+/* Forward of a DENSE SharedMLP layer with tensor-map TMA staging (csrc/sa_fwd_tma.cu): weights stationary in tensor
+ * memory, relu(GN(y_prev)) formed in place in the TMA tile (MN-major tcgen05 operand), thread = output channel in the
+ * epilogue.  Outputs as the gather == 0 mode of ogc_sa_mlp_layer_fwd_tc; w is (cout, cin) row-major.
+ * nsample == 64, m even, cin % 32 == 0 (<= 128), cout % 32 == 0 (<= 256). */
+OGC_API int ogc_sa_fwd_tma(int b, int m, int nsample, int cin, int cout, int last, const float *y_prev, const float *ss_prev,
+                           const float *w, float *y, double *sums, float *ymax, float *ymin, unsigned char *amax,
+                           unsigned char *amin, void *stream);
+
 /* Weight gradient of a DENSE SharedMLP layer with tensor-map TMA staging (csrc/sa_dw_tma.cu): the stored (b,c,p) tensors
  * land in shared memory as 128-byte-swizzled K-major tcgen05 operands, are turned into dY / relu(GN(y_prev)) and their
  * TF32 residuals in place, and contracted over positions on the tensor cores (3xTF32).  Same arguments and result as

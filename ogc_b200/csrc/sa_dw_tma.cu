@@ -263,9 +263,9 @@ extern "C" int ogc_sa_dw_tma(int b, int m, int nsample, int cout, int cin, const
     CUtensorMap tm_y, tm_dz, tm_yp;
     memset(&tm_dz, 0, sizeof(tm_dz));
     const uint64_t p64 = static_cast<uint64_t>(q.P);
-    bool ok = tma::make_2d_f32(&tm_y, y, p64, static_cast<uint64_t>(b) * cout, kWin, cout, true);
-    if (ok && !synth) ok = tma::make_2d_f32(&tm_dz, dz, p64, static_cast<uint64_t>(b) * cout, kWin, cout, true);
-    if (ok) ok = tma::make_2d_f32(&tm_yp, y_prev, p64, static_cast<uint64_t>(b) * cin, kWin, cin, true);
+    bool ok = tma::make_2d_f32(&tm_y, y, p64, static_cast<uint64_t>(b) * cout, kWin, cout, 1);
+    if (ok && !synth) ok = tma::make_2d_f32(&tm_dz, dz, p64, static_cast<uint64_t>(b) * cout, kWin, cout, 1);
+    if (ok) ok = tma::make_2d_f32(&tm_yp, y_prev, p64, static_cast<uint64_t>(b) * cin, kWin, cin, 1);
     if (!ok) return OGC_ERR_UNSUPPORTED;
     int per_sample = kNumSMs / b;
     const int ntiles = q.P / 128;

@@ -67,6 +67,15 @@ def _dw_tma_ok(S, M, cin, cout):
             and (DW_TMA_NARROW or cin >= 64 or cout >= 64))
 
 
+USE_FWD_TMA = True    # dense-layer forward with the TMA-staged operand (csrc/sa_fwd_tma.cu)
+FWD_TMA_NARROW = False # ... also for SA level 1's 32 -> 32 layers (measured: the warp-per-centre kernel is faster there)
+
+
+def _fwd_tma_ok(S, M, cin, cout):
+    return (USE_TC and USE_FWD_TMA and S == 64 and M % 2 == 0 and cout % 32 == 0 and cout <= 256 and cin % 32 == 0 and cin <= 128
+            and (FWD_TMA_NARROW or cin >= 64 or cout >= 64))
+
+
 DEBUG_KEEP = None     # diagnostics: a list that collects (layer, dz_prev, ab_prev, coef) of every backward
 STORE_Y = True      # stage 1: keep the pre-norm tensors for the per-layer backward kernels
 USE_CHAIN = False   # round-2 kernels (csrc/sa_chain_*.cu): positions on the MMA's M axis, layers chained through TMEM.
@@ -184,11 +193,17 @@ class _FusedSAMLP(Function):
             else:
                 ymax = ymin = amax = amin = None
             flops_bytes = B * (4 * cout * P + (4 * cin * P if l else 4 * P + 12 * N + 4 * N * Cf))
-            use_nw = l > 0 and _narrow_ok(S, cin, cout)
-            use_tc = not use_nw and _tc_ok(S, cin, cout, l == 0)
-            tag = "sa_mlp_fwd_nw" if use_nw else "sa_mlp_fwd_tc" if use_tc else "sa_mlp_fwd"
+            use_tma = l > 0 and _fwd_tma_ok(S, M, cin, cout)
+            use_nw = not use_tma and l > 0 and _narrow_ok(S, cin, cout)
+            use_tc = not use_tma and not use_nw and _tc_ok(S, cin, cout, l == 0)
+            tag = "sa_fwd_tma" if use_tma else "sa_mlp_fwd_nw" if use_nw else "sa_mlp_fwd_tc" if use_tc else "sa_mlp_fwd"
             with TIMER.span(f"{tag}[{cin}>{cout}]" if TIMER.detail else tag, flops_bytes, 2 * B * P * cin * cout):
-                if use_nw:
+                if use_tma:
+                    w2d = W.detach().reshape(cout, cin).contiguous()
+                    _lib.check(lib.ogc_sa_fwd_tma(
+                        B, M, S, cin, cout, int(last), _p(y_prev), _p(ss_prev), _p(w2d), _p(y), _p(sums), _p(ymax), _p(ymin),
+                        _p(amax), _p(amin), _st()), "ogc_sa_fwd_tma")
+                elif use_nw:
                     w2d = W.detach().reshape(cout, cin).contiguous()
                     _lib.check(lib.ogc_sa_mlp_narrow_fwd(
                         B, M, S, cin, cout, int(last), _p(y_prev), _p(ss_prev), _p(w2d), _p(gamma.detach()), _p(y), _p(sums), _p(ymax),

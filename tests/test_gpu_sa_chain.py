@@ -180,3 +180,26 @@ def test_dw_tma_matches_per_layer_kernels(b200, N, M, Cf, widths, narrow):
         rel = float((a - b).norm() / a.norm().clamp_min(1e-30))
         assert rel <= 2e-5, (name, rel)
         assert float((a - b).abs().max()) <= 1e-4 * float(a.abs().max()), (name, float((a - b).abs().max()))
+
+
+@pytest.mark.parametrize("N,M,Cf,widths,narrow", DW_SHAPES)
+def test_fwd_tma_matches_per_layer_kernels(b200, N, M, Cf, widths, narrow):
+    """ogc_sa_fwd_tma against ogc_sa_mlp_layer_fwd_tc / ogc_sa_mlp_narrow_fwd: pooled output, stored pre-norm tensors,
+    GroupNorm scale / shift, arg-max bytes (ties / near-ties aside)."""
+    from ogc_b200 import sa_fused
+    xyz, new_xyz, feat_pm, idx, mlp, layers = _setup(N, M, Cf, widths)
+    saved, default, default_n = {}, sa_fused.USE_FWD_TMA, sa_fused.FWD_TMA_NARROW
+    for tma in (False, True):
+        sa_fused.USE_FWD_TMA, sa_fused.FWD_TMA_NARROW = tma, narrow
+        try:
+            out = sa_fused.fused_sa_mlp(xyz, new_xyz, feat_pm.clone().requires_grad_(True), idx, layers)
+        finally:
+            sa_fused.USE_FWD_TMA, sa_fused.FWD_TMA_NARROW = default, default_n
+        saved[tma] = [out.detach().clone()] + [t.clone() for t in out.grad_fn.saved_tensors[4:]]
+    assert len(saved[False]) == len(saved[True])
+    for i, (a, b) in enumerate(zip(saved[False], saved[True])):
+        assert a.shape == b.shape
+        if a.dtype == torch.uint8:
+            assert float((a != b).float().mean()) < 1e-3, i
+        else:
+            assert float((a - b).abs().max()) <= 2e-5 * max(1.0, float(a.abs().max())), (i, float((a - b).abs().max()))
