@@ -314,6 +314,8 @@ def main():
     ap.add_argument("--pairs", type=int, default=None, help="KITTI-SF pairs per GPU per step (default: the config's)")
     ap.add_argument("--no-aug", action="store_true")
     ap.add_argument("--eager", action="store_true", help="one launch per kernel instead of CUDA-graph replay")
+    ap.add_argument("--no-prefetch", action="store_true",
+                    help="do not announce the next batch to the trainer (first-level FPS inside the step instead of under the previous one)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-ext", action="store_true", help="skip timing the reference CUDA extension arm")
     args = ap.parse_args()
@@ -483,7 +485,10 @@ def main():
         s.record()
         last = None
         for i in range(steps):
-            last = step_fn(it0 + i, src[i % n_batches], aug_transform=aug)
+            if args.eager or args.no_prefetch:
+                last = step_fn(it0 + i, src[i % n_batches], aug_transform=aug)
+            else:       # the batch of the next call is known (a loader one batch ahead): its first-level FPS runs under this step
+                last = step_fn(it0 + i, src[i % n_batches], aug_transform=aug, next_batch=src[(i + 1) % n_batches])
         e.record()
         barrier()
         ms = s.elapsed_time(e)
@@ -497,7 +502,10 @@ def main():
     # one-launch-per-kernel path
     step_fn = trainer.train_step if args.eager else trainer.train_step_graphed
     for i in range(max(args.warmup, 3)):
-        step_fn(it0 + i, resident[i % n_batches], aug_transform=aug)
+        if args.eager or args.no_prefetch:
+            step_fn(it0 + i, resident[i % n_batches], aug_transform=aug)
+        else:
+            step_fn(it0 + i, resident[i % n_batches], aug_transform=aug, next_batch=resident[(i + 1) % n_batches])
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -567,7 +575,9 @@ def main():
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong" if cfg == "strong32" else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": seg_workload, "name": cfg, "parallelism": f"dp{world}",
-                       "launch": "eager" if args.eager else "one CUDA graph per step",
+                       "launch": "eager" if args.eager else "one CUDA graph per step" + (
+                           "" if args.no_prefetch else "; the NEXT batch's clouds are copied in and their first-level FPS "
+                           "centres sampled on a side stream of this step's graph (one copy and one FPS per step, as without it)"),
                        "l2": "per-step working set (GBs of activations) >> 126 MB L2; inputs cycle over 4 distinct batches"},
             "e2e": {"value": clouds_per_step / (ms_e2e * 1e-3), "unit": "clouds/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * len(last_dict)},

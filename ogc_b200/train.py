@@ -139,7 +139,7 @@ class SegTrainer:
         if float(hi - lo) != 0.0:
             raise RuntimeError("ogc_b200: replicas disagree on the parameters after the start-up broadcast")
 
-    def _step_body(self, pcs, flows, it, aug_transform, defer, allreduce=True):
+    def _step_body(self, pcs, flows, it, aug_transform, defer, allreduce=True, c1=None):
         """zero_grad -> forward -> loss -> backward -> NaN count -> all-reduce -> Adam launch (no host sync when
         `defer`).  pcs, flows: (b,t,N,3) on the device."""
         self.segnet.train()
@@ -147,7 +147,8 @@ class SegTrainer:
         b, t, n, _ = pcs.shape
         flat = pcs.view(b * t, n, 3)
         pcs_l = [pcs[:, i].contiguous() for i in range(t)]
-        centres, fp_nn = self._prefetch_geometry(flat, pcs_l) if self.overlap_geometry and flat.is_cuda else (None, None)
+        centres, fp_nn = (self._prefetch_geometry(flat, pcs_l, c1) if self.overlap_geometry and flat.is_cuda
+                          else (None, None))
         masks = self.segnet(flat, flat, centres, fp_nn).view(b, t, n, -1)
         if centres is not None and getattr(self, "_geo_join", None):
             # every side-stream product has been consumed through its event; join the streams themselves as well so
@@ -170,7 +171,7 @@ class SegTrainer:
             dist.all_reduce(self.opt.flat_g_ext)          # the step's only collective: grads + NaN counter
         return loss_dict
 
-    def _prefetch_geometry(self, flat, pcs_l):
+    def _prefetch_geometry(self, flat, pcs_l, c1=None):
         """Everything that depends on the coordinates alone, arranged so that the latency-bound FPS chain (one CTA
         per cloud: 16 of 148 SMs busy for ~1.8 ms at KITTI-SF sizes) runs on a side stream UNDERNEATH the loss
         neighbourhoods (k-NN + ball query on 8192 x 8192, thousands of small CTAs that flow around it).  Fork / join
@@ -203,7 +204,9 @@ class SegTrainer:
                     t._ogc_ready = torch.cuda.Event()
                     t._ogc_ready.record(stream)
                     return t
-                centres = [ready(sa[0].sample(flat), side)]
+                # c1: the first level's centres when they were sampled during the PREVIOUS step (train_step_graphed with
+                # next_batch): the 1.3 ms single-wave FPS of the input clouds leaves the critical path altogether
+                centres = [ready(sa[0].sample(flat), side) if c1 is None else ready(c1, side)]
                 with torch.cuda.stream(third):
                     third.wait_event(centres[0]._ogc_ready)
                     nn0 = be.three_nn(flat.contiguous(), centres[0])
@@ -218,14 +221,23 @@ class SegTrainer:
                     fp_nn.append(nn_i)
         specs = losses.smooth_specs(self.criterion.smooth_loss) if hasattr(self.criterion, "smooth_loss") else None
         losses.NEIGHBOUR_CACHE.clear()
+        nbs = None
         if specs:
-            for pc in pcs_l:
-                handle = losses.tag_cloud(pc)
-                for kind, k, radius in specs:
-                    losses.NEIGHBOUR_CACHE[(handle, kind, k, radius)] = losses.neighbourhood(be, kind, k, radius, pc)
+            # the loss neighbourhoods are consumed after the network's forward: with the first-level centres prefetched
+            # (c1) nothing hides them any more, so they get a stream of their own and are joined before the criterion
+            if c1 is not None and third is not None:
+                if getattr(self, "_nb_stream", None) is None:
+                    self._nb_stream = torch.cuda.Stream()
+                nbs = self._nb_stream
+                nbs.wait_stream(main)
+            with torch.cuda.stream(nbs if nbs is not None else main):
+                for pc in pcs_l:
+                    handle = losses.tag_cloud(pc)
+                    for kind, k, radius in specs:
+                        losses.NEIGHBOUR_CACHE[(handle, kind, k, radius)] = losses.neighbourhood(be, kind, k, radius, pc)
         if third is None:                 # composed path: plain join
             main.wait_stream(side)
-        self._geo_join = (side, third)
+        self._geo_join = (side, third, nbs)
         return centres, fp_nn
 
     def train_step(self, it, batch, aug_transform=False):
@@ -255,6 +267,28 @@ class SegTrainer:
         g = {"pcs": torch.zeros(shape, dtype=torch.float32, device=dev),
              "flows": torch.zeros(shape, dtype=torch.float32, device=dev)}
         g["pcs"].copy_(self._last_inputs[0]); g["flows"].copy_(self._last_inputs[1])
+        prefetch = key[-1]
+        if prefetch:
+            # software pipeline across steps: this step's graph samples the first-level centres of the NEXT step's clouds
+            # on a side stream (a function of the coordinates alone: same kernel, same input, same result as sampling
+            # them inside the next step), and starts from the centres the previous step left in c1_next
+            sa0 = self.segnet.SA_modules[0]
+            g["next_pcs"] = g["pcs"].clone()
+            g["c1_cur"] = sa0.sample(g["pcs"].view(-1, shape[2], 3))
+            g["c1_next"] = g["c1_cur"].clone()
+            g["fps_stream"] = torch.cuda.Stream()
+
+        def body(allreduce):
+            if not prefetch:
+                return self._step_body(g["pcs"], g["flows"], it, aug_transform, defer=True, allreduce=allreduce)
+            main = torch.cuda.current_stream()
+            g["c1_cur"].copy_(g["c1_next"])
+            g["fps_stream"].wait_stream(main)
+            with torch.cuda.stream(g["fps_stream"]):
+                g["c1_next"].copy_(self.segnet.SA_modules[0].sample(g["next_pcs"].view(-1, shape[2], 3)))
+            d = self._step_body(g["pcs"], g["flows"], it, aug_transform, defer=True, allreduce=allreduce, c1=g["c1_cur"])
+            main.wait_stream(g["fps_stream"])
+            return d
         opt = self.opt
         snap = [x.clone() for x in (opt.flat_p, opt.m, opt.v, opt.state)]
         side = torch.cuda.Stream()
@@ -263,7 +297,7 @@ class SegTrainer:
             for _ in range(2):
                 # no collective in the warm-up: a rank-local re-capture (e.g. a ragged last batch on one rank) must not
                 # change the number of all-reduces the ranks issue
-                self._step_body(g["pcs"], g["flows"], it, aug_transform, defer=True, allreduce=False)
+                body(False)
                 opt.launch_step(1.0 / self.world_size)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
@@ -276,7 +310,7 @@ class SegTrainer:
         multi = self.world_size > 1
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            d = self._step_body(g["pcs"], g["flows"], it, aug_transform, defer=True, allreduce=False)
+            d = body(False)
             g["keys"] = d["_keys"]
             g["values"] = d["_values"]
             g["host"] = host[:len(d["_keys"])]
@@ -292,16 +326,33 @@ class SegTrainer:
         torch.cuda.empty_cache()
         return g
 
-    def train_step_graphed(self, it, batch, aug_transform=False):
+    def train_step_graphed(self, it, batch, aug_transform=False, next_batch=None):
         """Same semantics as train_step; the device work is a single CUDA-graph launch.  Re-captures when the
-        batch shape or the active loss weights (start_steps schedule) change."""
+        batch shape or the active loss weights (start_steps schedule) change.
+        next_batch: the batch of the FOLLOWING call, if the caller knows it (a data loader one batch ahead).  Its clouds
+        are copied in now and their first-level FPS centres are sampled on a side stream of this step's graph; the
+        following call then starts its network immediately.  The call after a `next_batch=None` call (or with another
+        batch than announced) samples its centres eagerly first, so results never depend on the hint."""
         if not hasattr(self, "_graphs"):
             self._graphs = {}
         pcs, _, flows, _ = batch
-        key = (tuple(pcs.shape), bool(aug_transform), self._loss_weights(it))
+        self._prefetch_mode = getattr(self, "_prefetch_mode", False) or next_batch is not None
+        key = (tuple(pcs.shape), bool(aug_transform), self._loss_weights(it), self._prefetch_mode)
         self._last_inputs = (pcs, flows)
+        fresh = key not in self._graphs
         g = self._graphs.get(key) or self._capture(key, it, tuple(pcs.shape), aug_transform)
-        g["pcs"].copy_(pcs, non_blocking=True)             # H2D from pinned memory (or D2D when resident)
+        if self._prefetch_mode:
+            if not fresh and g.get("announced") is pcs:
+                g["pcs"].copy_(g["next_pcs"])              # already on the device, centres in c1_next
+            else:
+                g["pcs"].copy_(pcs, non_blocking=True)
+                g["c1_next"].copy_(self.segnet.SA_modules[0].sample(g["pcs"].view(-1, pcs.shape[2], 3)))
+            g["announced"] = None
+            if next_batch is not None and tuple(next_batch[0].shape) == tuple(pcs.shape):
+                g["next_pcs"].copy_(next_batch[0], non_blocking=True)
+                g["announced"] = next_batch[0]
+        else:
+            g["pcs"].copy_(pcs, non_blocking=True)         # H2D from pinned memory (or D2D when resident)
         g["flows"].copy_(flows, non_blocking=True)
         self.opt.set_lr(self.opt.lr * lr_curve(it, self.global_batch_size, **self.sched))
         g["graph"].replay()

@@ -32,6 +32,29 @@ def test_graphed_step_equals_eager_step(b200):
     assert float(diff.max()) < 3e-3 and float(diff.mean()) < 2e-5
 
 
+def test_cross_step_fps_prefetch_changes_nothing(b200):
+    """train_step_graphed(..., next_batch=...) samples the next step's first-level FPS centres under the current step.
+    Same kernel, same input: the centres are bit-identical, so the steps must match a run without the hint (up to the
+    atomically ordered sums both runs have); a wrong or missing announcement falls back to sampling eagerly."""
+    from ogc_b200 import data
+    batches = [data.make_batch(40 + i, 2, 1024, aug=True) for i in range(4)]
+    a, p = _trainer(), _trainer()
+    hints = [batches[1], batches[2], None, None]               # announced, announced, none (-> eager sampling), none
+    for i, batch in enumerate(batches):
+        da = a.train_step_graphed(5000 + i, batch, aug_transform=True)
+        dp = p.train_step_graphed(5000 + i, batch, aug_transform=True, next_batch=hints[i])
+        for k in ("dynamic", "smooth", "invariance", "entropy", "rank", "sum"):
+            assert abs(da[k] - dp[k]) <= 2e-4 * max(1.0, abs(da[k])), (i, k, da[k], dp[k])
+    # the centres the prefetching graph used for its last step are the FPS centres of that step's clouds
+    g = next(iter(p._graphs.values()))
+    flat = batches[3][0].cuda().view(-1, 1024, 3)
+    assert torch.equal(g["c1_cur"], p.segnet.SA_modules[0].sample(flat))
+    # a WRONG announcement (another batch arrives than the one announced) must not be used
+    p.train_step_graphed(5004, batches[0], aug_transform=True, next_batch=batches[1])
+    p.train_step_graphed(5005, batches[2], aug_transform=True)
+    assert torch.equal(g["c1_cur"], p.segnet.SA_modules[0].sample(batches[2][0].cuda().view(-1, 1024, 3)))
+
+
 def test_device_hungarian_matches_scipy(b200):
     from scipy.optimize import linear_sum_assignment
     rng = np.random.default_rng(0)
