@@ -436,6 +436,16 @@ OGC_API int ogc_sa_fwd_tma(int b, int m, int nsample, int cin, int cout, int las
                            const float *w, float *y, double *sums, float *ymax, float *ymin, unsigned char *amax,
                            unsigned char *amin, void *stream);
 
+/* Input gradient of a DENSE SharedMLP layer, channel-major with tensor-map TMA staging (csrc/sa_dx_tma.cu): the dense
+ * mode of ogc_sa_mlp_layer_dx_tc (same results).  W^T stationary in tensor memory, dY formed in place in the TMA tiles of
+ * y / dz (MN-major operand), thread = input channel in the epilogue, TMA store of dz_prev.  cout == 256 runs as two
+ * launches over halves of the contraction.  nsample == 64, rows % 32 == 0 (<= 128), cout % 32 == 0 (<= 128, or 256). */
+OGC_API int ogc_sa_dx_tma(int b, int m, int nsample, int cout, int cin_full, int row_off, int rows, const float *dz,
+                          const float *go, int go_ctotal, int go_coff, const unsigned char *sel, const float *y,
+                          const float *coef, const float *w, const float *y_prev, const float *ss_prev,
+                          const float *mean_rstd_prev, const float *gamma_prev, float *dz_prev, double *ab_prev,
+                          float *dgamma_prev, float *dbeta_prev, void *stream);
+
 /* Weight gradient of a DENSE SharedMLP layer with tensor-map TMA staging (csrc/sa_dw_tma.cu): the stored (b,c,p) tensors
  * land in shared memory as 128-byte-swizzled K-major tcgen05 operands, are turned into dY / relu(GN(y_prev)) and their
  * TF32 residuals in place, and contracted over positions on the tensor cores (3xTF32).  Same arguments and result as

@@ -67,6 +67,7 @@ SIGNATURES = {
     "ogc_pw_mlp_input_grad": [_I] * 6 + [_P] * 5 + [_I, _I, _P],
     "ogc_sa_mlp_narrow_fwd": [_I] * 6 + [_P] * 11,
     "ogc_sa_mlp_narrow_dx": [_I] * 5 + [_P, _P, _I, _I] + [_P] * 13,
+    "ogc_sa_dx_tma": [_I] * 7 + [_P, _P, _I, _I] + [_P] * 13,
     "ogc_sa_fwd_tma": [_I] * 6 + [_P] * 10,
     "ogc_sa_dw_tma": [_I] * 5 + [_P, _P, _I, _I] + [_P] * 7,
     "ogc_sa_mlp_narrow_dw": [_I] * 5 + [_P, _P, _I, _I] + [_P] * 7,

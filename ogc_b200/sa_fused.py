@@ -76,6 +76,17 @@ def _fwd_tma_ok(S, M, cin, cout):
             and (FWD_TMA_NARROW or cin >= 64 or cout >= 64))
 
 
+USE_DX_TMA = "auto"   # dense input gradient in the channel-major TMA style (csrc/sa_dx_tma.cu): True = every dense layer,
+                      # "synth" = only the last layer (dz synthesised from the pooled gradient), "auto" = the last layer and the
+                      # 128-wide dense layers (measured: 64 -> 64 is faster in the positions-on-M kernel), False = never
+
+
+def _dx_tma_ok(S, cout, rows, synth):
+    if not (USE_TC and USE_DX_TMA) or (USE_DX_TMA == "synth" and not synth) or (USE_DX_TMA == "auto" and not synth and cout < 128):
+        return False
+    return S == 64 and rows % 32 == 0 and rows <= 128 and cout % 32 == 0 and (cout <= 128 or cout == 256)
+
+
 DEBUG_KEEP = None     # diagnostics: a list that collects (layer, dz_prev, ab_prev, coef) of every backward
 STORE_Y = True      # stage 1: keep the pre-norm tensors for the per-layer backward kernels
 USE_CHAIN = False   # round-2 kernels (csrc/sa_chain_*.cu): positions on the MMA's M axis, layers chained through TMEM.
@@ -312,6 +323,13 @@ class _FusedSAMLP(Function):
                             B, M, S, cout, cprev, _p(dz), _p(go), cL, 0, _p(sel), _p(ys[l]), _p(coef), _p(w2d),
                             _p(ys[l - 1]), _p(sss[l - 1]), _p(mrs[l - 1]), _p(params[3 * (l - 1) + 1]), _p(dz_prev),
                             _p(ab_prev), _p(dgamma_prev), _p(dbeta_prev), _st()), "ogc_sa_mlp_narrow_dx")
+                elif _dx_tma_ok(S, cout, cprev, dz is None):
+                    with TIMER.span(f"sa_dx_tma[{cout}>{cprev}]" if TIMER.detail else "sa_dx_tma", B * P * 4 * (2 * cout + 2 * cprev), 2 * B * P * cout * cprev):
+                        _lib.check(lib.ogc_sa_dx_tma(
+                            B, M, S, cout, cin, 0, cprev, _p(dz), _p(go), cL, 0, _p(sel), _p(ys[l]), _p(coef), _p(w2d),
+                            _p(ys[l - 1]), _p(sss[l - 1]), _p(mrs[l - 1]), _p(params[3 * (l - 1) + 1]), _p(dz_prev),
+                            _p(ab_prev), _p(dgamma_prev), _p(dbeta_prev), _st()), "ogc_sa_dx_tma")
+                    be.launches += 1 if cout > 128 else 0
                 elif _chain_dx_ok(S, M, cout, cprev, False) or (cprev % 64 == 0 and _chain_dx_ok(S, M, cout, cprev // 2, False)):
                     # a layer whose resident W^T (hi + lo) exceeds one SM runs as two launches of half the output channels
                     nblk = 1 if _chain_dx_ok(S, M, cout, cprev, False) else 2

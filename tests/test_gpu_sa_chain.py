@@ -203,3 +203,29 @@ def test_fwd_tma_matches_per_layer_kernels(b200, N, M, Cf, widths, narrow):
             assert float((a != b).float().mean()) < 1e-3, i
         else:
             assert float((a - b).abs().max()) <= 2e-5 * max(1.0, float(a.abs().max())), (i, float((a - b).abs().max()))
+
+
+@pytest.mark.parametrize("mode", [True, "synth"])
+@pytest.mark.parametrize("N,M,Cf,widths,narrow", DW_SHAPES)
+def test_dx_tma_matches_per_layer_kernels(b200, N, M, Cf, widths, narrow, mode):
+    """ogc_sa_dx_tma against the per-layer input-gradient kernels: ONE forward, two backward passes."""
+    from ogc_b200 import sa_fused
+    xyz, new_xyz, feat_pm, idx, mlp, layers = _setup(N, M, Cf, widths)
+    probe = torch.randn(3, widths[-1], M, device="cuda")
+    f = feat_pm.clone().requires_grad_(True)
+    out = sa_fused.fused_sa_mlp(xyz, new_xyz, f, idx, layers)
+    loss = (out * probe).sum()
+    wrt = [f] + list(mlp.parameters())
+    res, d_tma, d_chain, d_nw = {}, sa_fused.USE_DX_TMA, sa_fused.USE_CHAIN_DX, sa_fused.USE_NARROW
+    for new in (False, True):
+        sa_fused.USE_DX_TMA, sa_fused.USE_CHAIN_DX = (mode if new else False), False
+        sa_fused.USE_NARROW = d_nw and not (new and narrow)      # route SA1's narrow layers through the new kernel as well
+        try:
+            res[new] = [g.clone() for g in torch.autograd.grad(loss, wrt, retain_graph=True)]
+        finally:
+            sa_fused.USE_DX_TMA, sa_fused.USE_CHAIN_DX, sa_fused.USE_NARROW = d_tma, d_chain, d_nw
+    names = ["dfeat"] + [n for n, _ in mlp.named_parameters()]
+    for name, a, b in zip(names, res[False], res[True]):
+        rel = float((a - b).norm() / a.norm().clamp_min(1e-30))
+        assert rel <= 2e-5, (name, rel)
+        assert float((a - b).abs().max()) <= 1e-4 * float(a.abs().max()), (name, float((a - b).abs().max()))
