@@ -255,27 +255,30 @@ sa_dx_tma_kernel(const __grid_constant__ Params q, const __grid_constant__ CUten
                 if (q.final) mbar_arrive(&bar_ypfree[(s - 1) % NS]);
             }
             if (!q.final) asm volatile("bar.sync 3, %0;" ::"r"(kEpi) : "memory");      // staging reuse without the loader's hand-shake
+            float v[64];
+            if (prow) {                                  // the first half's sums: requested BEFORE the wait for this tile's MMAs
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float4 o = __ldg(reinterpret_cast<const float4 *>(prow + p0) + j);
+                    v[4 * j] = o.x; v[4 * j + 1] = o.y; v[4 * j + 2] = o.z; v[4 * j + 3] = o.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 64; ++j) v[j] = 0.f;
+            }
             mbar_wait(&bar_acc[buf], (s >> 1) & 1);
             tc::fence_after_sync();
-            float v[64];
             {
                 float h[32];
                 tc::tmem_ld32(trow + static_cast<uint32_t>(buf * kN), h);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = h[j];
+                for (int j = 0; j < 32; ++j) v[j] += h[j];
                 tc::tmem_ld32(trow + static_cast<uint32_t>(buf * kN + 32), h);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[32 + j] = h[j];
+                for (int j = 0; j < 32; ++j) v[32 + j] += h[j];
             }
             tc::fence_before_sync();
             mbar_arrive(&bar_accfree[buf]);
-            if (prow) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float4 o = __ldg(reinterpret_cast<const float4 *>(prow + p0) + j);
-                    v[4 * j] += o.x; v[4 * j + 1] += o.y; v[4 * j + 2] += o.z; v[4 * j + 3] += o.w;
-                }
-            }
             float s0 = 0.f, s1 = 0.f;
             if (q.final) mbar_wait(&bar_ypfull[st], (s / NS) & 1);
 #pragma unroll

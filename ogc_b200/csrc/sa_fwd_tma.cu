@@ -20,8 +20,8 @@
 namespace ogc {
 namespace fwt {
 
-constexpr int kEpiWarps = 4, kEpi = kEpiWarps * 32;
-constexpr int kSplitWarp0 = kEpiWarps, kSplitWarps = 8, kSplit = kSplitWarps * 32;
+constexpr int kEpiWarps = 8, kEpi = kEpiWarps * 32, kEpiGroup = 128;     // two epilogue groups of 4 warps alternate tiles
+constexpr int kSplitWarp0 = kEpiWarps, kSplitWarps = 4, kSplit = kSplitWarps * 32;
 constexpr int kMmaWarp = kSplitWarp0 + kSplitWarps, kLoadWarp = kMmaWarp + 1;
 constexpr int kThreads = (kLoadWarp + 1) * 32;
 constexpr int kMaxStages = 8;
@@ -58,7 +58,7 @@ sa_fwd_tma_kernel(const __grid_constant__ Params q, const __grid_constant__ CUte
     if (warp == kMmaWarp) tc::tmem_alloc(&tmem_base_s, 512);
     if (tid == 0) {
         for (int i = 0; i < kMaxStages; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_ready[i], kSplit); mbar_init(&bar_free[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc[i], 1); mbar_init(&bar_accfree[i], kEpi); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc[i], 1); mbar_init(&bar_accfree[i], kEpiGroup); }
         mbar_fence_init();
     }
     if (tid < kGnGroups * 2) gs[tid] = 0.0;
@@ -71,7 +71,7 @@ sa_fwd_tma_kernel(const __grid_constant__ Params q, const __grid_constant__ CUte
     const uint32_t col_acc = static_cast<uint32_t>(2 * Cin);        // two accumulators of N columns behind the weights
     auto tile_of = [&](int u) { return static_cast<int>(blockIdx.x) + u * static_cast<int>(gridDim.x); };
 
-    if (warp < kEpiWarps) {
+    if (warp < 4) {
         // ---- stationary operand: W[co][:] hi / lo into tensor memory, lane = output channel ----
         const int co = warp * 32 + lane;
         const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
@@ -88,8 +88,8 @@ sa_fwd_tma_kernel(const __grid_constant__ Params q, const __grid_constant__ CUte
         }
         tc::fence_before_sync();
     }
-    if (warp < kEpiWarps || warp == kMmaWarp)
-        asm volatile("bar.sync 2, %0;" ::"r"(kEpi + 32) : "memory");  // epilogue warps + the MMA warp: weights are in place
+    if (warp < 4 || warp == kMmaWarp)
+        asm volatile("bar.sync 2, %0;" ::"r"(kEpiGroup + 32) : "memory");  // first epilogue group + the MMA warp: weights are in place
 
     if (warp == kLoadWarp) {
         // ============================================ TMA loader ============================================
@@ -136,7 +136,7 @@ sa_fwd_tma_kernel(const __grid_constant__ Params q, const __grid_constant__ CUte
             const int st = s % NS;
             uint8_t *base = smem + static_cast<size_t>(st) * q.stage_bytes;
             mbar_wait(&bar_full[st], (s / NS) & 1);
-            for (int r = r0; r < Cin; r += 32) {
+            for (int r = r0; r < Cin; r += kSplit / 8) {
                 const float2 ss = tab_ss[r];
                 for (int j = 0; j < NB; ++j) {
                     const uint32_t off = static_cast<uint32_t>(j) * q.blk_bytes + static_cast<uint32_t>(r) * 128u + static_cast<uint32_t>(q4) * 16u;
@@ -154,19 +154,19 @@ sa_fwd_tma_kernel(const __grid_constant__ Params q, const __grid_constant__ CUte
     }
     if (warp < kEpiWarps) {
         // ============================================ epilogue: thread = output channel ============================================
-        const int co = warp * 32 + lane;
+        const int eg = warp >> 2, ngroups = q.nout;      // group eg takes the tiles s % ngroups == eg (its own accumulator + staging buffer)
+        const int co = (warp & 3) * 32 + lane;
         const bool valid = co < C;
-        const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + col_acc;
+        const bool leader = (warp & 3) == 0 && lane == 0;
+        const uint32_t trow = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + col_acc;
         double dsum = 0.0, dsq = 0.0;
         const size_t row = static_cast<size_t>(b) * q.Ctot + q.co_off + co;
-        for (int s = 0; s < n_my; ++s) {
+        for (int s = eg; s < n_my && eg < ngroups; s += ngroups) {
             const int buf = s & 1;
             const int p0 = tile_of(s) * N;
-            uint8_t *obuf = smem + q.off_out + static_cast<size_t>(s % q.nout) * q.out_bytes;
-            if (tid == 0) {                     // the TMA stores that read this staging buffer have finished reading it
-                if (q.nout == 2) tma::store_wait_read<1>(); else tma::store_wait_read<0>();
-            }
-            asm volatile("bar.sync 3, %0;" ::"r"(kEpi) : "memory");
+            uint8_t *obuf = smem + q.off_out + static_cast<size_t>(eg) * q.out_bytes;
+            if (leader) tma::store_wait_read<0>();       // this group's previous TMA store has finished reading the staging buffer
+            asm volatile("bar.sync %0, %1;" ::"r"(3 + eg), "r"(kEpiGroup) : "memory");
             mbar_wait(&bar_acc[buf], (s >> 1) & 1);
             tc::fence_after_sync();
             for (int cen = 0; cen < N / 64; ++cen) {
@@ -213,14 +213,14 @@ sa_fwd_tma_kernel(const __grid_constant__ Params q, const __grid_constant__ CUte
                 }
             }
             tc::fence_proxy_async();            // generic writes of the staging tile -> the TMA store's reads
-            asm volatile("bar.sync 3, %0;" ::"r"(kEpi) : "memory");
-            if (tid == 0) {
+            asm volatile("bar.sync %0, %1;" ::"r"(3 + eg), "r"(kEpiGroup) : "memory");
+            if (leader) {
                 for (int j = 0; j < NB; ++j)
                     tma::store_2d(&tm_y, p0 + 32 * j, b * q.Ctot + q.co_off, obuf + static_cast<size_t>(j) * (128u * 128u));
                 tma::store_commit();
             }
         }
-        if (tid == 0) tma::store_wait_all();
+        if (leader) tma::store_wait_all();
         if (valid && n_my > 0) {
             const int g = (q.co_off + co) / (q.Ctot / kGnGroups);
             atomicAdd(&gs[2 * g], dsum);
