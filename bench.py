@@ -448,6 +448,19 @@ def main():
                     "e2e": {"value": batch / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                             "d2h_bytes_per_step": 4 * len(last)},
                     "roofline": None, "loss": last}
+            # the reference's DEFAULT numerics run its 1x1 convolutions in TF32 (cudnn.allow_tf32); ours are fp32 matmuls for
+            # the 1e-4 parity.  The same step with TF32 matmuls allowed (the reference's default precision class), labelled:
+            del step
+            torch.cuda.empty_cache()
+            torch.backends.cuda.matmul.allow_tf32 = True
+            try:
+                step_tf32, _ = flow_step_fn(npoint, batch, iters, device)
+                ms_tf32, _ = time_cuda(step_tf32, args.steps, max(args.warmup, 3))
+                line["tf32_matmul_like_reference_default"] = {"value": batch / (ms_tf32 * 1e-3), "unit": "pairs/s", "ms_per_step": ms_tf32,
+                                                              "note": "torch.backends.cuda.matmul.allow_tf32 = True: not the parity configuration"}
+                del step_tf32
+            finally:
+                torch.backends.cuda.matmul.allow_tf32 = False
             if not args.no_ref_ext:
                 ref = ref_arm("flow", "--npoint", npoint, "--batch", batch, "--iters", iters, "--steps", 10, "--warmup", 3)
                 if "value" in ref:

@@ -7,7 +7,7 @@
 // this is a restatement of that published algorithm INCLUDING its tie-breaking (columns scanned through the
 // `remaining` list that starts in descending order; among equal reduced costs an unassigned column wins),
 // because empty slots make all-zero IoU rows -- ties are the common case.  The port is checked against scipy
-// on tie-heavy matrices in tests/test_lsap.py (host twin) and tests/test_gpu_losses.py (device).
+// on tie-heavy matrices in tests/test_lsap.py (host twin) and tests/test_gpu_step.py::test_device_hungarian_matches_scipy (device).
 #pragma once
 #include <math.h>
 
