@@ -33,6 +33,15 @@ def supported(channels):
     return all(c % 16 == 0 and c <= 256 for c in channels[1:])
 
 
+USE_TMA = True      # dense layers (l >= 1) through the TMA-staged tensor-core kernels of the SA block (csrc/sa_*_tma.cu): the
+                    # n points of a cloud are n / 64 "centres" of 64 positions to them
+
+
+def _tma_ok(n, cin, cout):
+    from . import sa_fused
+    return (USE_TMA and sa_fused.USE_TC and n % 128 == 0 and cin % 32 == 0 and cin <= 128 and cout % 32 == 0 and cout <= 128)
+
+
 class _FusedFP(Function):
     @staticmethod
     def forward(ctx, unknown, known, skip, known_feats, nn_d2, nn_idx, *params):
@@ -62,8 +71,13 @@ class _FusedFP(Function):
             y = torch.empty(B, cout, n, **f32)
             sums = torch.zeros(B, 4, 2, dtype=torch.float64, device=dev)
             with TIMER.span(f"fp_mlp_fwd[{cin}>{cout}]" if TIMER.detail else "fp_mlp_fwd", B * 4 * n * (cin + cout)):
-                _lib.check(lib.ogc_pw_mlp_layer_fwd(B, n, cin, cout, _p(a_prev), _p(ss_prev), _p(wt), _p(y), _p(sums),
-                                                    _st()), "ogc_pw_mlp_layer_fwd")
+                if l > 0 and _tma_ok(n, cin, cout):
+                    w2d = W.detach().reshape(cout, cin).contiguous()
+                    _lib.check(lib.ogc_sa_fwd_tma(B, n // 64, 64, cin, cout, 0, _p(a_prev), _p(ss_prev), _p(w2d), _p(y), _p(sums),
+                                                  None, None, None, None, _st()), "ogc_sa_fwd_tma")
+                else:
+                    _lib.check(lib.ogc_pw_mlp_layer_fwd(B, n, cin, cout, _p(a_prev), _p(ss_prev), _p(wt), _p(y), _p(sums),
+                                                        _st()), "ogc_pw_mlp_layer_fwd")
             ss = torch.empty(B, cout, 2, **f32)
             mr = torch.empty(B, 4, 2, **f32)
             _lib.check(lib.ogc_gn_finalize(B, cout, (cout // 4) * n, _p(sums), _p(gamma.detach()), _p(beta.detach()),
@@ -114,9 +128,13 @@ class _FusedFP(Function):
             a_prev = ys[l - 1] if l else x
             ss_prev = sss[l - 1] if l else None
             with TIMER.span(f"fp_mlp_dw[{cin}>{cout}]" if TIMER.detail else "fp_mlp_dw", B * n * 4 * (2 * cout + cin)):
-                _lib.check(lib.ogc_sa_mlp_layer_dw(B, 0, n, 1, cout, cin, 0, _p(dz), None, 0, 0, None, _p(ys[l]), _p(coef),
-                                                   _p(a_prev), _p(ss_prev), None, None, None, None, _p(dW), _st()),
-                           "ogc_sa_mlp_layer_dw")
+                if l > 0 and _tma_ok(n, cin, cout):
+                    _lib.check(lib.ogc_sa_dw_tma(B, n // 64, 64, cout, cin, _p(dz), None, 0, 0, None, _p(ys[l]), _p(coef),
+                                                 _p(a_prev), _p(ss_prev), _p(dW), _st()), "ogc_sa_dw_tma")
+                else:
+                    _lib.check(lib.ogc_sa_mlp_layer_dw(B, 0, n, 1, cout, cin, 0, _p(dz), None, 0, 0, None, _p(ys[l]), _p(coef),
+                                                       _p(a_prev), _p(ss_prev), None, None, None, None, _p(dW), _st()),
+                               "ogc_sa_mlp_layer_dw")
             be.launches += 2
             grads[3 * l] = dW.view_as(W)
             if l > 0:
@@ -126,10 +144,16 @@ class _FusedFP(Function):
                 dgamma_prev = torch.zeros(cprev, **f32)
                 dbeta_prev = torch.zeros(cprev, **f32)
                 with TIMER.span(f"fp_mlp_dx[{cout}>{cprev}]" if TIMER.detail else "fp_mlp_dx", B * n * 4 * (2 * cout + 2 * cprev)):
-                    _lib.check(lib.ogc_sa_mlp_layer_dx(
-                        B, 0, n, 1, cout, cin, 0, cprev, _p(dz), None, 0, 0, None, _p(ys[l]), _p(coef), _p(w2d),
-                        _p(ys[l - 1]), _p(sss[l - 1]), _p(mrs[l - 1]), _p(params[3 * (l - 1) + 1]), _p(dz_prev),
-                        _p(ab_prev), _p(dgamma_prev), _p(dbeta_prev), None, None, 0, 0, _st()), "ogc_sa_mlp_layer_dx")
+                    if _tma_ok(n, cprev, cout):
+                        _lib.check(lib.ogc_sa_dx_tma(
+                            B, n // 64, 64, cout, cin, 0, cprev, _p(dz), None, 0, 0, None, _p(ys[l]), _p(coef), _p(w2d),
+                            _p(ys[l - 1]), _p(sss[l - 1]), _p(mrs[l - 1]), _p(params[3 * (l - 1) + 1]), _p(dz_prev),
+                            _p(ab_prev), _p(dgamma_prev), _p(dbeta_prev), _st()), "ogc_sa_dx_tma")
+                    else:
+                        _lib.check(lib.ogc_sa_mlp_layer_dx(
+                            B, 0, n, 1, cout, cin, 0, cprev, _p(dz), None, 0, 0, None, _p(ys[l]), _p(coef), _p(w2d),
+                            _p(ys[l - 1]), _p(sss[l - 1]), _p(mrs[l - 1]), _p(params[3 * (l - 1) + 1]), _p(dz_prev),
+                            _p(ab_prev), _p(dgamma_prev), _p(dbeta_prev), None, None, 0, 0, _st()), "ogc_sa_mlp_layer_dx")
                 be.launches += 1
                 dz, ab, dgamma, dbeta = dz_prev, ab_prev, dgamma_prev, dbeta_prev
             else:

@@ -27,6 +27,7 @@ sa_fused.DW_TMA_NARROW = os.environ.get("DW_TMA_NARROW", "0") == "1"
 sa_fused.USE_FWD_TMA = os.environ.get("FWD_TMA", "1") == "1"
 sa_fused.FWD_TMA_NARROW = os.environ.get("FWD_TMA_NARROW", "1") == "1"
 sa_fused.USE_DX_TMA = {"0": False, "1": True}.get(os.environ.get("DX_TMA", "auto"), os.environ.get("DX_TMA", "auto"))
+sa_fused.USE_NARROW = os.environ.get("NARROW", "1") == "1"
 fwd_only = os.environ.get("FWD_ONLY", "0") == "1"
 for name, N, M, Cf, w in cfgs:
     xyz = (torch.rand(B, N, 3, device="cuda") - 0.5) * 40

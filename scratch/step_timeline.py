@@ -9,10 +9,10 @@ dev = torch.device('cuda', 0)
 be = backend.get_backend()
 tr = bench.build_trainer(dev, 1, 4)
 batches = [tuple(x.to(dev) for x in data.make_batch(i, 4, 8192, aug=True, fps_fn=be.fps, device=dev)) for i in range(2)]
-for i in range(4): tr.train_step_graphed(100000 + i, batches[i % 2], aug_transform=True)
+for i in range(4): tr.train_step_graphed(100000 + i, batches[i % 2], aug_transform=True, next_batch=batches[(i + 1) % 2])
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
-    tr.train_step_graphed(100010, batches[0], aug_transform=True)
+    tr.train_step_graphed(100010, batches[0], aug_transform=True, next_batch=batches[1])
     torch.cuda.synchronize()
 path = "/tmp/step_trace.json"
 prof.export_chrome_trace(path)
@@ -48,6 +48,6 @@ for n, (c, d) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
 own = sum(d for n, (c, d) in agg.items() if ("ogc" in n or "chain" in n or "_kernel" in n and "at::" not in n))
 print(f"concurrency: sum of activity durations {sum(e['dur'] for e in ev) / 1e3:.3f} ms")
 # time where only small (<= 32 CTAs) kernels run is not visible here; list the long single-stream stretches at the start
-print("first 25 activities:")
-for e in ev[:25]:
+print("first 40 activities:")
+for e in ev[:40]:
     print(f"    {(e['ts'] - t0) / 1e3:7.3f} +{e['dur'] / 1e3:6.3f} ms  s{e['args'].get('stream')}  {e['name'][:70]}")
