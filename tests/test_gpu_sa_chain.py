@@ -1,6 +1,10 @@
-"""GPU: the chained set-abstraction kernels (csrc/sa_chain_*.cu: positions on the MMA's M axis, layers chained through
-tensor memory) against the round-1 per-layer kernels and against the torch-composed reference expression
-(utils/pointnet2_util.py:33-44): pooled output, GroupNorm scale/shift, arg-max positions, stored pre-norm tensors."""
+"""GPU: the round-2 set-abstraction kernels against the round-1 per-layer kernels and against the torch-composed reference
+expression (utils/pointnet2_util.py:33-44).
+  * chained forward (csrc/sa_chain_fwd.cu: positions on the MMA's M axis, layers chained through tensor memory): pooled
+    output, GroupNorm scale/shift, arg-max positions, stored pre-norm tensors;
+  * tensor-map-TMA kernels: forward (sa_fwd_tma.cu), input gradient (sa_chain_bwd.cu positions-on-M, sa_dx_tma.cu
+    channel-major), weight gradient (sa_dw_tma.cu) -- every gradient of the block, ONE forward and two backward passes
+    over the same saved tensors (two forward runs can differ in a ReLU / arg-max decision)."""
 import pytest
 import torch
 
