@@ -14,10 +14,15 @@ exchange one NCCL all-reduce (grads + NaN counter).
 
     value        clouds/s with the batch already resident in HBM (CUDA events, max over ranks)
     e2e          the same through the public step API with pinned-host inputs copied in and the loss dict read back
-    roofline     the dominant libogc_b200 kernel family of the step: bound "tensor" (contractions: useful fp32-equivalent
-                 FLOP/s against the TF32 peak = half the measured bf16 cuBLAS peak; the 3xTF32 split issues 3x that work)
-                 or "hbm" (SURVEY 8d algorithmic bytes / time against the measured copy bandwidth); `traffic` = DRAM
-                 bytes per launch from the committed ncu capture; `step` = the whole-step HBM fraction of SURVEY 8d
+    roofline     the dominant libogc_b200 kernel family of the step's critical path (the single-wave kernels hidden on side
+                 streams -- FPS chain, three_nn, Hungarian, nuclear norm -- are in `ops` only).  A contraction kernel is
+                 placed by its arithmetic intensity (3xTF32 work per algorithmic byte) against the ridge of the two
+                 measured peaks: "tensor" (useful fp32-equivalent FLOP/s against the TF32 peak = half the measured bf16
+                 cuBLAS peak) or "hbm" (SURVEY 8d algorithmic bytes / time against the measured copy bandwidth; the
+                 tensor fractions alongside); `traffic` = DRAM bytes per launch from the committed ncu capture; `step` =
+                 the whole-step HBM fraction of SURVEY 8d
+    The step loop announces the NEXT batch to the trainer (a loader one batch ahead): its clouds are copied in and their
+    first-level FPS centres sampled under the current step -- one copy and one FPS per step either way (--no-prefetch off).
     ops          every kernel family of ours (FPS and ball_query GB/s included, as BASELINE.json's metric asks)
     cpu_baseline the CPU port (oracle kernels + the same torch step, all host cores) on a bounded sample   } run in
     ref_cuda_ext the UNMODIFIED reference Python over the reference's own CUDA extension on the same GPU,  } SUBPROCESSES:
