@@ -90,6 +90,7 @@ class _FusedFP(Function):
         _lib.check(lib.ogc_gn_relu_apply(B, cL, n, _p(ys[-1]), _p(sss[-1]), _p(out), _st()), "ogc_gn_relu_apply")
         be.launches += 1
         ctx.dims = (B, n, m, c2, c1, L)
+        ctx.param_objs = params
         ctx.save_for_backward(idx, wgt, x, *ys, *sss, *mrs, *[p.detach() for p in params])
         return out
 
@@ -108,9 +109,11 @@ class _FusedFP(Function):
         grads = [None] * (3 * L)
         cL = ys[-1].shape[1]
         dz = torch.empty(B, cL, n, **f32)
+        from . import sa_fused
+        tg = sa_fused.grad_targets(ctx.param_objs)          # accumulate straight into the parameters' .grad (trainer's backward)
         ab = torch.zeros(B, 4, 2, dtype=torch.float64, device=dev)
-        dgamma = torch.zeros(cL, **f32)
-        dbeta = torch.zeros(cL, **f32)
+        dgamma = tg[3 * (L - 1) + 1] if tg else torch.zeros(cL, **f32)
+        dbeta = tg[3 * (L - 1) + 2] if tg else torch.zeros(cL, **f32)
         _lib.check(lib.ogc_gn_relu_bwd_stats(B, cL, n, _p(go), _p(ys[-1]), _p(sss[-1]), _p(mrs[-1]),
                                              _p(params[3 * (L - 1) + 1]), _p(dz), _p(ab), _p(dgamma), _p(dbeta), _st()),
                    "ogc_gn_relu_bwd_stats")
@@ -123,8 +126,9 @@ class _FusedFP(Function):
             coef = torch.empty(B, cout, 4, **f32)
             _lib.check(lib.ogc_gn_bwd_coef(B, cout, (cout // 4) * n, _p(ab), _p(mrs[l]), _p(gamma), _p(coef), _st()),
                        "ogc_gn_bwd_coef")
-            grads[3 * l + 1], grads[3 * l + 2] = dgamma, dbeta
-            dW = torch.zeros(cout, cin, **f32)
+            if not tg:
+                grads[3 * l + 1], grads[3 * l + 2] = dgamma, dbeta
+            dW = tg[3 * l].view(cout, cin) if tg else torch.zeros(cout, cin, **f32)
             a_prev = ys[l - 1] if l else x
             ss_prev = sss[l - 1] if l else None
             with TIMER.span(f"fp_mlp_dw[{cin}>{cout}]" if TIMER.detail else "fp_mlp_dw", B * n * 4 * (2 * cout + cin)):
@@ -136,13 +140,14 @@ class _FusedFP(Function):
                                                        _p(a_prev), _p(ss_prev), None, None, None, None, _p(dW), _st()),
                                "ogc_sa_mlp_layer_dw")
             be.launches += 2
-            grads[3 * l] = dW.view_as(W)
+            if not tg:
+                grads[3 * l] = dW.view_as(W)
             if l > 0:
                 cprev = params[3 * (l - 1)].shape[0]
                 dz_prev = torch.empty(B, cprev, n, **f32)
                 ab_prev = torch.zeros(B, 4, 2, dtype=torch.float64, device=dev)
-                dgamma_prev = torch.zeros(cprev, **f32)
-                dbeta_prev = torch.zeros(cprev, **f32)
+                dgamma_prev = tg[3 * (l - 1) + 1] if tg else torch.zeros(cprev, **f32)
+                dbeta_prev = tg[3 * (l - 1) + 2] if tg else torch.zeros(cprev, **f32)
                 with TIMER.span(f"fp_mlp_dx[{cout}>{cprev}]" if TIMER.detail else "fp_mlp_dx", B * n * 4 * (2 * cout + 2 * cprev)):
                     if _tma_ok(n, cprev, cout):
                         _lib.check(lib.ogc_sa_dx_tma(

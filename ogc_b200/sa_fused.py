@@ -87,6 +87,21 @@ def _dx_tma_ok(S, cout, rows, synth):
     return S == 64 and rows % 32 == 0 and rows <= 128 and cout % 32 == 0 and (cout <= 128 or cout == 256)
 
 
+ACCUMULATE_INTO_GRAD = False   # set by the trainers around loss.backward(): the fused blocks' weight / GroupNorm gradients are
+                               # accumulated by the kernels straight into the parameters' .grad (views of the flat gradient
+                               # buffer) instead of into fresh zeroed tensors that autograd then adds on: ~115 tiny launches less
+
+
+def grad_targets(param_objs):
+    """The .grad tensors of the parameters if every one can take the kernels' atomic accumulation directly, else None."""
+    if not ACCUMULATE_INTO_GRAD:
+        return None
+    gs = [p.grad for p in param_objs]
+    if any(g is None or not g.is_contiguous() or g.dtype != torch.float32 or not p.requires_grad for g, p in zip(gs, param_objs)):
+        return None
+    return gs
+
+
 DEBUG_KEEP = None     # diagnostics: a list that collects (layer, dz_prev, ab_prev, coef) of every backward
 STORE_Y = True      # stage 1: keep the pre-norm tensors for the per-layer backward kernels
 USE_CHAIN = False   # round-2 kernels (csrc/sa_chain_*.cu): positions on the MMA's M axis, layers chained through TMEM.
@@ -187,6 +202,7 @@ class _FusedSAMLP(Function):
             ctx.dims = (B, N, M, S, Cf, L)
             ctx.feat_needs_grad = feat_pm.requires_grad
             ctx.has_feat = True
+            ctx.param_objs = params
             ctx.save_for_backward(xyz, new_xyz, feat_pm, idx, sel, ysel, *ys, *sss, *mrs, *[p.detach() for p in params])
             return out
         for l in range(L):
@@ -244,6 +260,7 @@ class _FusedSAMLP(Function):
         _lib.check(lib.ogc_sa_finish(B, cout, M, _p(ymax), _p(ymin), _p(amax), _p(amin), _p(sss[-1]), _p(out), None,
                                      cout, 0, _p(sel), _p(ysel), _st()), "ogc_sa_finish")
         be.launches += 1
+        ctx.param_objs = params
         ctx.dims = (B, N, M, S, Cf, L)
         ctx.feat_needs_grad = feat_pm is not None and feat_pm.requires_grad
         ctx.has_feat = feat_pm is not None
@@ -270,9 +287,10 @@ class _FusedSAMLP(Function):
         dfeat_pm = None
 
         cL = params[3 * (L - 1)].shape[0]
+        tg = grad_targets(ctx.param_objs)          # accumulate straight into the parameters' .grad (trainer's backward)
         ab = torch.zeros(B, 4, 2, dtype=torch.float64, device=dev)
-        dgamma = torch.zeros(cL, **f32)
-        dbeta = torch.zeros(cL, **f32)
+        dgamma = tg[3 * (L - 1) + 1] if tg else torch.zeros(cL, **f32)
+        dbeta = tg[3 * (L - 1) + 2] if tg else torch.zeros(cL, **f32)
         _lib.check(lib.ogc_sa_last_stats(B, cL, M, _p(go), cL, 0, _p(sel), _p(ysel), _p(mrs[-1]), _p(params[3 * (L - 1) + 1]),
                                          _p(ab), _p(dgamma), _p(dbeta), _st()), "ogc_sa_last_stats")
         be.launches += 1
@@ -284,8 +302,9 @@ class _FusedSAMLP(Function):
             coef = torch.empty(B, cout, 4, **f32)
             _lib.check(lib.ogc_gn_bwd_coef(B, cout, (cout // 4) * P, _p(ab), _p(mrs[l]), _p(gamma), _p(coef), _st()),
                        "ogc_gn_bwd_coef")
-            grads[3 * l + 1], grads[3 * l + 2] = dgamma, dbeta
-            dW = torch.zeros(cout, cin, **f32)
+            if not tg:
+                grads[3 * l + 1], grads[3 * l + 2] = dgamma, dbeta
+            dW = tg[3 * l].view(cout, cin) if tg else torch.zeros(cout, cin, **f32)
             gather = l == 0
             dw_nw = not gather and _narrow_ok(S, cin, cout)
             dw_tc = not dw_nw and _tc_dw_ok(S, cin, cout)
@@ -307,13 +326,14 @@ class _FusedSAMLP(Function):
                         _p(ys[l - 1]) if l else None, _p(sss[l - 1]) if l else None,
                         _p(xyz), _p(new_xyz), _p(feat_pm), _p(idx), _p(dW), _st()), "ogc_sa_mlp_layer_dw")
             be.launches += 2
-            grads[3 * l] = dW.view_as(W)
+            if not tg:
+                grads[3 * l] = dW.view_as(W)
             if l > 0:
                 cprev = params[3 * (l - 1)].shape[0]
                 dz_prev = torch.empty(B, cprev, P, **f32)
                 ab_prev = torch.zeros(B, 4, 2, dtype=torch.float64, device=dev)
-                dgamma_prev = torch.zeros(cprev, **f32)
-                dbeta_prev = torch.zeros(cprev, **f32)
+                dgamma_prev = tg[3 * (l - 1) + 1] if tg else torch.zeros(cprev, **f32)
+                dbeta_prev = tg[3 * (l - 1) + 2] if tg else torch.zeros(cprev, **f32)
                 dx_nw = _narrow_ok(S, cprev, cout)
                 dx_tc = not dx_nw and _tc_dx_ok(S, cout, cprev, False)
                 dx_fn, dx_tag = (lib.ogc_sa_mlp_layer_dx_tc, "sa_mlp_dx_tc") if dx_tc else (lib.ogc_sa_mlp_layer_dx, "sa_mlp_dx")

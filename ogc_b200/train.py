@@ -165,7 +165,12 @@ class SegTrainer:
                                              aug_transform=aug_transform)
         finally:
             self.criterion.defer_logging = False
-        loss.backward()
+        from . import sa_fused
+        sa_fused.ACCUMULATE_INTO_GRAD = True       # the fused blocks' kernels accumulate into the flat gradient buffer directly
+        try:
+            loss.backward()
+        finally:
+            sa_fused.ACCUMULATE_INTO_GRAD = False
         self.opt.count_nan()
         if self.world_size > 1 and allreduce:
             dist.all_reduce(self.opt.flat_g_ext)          # the step's only collective: grads + NaN counter
