@@ -64,18 +64,19 @@ class _FusedFP(Function):
         be.launches += 1
         ys, sss, mrs = [], [], []
         a_prev, ss_prev = x, None
+        sums_all = torch.zeros(L, B, 4, 2, dtype=torch.float64, device=dev)      # one fill for all layers
         for l in range(L):
             W, gamma, beta = params[3 * l], params[3 * l + 1], params[3 * l + 2]
             cout, cin = W.shape[0], W.shape[1]
-            wt = W.detach().reshape(cout, cin).t().contiguous()
             y = torch.empty(B, cout, n, **f32)
-            sums = torch.zeros(B, 4, 2, dtype=torch.float64, device=dev)
+            sums = sums_all[l]
             with TIMER.span(f"fp_mlp_fwd[{cin}>{cout}]" if TIMER.detail else "fp_mlp_fwd", B * 4 * n * (cin + cout)):
                 if l > 0 and _tma_ok(n, cin, cout):
                     w2d = W.detach().reshape(cout, cin).contiguous()
                     _lib.check(lib.ogc_sa_fwd_tma(B, n // 64, 64, cin, cout, 0, _p(a_prev), _p(ss_prev), _p(w2d), _p(y), _p(sums),
                                                   None, None, None, None, _st()), "ogc_sa_fwd_tma")
                 else:
+                    wt = W.detach().reshape(cout, cin).t().contiguous()       # only the SIMT kernel wants W^T
                     _lib.check(lib.ogc_pw_mlp_layer_fwd(B, n, cin, cout, _p(a_prev), _p(ss_prev), _p(wt), _p(y), _p(sums),
                                                         _st()), "ogc_pw_mlp_layer_fwd")
             ss = torch.empty(B, cout, 2, **f32)
@@ -111,7 +112,8 @@ class _FusedFP(Function):
         dz = torch.empty(B, cL, n, **f32)
         from . import sa_fused
         tg = sa_fused.grad_targets(ctx.param_objs)          # accumulate straight into the parameters' .grad (trainer's backward)
-        ab = torch.zeros(B, 4, 2, dtype=torch.float64, device=dev)
+        ab_all = torch.zeros(L, B, 4, 2, dtype=torch.float64, device=dev)        # one fill for all layers
+        ab = ab_all[L - 1]
         dgamma = tg[3 * (L - 1) + 1] if tg else torch.zeros(cL, **f32)
         dbeta = tg[3 * (L - 1) + 2] if tg else torch.zeros(cL, **f32)
         _lib.check(lib.ogc_gn_relu_bwd_stats(B, cL, n, _p(go), _p(ys[-1]), _p(sss[-1]), _p(mrs[-1]),
@@ -145,7 +147,7 @@ class _FusedFP(Function):
             if l > 0:
                 cprev = params[3 * (l - 1)].shape[0]
                 dz_prev = torch.empty(B, cprev, n, **f32)
-                ab_prev = torch.zeros(B, 4, 2, dtype=torch.float64, device=dev)
+                ab_prev = ab_all[l - 1]
                 dgamma_prev = tg[3 * (l - 1) + 1] if tg else torch.zeros(cprev, **f32)
                 dbeta_prev = tg[3 * (l - 1) + 2] if tg else torch.zeros(cprev, **f32)
                 with TIMER.span(f"fp_mlp_dx[{cout}>{cprev}]" if TIMER.detail else "fp_mlp_dx", B * n * 4 * (2 * cout + 2 * cprev)):

@@ -205,13 +205,13 @@ class _FusedSAMLP(Function):
             ctx.param_objs = params
             ctx.save_for_backward(xyz, new_xyz, feat_pm, idx, sel, ysel, *ys, *sss, *mrs, *[p.detach() for p in params])
             return out
+        sums_all = torch.zeros(L, B, 4, 2, dtype=torch.float64, device=dev)      # one fill for all layers
         for l in range(L):
             W, gamma, beta = params[3 * l], params[3 * l + 1], params[3 * l + 2]
             cout, cin = W.shape[0], W.shape[1]
-            wt = W.detach().reshape(cout, cin).t().contiguous()
             last = l == L - 1
             y = torch.empty(B, cout, P, **f32)
-            sums = torch.zeros(B, 4, 2, dtype=torch.float64, device=dev)
+            sums = sums_all[l]
             if last:
                 ymax = torch.empty(B, cout, M, **f32)
                 ymin = torch.empty(B, cout, M, **f32)
@@ -242,6 +242,7 @@ class _FusedSAMLP(Function):
                         _p(y_prev), _p(ss_prev), _p(w2d), _p(y), _p(sums), _p(ymax), _p(ymin), _p(amax), _p(amin),
                         _st()), "ogc_sa_mlp_layer_fwd_tc")
                 else:
+                    wt = W.detach().reshape(cout, cin).t().contiguous()       # only the SIMT kernel wants W^T
                     _lib.check(lib.ogc_sa_mlp_layer_fwd(
                         B, N, M, S, cin, cout, int(l == 0), int(last), _p(xyz), _p(new_xyz), _p(feat_pm), _p(idx),
                         _p(y_prev), _p(ss_prev), _p(wt), _p(y), _p(sums), _p(ymax), _p(ymin), _p(amax), _p(amin),
@@ -288,7 +289,8 @@ class _FusedSAMLP(Function):
 
         cL = params[3 * (L - 1)].shape[0]
         tg = grad_targets(ctx.param_objs)          # accumulate straight into the parameters' .grad (trainer's backward)
-        ab = torch.zeros(B, 4, 2, dtype=torch.float64, device=dev)
+        ab_all = torch.zeros(L, B, 4, 2, dtype=torch.float64, device=dev)        # one fill for all layers
+        ab = ab_all[L - 1]
         dgamma = tg[3 * (L - 1) + 1] if tg else torch.zeros(cL, **f32)
         dbeta = tg[3 * (L - 1) + 2] if tg else torch.zeros(cL, **f32)
         _lib.check(lib.ogc_sa_last_stats(B, cL, M, _p(go), cL, 0, _p(sel), _p(ysel), _p(mrs[-1]), _p(params[3 * (L - 1) + 1]),
@@ -331,7 +333,7 @@ class _FusedSAMLP(Function):
             if l > 0:
                 cprev = params[3 * (l - 1)].shape[0]
                 dz_prev = torch.empty(B, cprev, P, **f32)
-                ab_prev = torch.zeros(B, 4, 2, dtype=torch.float64, device=dev)
+                ab_prev = ab_all[l - 1]
                 dgamma_prev = tg[3 * (l - 1) + 1] if tg else torch.zeros(cprev, **f32)
                 dbeta_prev = tg[3 * (l - 1) + 2] if tg else torch.zeros(cprev, **f32)
                 dx_nw = _narrow_ok(S, cprev, cout)
