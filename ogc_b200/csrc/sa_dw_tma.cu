@@ -113,7 +113,9 @@ sa_dw_tma_kernel(const __grid_constant__ Params q, const __grid_constant__ CUten
         }
     } else if (warp == kMmaWarp) {
         // ============================================ MMA issuer ============================================
-        const uint32_t idesc = tc::make_idesc_tf32(128, Cin, 0, 0);
+        // two MMAs per 8 positions instead of three: dY x [a ; a_lo] (the two tiles are adjacent: one B operand of 2 C_in rows)
+        // puts hi*hi and hi*lo into adjacent column ranges, dY_lo x a accumulates into the first; the epilogue adds the ranges
+        const uint32_t idesc1 = tc::make_idesc_tf32(128, 2 * Cin, 0, 0), idesc2 = tc::make_idesc_tf32(128, Cin, 0, 0);
         const int mblocks = C > 128 ? 2 : 1;
         for (int s = 0; s < nst; ++s) {
             const int st = s % NS;
@@ -122,16 +124,15 @@ sa_dw_tma_kernel(const __grid_constant__ Params q, const __grid_constant__ CUten
             for (int j = 0; j < W; ++j) {
                 const uint32_t base = smem_u32(smem + static_cast<size_t>(st) * q.stage_bytes + static_cast<size_t>(j) * q.win_bytes);
                 const uint64_t dv = tc::make_desc_sw128(base + q.off_v, 16, 1024), dl = tc::make_desc_sw128(base + q.off_l, 16, 1024);
-                const uint64_t da = tc::make_desc_sw128(base + q.off_a, 16, 1024), dal = tc::make_desc_sw128(base + q.off_al, 16, 1024);
+                    const uint64_t da = tc::make_desc_sw128(base + q.off_a, 16, 1024);          // a tile, a_lo tile right behind it
                 for (int mb = 0; mb < mblocks; ++mb) {
-                    const uint32_t d = tmem_base + static_cast<uint32_t>(mb * Cin);
+                    const uint32_t d = tmem_base + static_cast<uint32_t>(mb * 2 * Cin);
                     const uint64_t moff = static_cast<uint64_t>(mb) * ((128u * 128u) >> 4);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint32_t acc = (s | j | k) ? 1u : 0u;
-                        tc::mma_tf32_ss_elect(d, dv + moff + 2u * k, da + 2u * k, idesc, acc);
-                        tc::mma_tf32_ss_elect(d, dv + moff + 2u * k, dal + 2u * k, idesc, 1u);
-                        tc::mma_tf32_ss_elect(d, dl + moff + 2u * k, da + 2u * k, idesc, 1u);
+                        tc::mma_tf32_ss_elect(d, dv + moff + 2u * k, da + 2u * k, idesc1, acc);
+                        tc::mma_tf32_ss_elect(d, dl + moff + 2u * k, da + 2u * k, idesc2, 1u);
                     }
                 }
             }
@@ -209,11 +210,12 @@ sa_dw_tma_kernel(const __grid_constant__ Params q, const __grid_constant__ CUten
             for (int mb = 0; mb < (C > 128 ? 2 : 1); ++mb) {
                 const int co = mb * 128 + warp * 32 + lane;
                 for (int c0 = 0; c0 < Cin; c0 += 32) {
-                    float v[32];
-                    tc::tmem_ld32(trow + static_cast<uint32_t>(mb * Cin + c0), v);
+                    float v[32], w[32];
+                    tc::tmem_ld32(trow + static_cast<uint32_t>(mb * 2 * Cin + c0), v);             // hi*hi + lo*hi
+                    tc::tmem_ld32(trow + static_cast<uint32_t>(mb * 2 * Cin + Cin + c0), w);       // hi*lo
                     if (co < C) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) atomicAdd(q.dw + static_cast<size_t>(co) * Cin + c0 + j, v[j]);
+                        for (int j = 0; j < 32; ++j) atomicAdd(q.dw + static_cast<size_t>(co) * Cin + c0 + j, v[j] + w[j]);
                     }
                 }
             }
