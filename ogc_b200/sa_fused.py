@@ -59,7 +59,7 @@ def _chain_dx_ok(S, M, cout, rows, scatter):
 
 
 USE_DW_TMA = True     # dense-layer weight gradient with TMA-staged operands (csrc/sa_dw_tma.cu)
-DW_TMA_NARROW = False # ... also for SA level 1's 32 -> 32 layers (measured: the warp-per-centre kernel is faster there)
+DW_TMA_NARROW = True  # ... also for SA level 1's 32 -> 32 layers (0.22-0.25 ms vs 0.22-0.28 for the warp-per-centre kernel)
 
 
 def _dw_tma_ok(S, M, cin, cout):
