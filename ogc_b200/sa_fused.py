@@ -8,6 +8,7 @@ without materialising the grouped (B,3+C,M,S) tensor or any normalised / rectifi
 one kernel per layer in the forward, two per layer in the backward (see the .cu headers).
 """
 import ctypes
+import os
 
 import torch
 from torch.autograd import Function
