@@ -31,125 +31,140 @@ __device__ __forceinline__ float ex2_approx(float x) {       // MUFU.EX2
     return r;
 }
 
-constexpr int kIcpQ = 4;           // source points per warp: one read of a target point from shared memory serves all of them
+constexpr int kIcpCThreads = 256;   // correspondence kernel: thread = source point
 
-// The shared-memory reads (3 + K words per pair) bounded the one-query-per-warp version; with kIcpQ queries per warp they
-// are amortised, and the queries are processed in PAIRS on packed fp32 FMAs (a 3-register FFMA issues every other cycle,
-// FFMA2 retires two per slot): distance, the K-term consistency dot product and the running sums of two queries per
-// instruction.  exp(x) = 2^(x log2 e) with log2 e folded into 1/T.  Each query keeps its own online-softmax state and visits
-// the targets in the same order as the one-query version.  199 -> 139 ms for 64 clouds x 8192 points x 20 iterations.
+__device__ __forceinline__ float2 ld_smem_f2(const float *p) { return *reinterpret_cast<const float2 *>(p); }
+
+// Round-2 form: THREAD = source point.  Every datum of a target (coordinates, K mask entries) is then warp-uniform -- one
+// broadcast shared-memory read serves 32 pairs -- and the per-pair work is pure arithmetic on registers.  Targets are taken
+// two at a time on packed fp32 FMAs (a 3-register FFMA issues every other cycle, FFMA2 retires two per slot): the tile
+// is stored structure-of-arrays so that (x_t, x_t+1) and (m2_t[k], m2_t+1[k]) are adjacent.  TWO passes over the target
+// cloud instead of an online softmax: pass 1 finds the nearest target (the softmax maximum is -d_min / T), pass 2
+// accumulates with that fixed maximum -- no rescaling branch, no lane merge.  exp(x) = 2^(x log2 e), log2 e folded into
+// 1/T; MUFU sqrt / ex2.  Two source points per thread share the broadcast reads.  29 -> ~18 instructions per pair.
+constexpr int kIcpQ = 2;            // source points per THREAD: the 3 + K broadcast reads of a target pair serve both
+
 template <int K>
-__global__ void __launch_bounds__(kIcpThreads)
+__global__ void __launch_bounds__(kIcpCThreads)
 icp_correspond_kernel(int n1, int n2, float inv_temp, const float *__restrict__ pc1, const float *__restrict__ flow,
                       const float *__restrict__ pc2, const float *__restrict__ mask1, const float *__restrict__ mask2,
                       float *__restrict__ flow_out) {
-    __shared__ float sp[kIcpTile * 3];
-    __shared__ float sm[kIcpTile * K];
-    constexpr int NP = kIcpQ / 2;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ __align__(16) float sx[kIcpTile], sy[kIcpTile], sz[kIcpTile];
+    __shared__ __align__(16) float sm[K * kIcpTile];            // [k][target]
     const int b = blockIdx.y;
-    const int q0 = (blockIdx.x * kIcpWarps + warp) * kIcpQ;
+    const int q0 = blockIdx.x * (kIcpCThreads * kIcpQ) + threadIdx.x;      // queries q0, q0 + 256: coalesced loads / stores
     pc2 += static_cast<size_t>(b) * n2 * 3;
     mask2 += static_cast<size_t>(b) * n2 * K;
     const float scale2 = -inv_temp * 1.4426950408889634f;       // s2 = -d / T * log2(e)
 
     float px[kIcpQ], py[kIcpQ], pz[kIcpQ];
-    float2 qx[NP], qy[NP], qz[NP], m1[NP][K], Z[NP], A[NP], vx[NP], vy[NP], vz[NP];
-    float mx[kIcpQ];
+    float2 qx[kIcpQ], qy[kIcpQ], qz[kIcpQ], m1[kIcpQ][K];
 #pragma unroll
     for (int u = 0; u < kIcpQ; ++u) {
-        const int q = q0 + u;
+        const int q = q0 + u * kIcpCThreads;
         float fx = 0.f, fy = 0.f, fz = 0.f;
         px[u] = py[u] = pz[u] = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) m1[u][k] = make_float2(0.f, 0.f);
         if (q < n1) {
             const size_t o = (static_cast<size_t>(b) * n1 + q) * 3;
             px[u] = __ldg(pc1 + o); py[u] = __ldg(pc1 + o + 1); pz[u] = __ldg(pc1 + o + 2);
             fx = px[u] + __ldg(flow + o); fy = py[u] + __ldg(flow + o + 1); fz = pz[u] + __ldg(flow + o + 2);
-        }
-        (u & 1 ? qx[u >> 1].y : qx[u >> 1].x) = fx;
-        (u & 1 ? qy[u >> 1].y : qy[u >> 1].x) = fy;
-        (u & 1 ? qz[u >> 1].y : qz[u >> 1].x) = fz;
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const float v = q < n1 ? __ldg(mask1 + (static_cast<size_t>(b) * n1 + q) * K + k) : 0.f;
-            (u & 1 ? m1[u >> 1][k].y : m1[u >> 1][k].x) = v;
+            for (int k = 0; k < K; ++k) {
+                const float v = __ldg(mask1 + (static_cast<size_t>(b) * n1 + q) * K + k);
+                m1[u][k] = make_float2(v, v);
+            }
         }
-        mx[u] = -INFINITY;
+        qx[u] = make_float2(fx, fx); qy[u] = make_float2(fy, fy); qz[u] = make_float2(fz, fz);
     }
+    const float2 mone2 = make_float2(-1.f, -1.f), one2 = make_float2(1.f, 1.f), zero2 = make_float2(0.f, 0.f);
+    auto load_xyz = [&](int t0, int tn) {
+        for (int i = threadIdx.x; i < kIcpTile; i += kIcpCThreads) {
+            const bool in = i < tn;                  // padding targets sit at +inf distance: weight 0, never the nearest
+            sx[i] = in ? __ldg(pc2 + static_cast<size_t>(t0 + i) * 3) : 1e18f;
+            sy[i] = in ? __ldg(pc2 + static_cast<size_t>(t0 + i) * 3 + 1) : 1e18f;
+            sz[i] = in ? __ldg(pc2 + static_cast<size_t>(t0 + i) * 3 + 2) : 1e18f;
+        }
+    };
+    // ---- pass 1: squared distance to the nearest target ----
+    float2 dmin[kIcpQ];
 #pragma unroll
-    for (int p = 0; p < NP; ++p) Z[p] = A[p] = vx[p] = vy[p] = vz[p] = make_float2(0.f, 0.f);
-    const float2 one2 = make_float2(1.f, 1.f), zero2 = make_float2(0.f, 0.f);
-    const bool has_q = q0 < n1;
+    for (int u = 0; u < kIcpQ; ++u) dmin[u] = make_float2(INFINITY, INFINITY);
     for (int t0 = 0; t0 < n2; t0 += kIcpTile) {
         const int tn = min(kIcpTile, n2 - t0);
         __syncthreads();
-        for (int i = threadIdx.x; i < tn * 3; i += kIcpThreads) sp[i] = __ldg(pc2 + static_cast<size_t>(t0) * 3 + i);
-        for (int i = threadIdx.x; i < tn * K; i += kIcpThreads) sm[i] = __ldg(mask2 + static_cast<size_t>(t0) * K + i);
+        load_xyz(t0, tn);
         __syncthreads();
-        if (!has_q) continue;
-        for (int j = lane; j < tn; j += 32) {
-            const float x = sp[j * 3], y = sp[j * 3 + 1], z = sp[j * 3 + 2];
-            const float2 nx = make_float2(-x, -x), ny = make_float2(-y, -y), nz = make_float2(-z, -z);
-            const float2 x2 = make_float2(x, x), y2 = make_float2(y, y), z2 = make_float2(z, z);
-            float2 m2[K];
+#pragma unroll 4
+        for (int j = 0; j < kIcpTile; j += 2) {
+            const float2 x2 = ld_smem_f2(sx + j), y2 = ld_smem_f2(sy + j), z2 = ld_smem_f2(sz + j);
 #pragma unroll
-            for (int k = 0; k < K; ++k) { const float v = sm[j * K + k]; m2[k] = make_float2(v, v); }
-#pragma unroll
-            for (int p = 0; p < NP; ++p) {
-                const float2 dx = ffma2(one2, qx[p], nx), dy = ffma2(one2, qy[p], ny), dz = ffma2(one2, qz[p], nz);
+            for (int u = 0; u < kIcpQ; ++u) {
+                const float2 dx = ffma2(mone2, x2, qx[u]), dy = ffma2(mone2, y2, qy[u]), dz = ffma2(mone2, z2, qz[u]);
                 float2 d2 = ffma2(dx, dx, zero2);
                 d2 = ffma2(dy, dy, d2);
                 d2 = ffma2(dz, dz, d2);
-                const float s0 = sqrt_approx(d2.x) * scale2, s1 = sqrt_approx(d2.y) * scale2;
-                float2 c = zero2;
-#pragma unroll
-                for (int k = 0; k < K; ++k) c = ffma2(m1[p][k], m2[k], c);
-                if (s0 > mx[2 * p]) {                 // rescale the running sums of the first query to its new maximum
-                    const float r = ex2_approx(mx[2 * p] - s0);
-                    Z[p].x *= r; A[p].x *= r; vx[p].x *= r; vy[p].x *= r; vz[p].x *= r;
-                    mx[2 * p] = s0;
-                }
-                if (s1 > mx[2 * p + 1]) {
-                    const float r = ex2_approx(mx[2 * p + 1] - s1);
-                    Z[p].y *= r; A[p].y *= r; vx[p].y *= r; vy[p].y *= r; vz[p].y *= r;
-                    mx[2 * p + 1] = s1;
-                }
-                const float2 e = make_float2(ex2_approx(s0 - mx[2 * p]), ex2_approx(s1 - mx[2 * p + 1]));
-                const float2 ec = ffma2(e, c, zero2);
-                Z[p] = ffma2(e, one2, Z[p]);
-                A[p] = ffma2(ec, one2, A[p]);
-                vx[p] = ffma2(ec, x2, vx[p]); vy[p] = ffma2(ec, y2, vy[p]); vz[p] = ffma2(ec, z2, vz[p]);
+                dmin[u].x = fminf(dmin[u].x, d2.x);
+                dmin[u].y = fminf(dmin[u].y, d2.y);
             }
         }
     }
-    if (!has_q) return;
+    // - (softmax maximum in base-2 units), from the SAME arithmetic pass 2 uses for every pair
+    float2 nmx[kIcpQ];
 #pragma unroll
     for (int u = 0; u < kIcpQ; ++u) {
-        // merge the 32 lane states of query u (base-2 exponents)
-        const int p = u >> 1;
-        float mxu = mx[u], Zu = u & 1 ? Z[p].y : Z[p].x, Au = u & 1 ? A[p].y : A[p].x;
-        float vxu = u & 1 ? vx[p].y : vx[p].x, vyu = u & 1 ? vy[p].y : vy[p].x, vzu = u & 1 ? vz[p].y : vz[p].x;
+        const float nm = -(sqrt_approx(fminf(dmin[u].x, dmin[u].y)) * scale2);
+        nmx[u] = make_float2(nm, nm);
+    }
+    const float2 sc2 = make_float2(scale2, scale2);
+    // ---- pass 2: softmax-weighted sums with the maximum fixed ----
+    float2 Z[kIcpQ], A[kIcpQ], vx[kIcpQ], vy[kIcpQ], vz[kIcpQ];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float omx = __shfl_xor_sync(OGC_FULL_MASK, mxu, o);
-            const float oZ = __shfl_xor_sync(OGC_FULL_MASK, Zu, o), oA = __shfl_xor_sync(OGC_FULL_MASK, Au, o);
-            const float ox = __shfl_xor_sync(OGC_FULL_MASK, vxu, o), oy = __shfl_xor_sync(OGC_FULL_MASK, vyu, o),
-                        oz = __shfl_xor_sync(OGC_FULL_MASK, vzu, o);
-            const float nm = fmaxf(mxu, omx);
-            const float ra = (mxu == -INFINITY) ? 0.f : ex2_approx(mxu - nm), rb = (omx == -INFINITY) ? 0.f : ex2_approx(omx - nm);
-            Zu = Zu * ra + oZ * rb; Au = Au * ra + oA * rb;
-            vxu = vxu * ra + ox * rb; vyu = vyu * ra + oy * rb; vzu = vzu * ra + oz * rb;
-            mxu = nm;
+    for (int u = 0; u < kIcpQ; ++u) Z[u] = A[u] = vx[u] = vy[u] = vz[u] = zero2;
+    for (int t0 = 0; t0 < n2; t0 += kIcpTile) {
+        const int tn = min(kIcpTile, n2 - t0);
+        __syncthreads();
+        load_xyz(t0, tn);
+        for (int i = threadIdx.x; i < kIcpTile * K; i += kIcpCThreads) {
+            const int t = i / K, k = i - t * K;
+            sm[k * kIcpTile + t] = t < tn ? __ldg(mask2 + static_cast<size_t>(t0) * K + i) : 0.f;
         }
-        const int q = q0 + u;
-        if (lane == 0 && q < n1) {
-            const float invZ = 1.0f / Zu;
-            const float rs = fmaxf(Au * invZ, 1e-10f);
-            const size_t o = (static_cast<size_t>(b) * n1 + q) * 3;
-            flow_out[o] = (vxu * invZ) / rs - px[u];
-            flow_out[o + 1] = (vyu * invZ) / rs - py[u];
-            flow_out[o + 2] = (vzu * invZ) / rs - pz[u];
+        __syncthreads();
+#pragma unroll 2
+        for (int j = 0; j < kIcpTile; j += 2) {
+            const float2 x2 = ld_smem_f2(sx + j), y2 = ld_smem_f2(sy + j), z2 = ld_smem_f2(sz + j);
+            float2 m2[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) m2[k] = ld_smem_f2(sm + k * kIcpTile + j);
+#pragma unroll
+            for (int u = 0; u < kIcpQ; ++u) {
+                const float2 dx = ffma2(mone2, x2, qx[u]), dy = ffma2(mone2, y2, qy[u]), dz = ffma2(mone2, z2, qz[u]);
+                float2 d2 = ffma2(dx, dx, zero2);
+                d2 = ffma2(dy, dy, d2);
+                d2 = ffma2(dz, dz, d2);
+                const float2 arg = ffma2(make_float2(sqrt_approx(d2.x), sqrt_approx(d2.y)), sc2, nmx[u]);     // s2 - max <= 0
+                float2 c = zero2;
+#pragma unroll
+                for (int k = 0; k < K; ++k) c = ffma2(m1[u][k], m2[k], c);
+                const float2 e = make_float2(ex2_approx(arg.x), ex2_approx(arg.y));
+                const float2 ec = ffma2(e, c, zero2);
+                Z[u] = ffma2(e, one2, Z[u]);
+                A[u] = ffma2(ec, one2, A[u]);
+                vx[u] = ffma2(ec, x2, vx[u]); vy[u] = ffma2(ec, y2, vy[u]); vz[u] = ffma2(ec, z2, vz[u]);
+            }
         }
+    }
+#pragma unroll
+    for (int u = 0; u < kIcpQ; ++u) {
+        const int q = q0 + u * kIcpCThreads;
+        if (q >= n1) continue;
+        const float invZ = 1.0f / (Z[u].x + Z[u].y);
+        const float rs = fmaxf((A[u].x + A[u].y) * invZ, 1e-10f);
+        const size_t o = (static_cast<size_t>(b) * n1 + q) * 3;
+        flow_out[o] = ((vx[u].x + vx[u].y) * invZ) / rs - px[u];
+        flow_out[o + 1] = ((vy[u].x + vy[u].y) * invZ) / rs - py[u];
+        flow_out[o + 2] = ((vz[u].x + vz[u].y) * invZ) / rs - pz[u];
     }
 }
 
@@ -233,11 +248,11 @@ extern "C" int ogc_icp_correspond(int b, int n1, int n2, int k, float temperatur
     if (b == 0 || n1 == 0) return OGC_OK;
     if (!pc1 || !flow || !pc2 || !mask1 || !mask2 || !flow_out) return OGC_ERR_INVALID_ARG;
     if (b > 65535) return OGC_ERR_UNSUPPORTED;
-    dim3 grid((n1 + kIcpWarps * kIcpQ - 1) / (kIcpWarps * kIcpQ), b);
+    dim3 grid((n1 + kIcpCThreads * kIcpQ - 1) / (kIcpCThreads * kIcpQ), b);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const float it = 1.0f / temperature;
     switch (k) {
-#define OGC_ICP_CASE(KK) case KK: icp_correspond_kernel<KK><<<grid, kIcpThreads, 0, st>>>(n1, n2, it, pc1, flow, pc2, mask1, mask2, flow_out); break;
+#define OGC_ICP_CASE(KK) case KK: icp_correspond_kernel<KK><<<grid, kIcpCThreads, 0, st>>>(n1, n2, it, pc1, flow, pc2, mask1, mask2, flow_out); break;
         OGC_ICP_CASE(1) OGC_ICP_CASE(2) OGC_ICP_CASE(3) OGC_ICP_CASE(4) OGC_ICP_CASE(5) OGC_ICP_CASE(6) OGC_ICP_CASE(7)
         OGC_ICP_CASE(8) OGC_ICP_CASE(9) OGC_ICP_CASE(10) OGC_ICP_CASE(11) OGC_ICP_CASE(12) OGC_ICP_CASE(13)
         OGC_ICP_CASE(14) OGC_ICP_CASE(15) OGC_ICP_CASE(16)
