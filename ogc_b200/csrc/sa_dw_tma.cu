@@ -77,11 +77,14 @@ sa_dw_tma_kernel(const __grid_constant__ Params q, const __grid_constant__ CUten
     auto load_sg = [&](int u, int e) {           // e in [0, 2 C): centre e / C, channel e % C of the CTA's u-th tile
         const int cen = e / C, c = e - cen * C;
         const int m = 2 * tile_of(u) + cen;
-        return make_float2(static_cast<float>(__ldg(q.sel + (static_cast<size_t>(b) * C + c) * M + m)),
+        // the slot stays an integer bit pattern until it is stored into the table: a conversion right behind the load
+        // would wait for it here, a whole tile before the value is needed
+        return make_float2(__int_as_float(static_cast<int>(__ldg(q.sel + (static_cast<size_t>(b) * C + c) * M + m))),
                            __ldg(q.go + (static_cast<size_t>(b) * q.go_ctotal + q.go_coff + c) * M + m));
     };
+    auto sg_entry = [](float2 raw) { return make_float2(static_cast<float>(__float_as_int(raw.x)), raw.y); };
     if (SYNTH && n_my > 0)
-        for (int e = tid; e < 2 * C; e += kThreads) tab_sg[e] = load_sg(0, e);
+        for (int e = tid; e < 2 * C; e += kThreads) tab_sg[e] = sg_entry(load_sg(0, e));
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -197,8 +200,8 @@ sa_dw_tma_kernel(const __grid_constant__ Params q, const __grid_constant__ CUten
             if (SYNTH && tile_last && u + 1 < n_my) {   // every splitter has finished this tile's windows once it passes the barrier
                 asm volatile("bar.sync 1, %0;" ::"r"(kSplit) : "memory");
                 float2 *dst = tab_sg + (((u + 1) & 1) * 2) * C;
-                if (tid < 2 * C) dst[tid] = sg_next[0];
-                if (tid + kSplit < 2 * C) dst[tid + kSplit] = sg_next[1];
+                if (tid < 2 * C) dst[tid] = sg_entry(sg_next[0]);
+                if (tid + kSplit < 2 * C) dst[tid + kSplit] = sg_entry(sg_next[1]);
                 asm volatile("bar.sync 1, %0;" ::"r"(kSplit) : "memory");
             }
         }

@@ -84,11 +84,13 @@ sa_dx_tma_kernel(const __grid_constant__ Params q, const __grid_constant__ CUten
     auto tile_of = [&](int u) { return static_cast<int>(blockIdx.x) + u * static_cast<int>(gridDim.x); };
     auto load_sg = [&](int u, int c) {
         const int m = tile_of(u);
-        return make_float2(static_cast<float>(__ldg(q.sel + (static_cast<size_t>(b) * q.Ctot + q.co_off + c) * M + m)),
+        // (the slot stays an integer bit pattern until it is stored into the table: see sa_dw_tma.cu)
+        return make_float2(__int_as_float(static_cast<int>(__ldg(q.sel + (static_cast<size_t>(b) * q.Ctot + q.co_off + c) * M + m))),
                            __ldg(q.go + (static_cast<size_t>(b) * q.go_ctotal + q.go_coff + q.co_off + c) * M + m));
     };
+    auto sg_entry = [](float2 raw) { return make_float2(static_cast<float>(__float_as_int(raw.x)), raw.y); };
     if (SYNTH && n_my > 0)
-        for (int c = tid; c < Kc; c += kThreads) tab_sg[c] = load_sg(0, c);
+        for (int c = tid; c < Kc; c += kThreads) tab_sg[c] = sg_entry(load_sg(0, c));
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -222,7 +224,7 @@ sa_dx_tma_kernel(const __grid_constant__ Params q, const __grid_constant__ CUten
                     float2 *dst = tab_sg + ((s + 1) & 1) * Kc;
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        if (r0 + 32 * i < Kc) dst[r0 + 32 * i] = sg_next[i];
+                        if (r0 + 32 * i < Kc) dst[r0 + 32 * i] = sg_entry(sg_next[i]);
                 }
                 asm volatile("bar.sync 1, %0;" ::"r"(kSplit) : "memory");
             }
