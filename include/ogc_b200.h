@@ -473,6 +473,38 @@ OGC_API int ogc_mask_head_bwd(int b, int d, int n, int k, float inv_temperature,
 OGC_API int ogc_softmax_transfer(int b, int n1, int n2, int k, float temperature, const float *query, const float *key,
                                  const float *val, float *out, void *stream);
 
+/* =====================================================================================
+ * BatchNorm shared MLP of the FlowStep3D blocks (csrc/bn_mlp.cu) -- replaces the torch-level stack of the reference's
+ * PointNetSetAbstraction / FlowEmbedding MLPs (utils/flowstep3d_util.py:52-64, :126-137): per layer Conv2d 1x1,
+ * BatchNorm2d in training mode (statistics over batch x npoint x nsample), ReLU; torch.max over nsample at the end.
+ * The contractions are ogc_pw_mlp_layer_fwd / ogc_sa_mlp_layer_dw / ogc_sa_mlp_layer_dx / ogc_pw_mlp_input_grad (their
+ * per-(sample, channel) tables hold the per-channel BatchNorm value for every sample); the entry points below make
+ * the statistics, the tables, the pooling and the backward entry.  p = m * nsample positions per sample.
+ * ===================================================================================== */
+/* sums (c,2) fp64 += [sum y, sum y^2] over (b, p) per channel (zero it first). */
+OGC_API int ogc_bn_stats(int b, int c, int p, const float *y, double *sums, void *stream);
+/* scale_shift (b,c,2) = [gamma*rstd, beta - mean*gamma*rstd] for every sample, mean_rstd (c,2); count = b*p; biased
+ * variance, eps 1e-5.  running_mean / running_var (c), when given, are updated like nn.BatchNorm2d does in training
+ * mode: (1-momentum)*old + momentum*new with the UNBIASED batch variance. */
+OGC_API int ogc_bn_finalize(int b, int c, long long count, const double *sums, const float *gamma, const float *beta,
+                            float *scale_shift, float *mean_rstd, float *running_mean, float *running_var,
+                            float momentum, void *stream);
+/* out (b,c,m) = max over nsample of relu(scale*y+shift) (scale_shift != NULL) or of y (bare convolution block);
+ * sel (b,c,m) = first winning slot, 255 = clamped by the ReLU.  nsample < 255. */
+OGC_API int ogc_bn_pool(int b, int c, int m, int nsample, const float *y, const float *scale_shift, float *out,
+                        unsigned char *sel, void *stream);
+/* dz (b,c,p) = go (b,c,m) at the winning slot, 0 elsewhere; with mean_rstd / ab given also the last layer's
+ * BatchNorm-backward sums ab (c,2) fp64 += [sum dz, sum dz*yhat] (both NULL for a bare convolution block). */
+OGC_API int ogc_bn_pool_bwd(int b, int c, int m, int nsample, const float *go, const unsigned char *sel, const float *y,
+                            const float *mean_rstd, float *dz, double *ab, void *stream);
+/* ab (c,2) fp64 += [sum dz, sum dz*yhat] of an inner layer from its ReLU-masked dz (b,c,p) and pre-norm y. */
+OGC_API int ogc_bn_bwd_stats(int b, int c, int p, const float *dz, const float *y, const float *mean_rstd, double *ab,
+                             void *stream);
+/* coef (b,c,4) = [gamma rstd, gamma rstd A/count, gamma rstd^2 Bx/count, mean] for every sample (the dY table of
+ * ogc_sa_mlp_layer_dx / _dw); dgamma (c) += Bx, dbeta (c) += A. */
+OGC_API int ogc_bn_bwd_coef(int b, int c, long long count, const double *ab, const float *mean_rstd, const float *gamma,
+                            float *coef, float *dgamma, float *dbeta, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,6 +75,12 @@ SIGNATURES = {
     "ogc_mask_head_bwd": [_I] * 4 + [_F] + [_P] * 7,
     "ogc_softmax_transfer": [_I] * 4 + [_F] + [_P] * 5,
     "ogc_adam_step_dev": [_LL, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _P, _P],
+    "ogc_bn_stats": [_I] * 3 + [_P] * 3,
+    "ogc_bn_finalize": [_I, _I, _LL] + [_P] * 7 + [_F, _P],
+    "ogc_bn_pool": [_I] * 4 + [_P] * 5,
+    "ogc_bn_pool_bwd": [_I] * 4 + [_P] * 7,
+    "ogc_bn_bwd_stats": [_I] * 3 + [_P] * 5,
+    "ogc_bn_bwd_coef": [_I, _I, _LL] + [_P] * 7,
 }
 
 _lib = None

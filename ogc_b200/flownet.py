@@ -13,6 +13,23 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 import pointnet2.pointnet2 as ops
+from ogc_b200 import backend as _backend_mod
+from ogc_b200 import bn_fused
+
+USE_FUSED_MLP = True     # the blocks' (conv1x1, BatchNorm, ReLU) x L + max over nsample through csrc/bn_mlp.cu and the
+                         # pointwise contraction kernels (ogc_b200/bn_fused.py); False: torch matmul + BatchNorm2d (tests)
+
+
+def _fused_mlp_ok(x, convs, bns, use_act):
+    """The fused block covers CUDA tensors on the b200 back-end, BatchNorm in training mode (batch statistics: the
+    reference trains and evaluates its flow network that way only in train(); eval() takes the composed path)."""
+    if not (USE_FUSED_MLP and x.is_cuda and x.dtype == torch.float32 and x.shape[0] > 0):
+        return False
+    if getattr(_backend_mod.get_backend(), "name", "") != "b200":
+        return False
+    if use_act and not all(bn.training and bn.affine for bn in bns):
+        return False
+    return bn_fused.supported([c.weight.shape[0] for c in convs], x.shape[-1])
 
 
 def _conv1x1(conv, x):
@@ -66,6 +83,8 @@ class FlowSA(nn.Module):
         _, idx = ops.knn(self.nsample, new_xyz_t, xyz_t)
         grouped = torch.cat([ops.grouping_operation(xyz, idx) - new_xyz.unsqueeze(-1),
                              ops.grouping_operation(points.contiguous(), idx)], dim=1)
+        if _fused_mlp_ok(grouped, self.mlp_convs, self.mlp_bns, self.use_act):
+            return new_xyz, bn_fused.fused_bn_mlp(grouped, self.mlp_convs, self.mlp_bns if self.use_act else None), fps_idx
         for conv, bn in zip(self.mlp_convs, self.mlp_bns):
             grouped = _conv1x1(conv, grouped)
             if self.use_act:
@@ -93,6 +112,8 @@ class FlowEmbedding(nn.Module):
         pos_diff = ops.grouping_operation(pos2.contiguous(), idx) - pos1.unsqueeze(-1)
         feat2 = ops.grouping_operation(feature2.contiguous(), idx)
         x = torch.cat([pos_diff, feat2, feature1.unsqueeze(-1).expand(-1, -1, -1, self.nsample)], dim=1)
+        if _fused_mlp_ok(x, self.mlp_convs, self.mlp_bns, True):
+            return bn_fused.fused_bn_mlp(x, self.mlp_convs, self.mlp_bns)
         for conv, bn in zip(self.mlp_convs, self.mlp_bns):
             x = F.relu(bn(_conv1x1(conv, x)))
         return x.max(dim=-1).values

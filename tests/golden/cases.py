@@ -58,6 +58,12 @@ FLOW_LOSS = {   # config/flow/ogcdr/ogcdr_unsup.yaml:37-52 with 3 unrolled itera
 CASES["flownet_ogcdr_512"] = {"kind": "flownet", "npoint": 512, "B": 2, "seed": 15, "iters": 3, "loss_cfg": FLOW_LOSS,
                               "grad_params": ["encoder_loc.sa1.mlp_convs.0.weight", "gru.convq.mlp_convs.0.weight",
                                               "flow_regressor.fc.weight", "global_corr_layer.epsilon"]}
+# BASELINE configs[2]'s own cloud size (ogcdr: 2048 points), one pair per sample, 2 + 3 unrolled iterations as above
+CASES["flownet_ogcdr_2048"] = {"kind": "flownet", "npoint": 2048, "B": 2, "seed": 16, "iters": 3, "loss_cfg": FLOW_LOSS,
+                               "grad_params": ["encoder_loc.sa1.mlp_convs.0.weight", "encoder_glob.sa1.mlp_bns.1.weight",
+                                               "local_corr_layer.mlp_convs.1.weight", "gru.convq.mlp_convs.0.weight",
+                                               "flow_regressor.sa1.mlp_convs.2.weight", "flow_regressor.fc.weight",
+                                               "global_corr_layer.epsilon"]}
 CASES["oa_icp"] = {"kind": "oa_icp", "B": 2, "N": 768, "K": 6, "seed": 14, "scale": 8.0, "icp_iter": 4}
 CASES["vote"] = {"kind": "vote", "T": 5, "N": 384, "K": 5, "seed": 21, "window": 3}
 

