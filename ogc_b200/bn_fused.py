@@ -16,12 +16,13 @@ No normalised / rectified tensor is materialised; only the pre-norm y_l are stor
 and `num_batches_tracked` are updated as nn.BatchNorm2d does.
 """
 import ctypes
+import os
 
 import torch
 from torch.autograd import Function
 
 from . import _lib
-from .backend import get_backend
+from .backend import TIMER, get_backend
 
 
 def _p(t):
@@ -35,6 +36,19 @@ def _st():
 def supported(widths, nsample):
     """Shapes the kernels cover: layer outputs multiples of 16 up to 256, fewer than 255 neighbour slots."""
     return nsample < 255 and all(c % 16 == 0 and c <= 256 for c in widths)
+
+
+USE_TMA = os.environ.get("OGC_BN_TMA", "0") == "1"
+# True: dense inner layers (l >= 1) through the TMA-staged tensor-core kernels of the SA block (csrc/sa_*_tma.cu, 3xTF32
+# split; the M*S positions of a sample are (M*S)/64 "centres" of 64 positions to them).  Measured on a B200: the step
+# 27.3 -> 23.8 ms, every block within 5e-7 of fp64 either way -- but the untrained recurrent network amplifies the split's
+# different rounding to 1.3e-4 on the second iteration's flow (fp32 SIMT kernels: 5e-5; parity bound 1e-4), so the
+# parity configuration keeps the fp32 kernels and bench.py reports the tensor-core variant as a labelled extra.
+
+
+def _tma_ok(P, cin, cout):
+    from . import sa_fused
+    return (USE_TMA and sa_fused.USE_TC and P % 128 == 0 and cin % 32 == 0 and cin <= 128 and cout % 32 == 0 and cout <= 128)
 
 
 class _FusedBnMlp(Function):
@@ -59,9 +73,16 @@ class _FusedBnMlp(Function):
             W = params[stride * l]
             cout, cin = W.shape[0], W.shape[1]
             y = torch.empty(B, cout, P, **f32)
-            wt = W.detach().reshape(cout, cin).t().contiguous()
-            _lib.check(lib.ogc_pw_mlp_layer_fwd(B, P, cin, cout, _p(a_prev), _p(ss_prev), _p(wt), _p(y), _p(gn_scratch), _st()),
-                       "ogc_pw_mlp_layer_fwd")
+            tma = l > 0 and use_act and _tma_ok(P, cin, cout)
+            with TIMER.span("flow_mlp_fwd_tma" if tma else "flow_mlp_fwd", B * 4 * P * (cin + cout), 2 * B * P * cin * cout):
+                if tma:
+                    w2d = W.detach().reshape(cout, cin).contiguous()
+                    _lib.check(lib.ogc_sa_fwd_tma(B, P // 64, 64, cin, cout, 0, _p(a_prev), _p(ss_prev), _p(w2d), _p(y), _p(gn_scratch),
+                                                  None, None, None, None, _st()), "ogc_sa_fwd_tma")
+                else:
+                    wt = W.detach().reshape(cout, cin).t().contiguous()       # only the SIMT kernel wants W^T
+                    _lib.check(lib.ogc_pw_mlp_layer_fwd(B, P, cin, cout, _p(a_prev), _p(ss_prev), _p(wt), _p(y), _p(gn_scratch), _st()),
+                               "ogc_pw_mlp_layer_fwd")
             be.launches += 1
             ys.append(y)
             if use_act:
@@ -69,7 +90,8 @@ class _FusedBnMlp(Function):
                 ss = torch.empty(B, cout, 2, **f32)
                 mr = torch.empty(cout, 2, **f32)
                 rm, rv, mom = running[l] if running[l] is not None else (None, None, 0.0)
-                _lib.check(lib.ogc_bn_stats(B, cout, P, _p(y), _p(sums_all[l]), _st()), "ogc_bn_stats")
+                with TIMER.span("flow_bn_stats", B * 4 * P * cout):
+                    _lib.check(lib.ogc_bn_stats(B, cout, P, _p(y), _p(sums_all[l]), _st()), "ogc_bn_stats")
                 _lib.check(lib.ogc_bn_finalize(B, cout, B * P, _p(sums_all[l]), _p(gamma.detach()), _p(beta.detach()), _p(ss),
                                                _p(mr), _p(rm), _p(rv), float(mom), _st()), "ogc_bn_finalize")
                 be.launches += 2
@@ -80,8 +102,9 @@ class _FusedBnMlp(Function):
         cL = ys[-1].shape[1]
         out = torch.empty(B, cL, M, **f32)
         sel = torch.empty(B, cL, M, dtype=torch.uint8, device=dev)
-        _lib.check(lib.ogc_bn_pool(B, cL, M, S, _p(ys[-1]), _p(sss[-1]) if use_act else None, _p(out), _p(sel), _st()),
-                   "ogc_bn_pool")
+        with TIMER.span("flow_pool", B * cL * (4 * P + 5 * M)):
+            _lib.check(lib.ogc_bn_pool(B, cL, M, S, _p(ys[-1]), _p(sss[-1]) if use_act else None, _p(out), _p(sel), _st()),
+                       "ogc_bn_pool")
         be.launches += 1
         ctx.dims = (B, M, S, L, use_act)
         ctx.param_objs = params
@@ -111,8 +134,9 @@ class _FusedBnMlp(Function):
         cmax = max(y.shape[1] for y in ys)
         dz = torch.empty(B, cL, P, **f32)
         ab_all = torch.zeros(L, cmax, 2, dtype=torch.float64, device=dev) if use_act else None
-        _lib.check(lib.ogc_bn_pool_bwd(B, cL, M, S, _p(go), _p(sel), _p(ys[-1]), _p(mrs[-1]) if use_act else None, _p(dz),
-                                       _p(ab_all[L - 1]) if use_act else None, _st()), "ogc_bn_pool_bwd")
+        with TIMER.span("flow_pool_bwd", B * cL * (4 * P + 9 * M)):
+            _lib.check(lib.ogc_bn_pool_bwd(B, cL, M, S, _p(go), _p(sel), _p(ys[-1]), _p(mrs[-1]) if use_act else None, _p(dz),
+                                           _p(ab_all[L - 1]) if use_act else None, _st()), "ogc_bn_pool_bwd")
         be.launches += 1
         if use_act:       # the dense input-gradient kernel also emits GroupNorm sums of the previous layer: parked here
             gn_mr = torch.zeros(B, 4, 2, **f32)
@@ -139,21 +163,36 @@ class _FusedBnMlp(Function):
             dW = tg[stride * l].view(cout, cin) if tg else torch.zeros(cout, cin, **f32)
             a_prev = ys[l - 1] if l else x
             ss_prev = sss[l - 1] if (l and use_act) else None
-            _lib.check(lib.ogc_sa_mlp_layer_dw(B, 0, P, 1, cout, cin, 0, _p(dz), None, 0, 0, None, _p(ys[l]), _p(coef),
-                                               _p(a_prev), _p(ss_prev), None, None, None, None, _p(dW), _st()),
-                       "ogc_sa_mlp_layer_dw")
+            tma = l > 0 and use_act and _tma_ok(P, cin, cout)
+            with TIMER.span("flow_mlp_dw_tma" if tma else "flow_mlp_dw", B * P * 4 * (2 * cout + cin), 2 * B * P * cin * cout):
+                if tma:
+                    _lib.check(lib.ogc_sa_dw_tma(B, P // 64, 64, cout, cin, _p(dz), None, 0, 0, None, _p(ys[l]), _p(coef),
+                                                 _p(a_prev), _p(ss_prev), _p(dW), _st()), "ogc_sa_dw_tma")
+                else:
+                    _lib.check(lib.ogc_sa_mlp_layer_dw(B, 0, P, 1, cout, cin, 0, _p(dz), None, 0, 0, None, _p(ys[l]), _p(coef),
+                                                       _p(a_prev), _p(ss_prev), None, None, None, None, _p(dW), _st()),
+                               "ogc_sa_mlp_layer_dw")
             be.launches += 1
             if not tg:
                 grads[stride * l] = dW.view_as(W)
             if l > 0 and use_act:
                 cprev = ys[l - 1].shape[1]
                 dz_prev = torch.empty(B, cprev, P, **f32)
-                _lib.check(lib.ogc_sa_mlp_layer_dx(
-                    B, 0, P, 1, cout, cin, 0, cprev, _p(dz), None, 0, 0, None, _p(ys[l]), _p(coef), _p(w2d),
-                    _p(ys[l - 1]), _p(sss[l - 1]), _p(gn_mr), _p(params[3 * (l - 1) + 1]), _p(dz_prev),
-                    _p(gn_ab), _p(gn_dg[0]), _p(gn_dg[1]), None, None, 0, 0, _st()), "ogc_sa_mlp_layer_dx")
-                _lib.check(lib.ogc_bn_bwd_stats(B, cprev, P, _p(dz_prev), _p(ys[l - 1]), _p(mrs[l - 1]), _p(ab_all[l - 1]),
-                                                _st()), "ogc_bn_bwd_stats")
+                tma = _tma_ok(P, cprev, cout)
+                with TIMER.span("flow_mlp_dx_tma" if tma else "flow_mlp_dx", B * P * 4 * (2 * cout + 2 * cprev), 2 * B * P * cprev * cout):
+                    if tma:
+                        _lib.check(lib.ogc_sa_dx_tma(
+                            B, P // 64, 64, cout, cin, 0, cprev, _p(dz), None, 0, 0, None, _p(ys[l]), _p(coef), _p(w2d),
+                            _p(ys[l - 1]), _p(sss[l - 1]), _p(gn_mr), _p(params[3 * (l - 1) + 1]), _p(dz_prev),
+                            _p(gn_ab), _p(gn_dg[0]), _p(gn_dg[1]), _st()), "ogc_sa_dx_tma")
+                    else:
+                        _lib.check(lib.ogc_sa_mlp_layer_dx(
+                            B, 0, P, 1, cout, cin, 0, cprev, _p(dz), None, 0, 0, None, _p(ys[l]), _p(coef), _p(w2d),
+                            _p(ys[l - 1]), _p(sss[l - 1]), _p(gn_mr), _p(params[3 * (l - 1) + 1]), _p(dz_prev),
+                            _p(gn_ab), _p(gn_dg[0]), _p(gn_dg[1]), None, None, 0, 0, _st()), "ogc_sa_mlp_layer_dx")
+                with TIMER.span("flow_bn_bwd_stats", B * P * 8 * cprev):
+                    _lib.check(lib.ogc_bn_bwd_stats(B, cprev, P, _p(dz_prev), _p(ys[l - 1]), _p(mrs[l - 1]), _p(ab_all[l - 1]),
+                                                    _st()), "ogc_bn_bwd_stats")
                 be.launches += 2
                 dz = dz_prev
             elif l > 0:
@@ -170,8 +209,9 @@ class _FusedBnMlp(Function):
                 d_x = torch.empty(B, cin, P, **f32)
                 for off in range(0, cin, 128):
                     rows = min(128, cin - off)
-                    _lib.check(lib.ogc_pw_mlp_input_grad(B, P, cout, cin, off, rows, _p(dz), _p(ys[0]), _p(coef), _p(w2d),
-                                                         _p(d_x), cin, off, _st()), "ogc_pw_mlp_input_grad")
+                    with TIMER.span("flow_mlp_dx", B * P * 4 * (2 * cout + rows), 2 * B * P * rows * cout):
+                        _lib.check(lib.ogc_pw_mlp_input_grad(B, P, cout, cin, off, rows, _p(dz), _p(ys[0]), _p(coef), _p(w2d),
+                                                           _p(d_x), cin, off, _st()), "ogc_pw_mlp_input_grad")
                     be.launches += 1
                 d_x = d_x.view(B, cin, M, S)
         return (d_x, None, None, *grads)

@@ -36,6 +36,7 @@ def run(device, iters, CASE=CASE):
 def check(preds, loss, d, grads, prefix, tol, gtol, G=G):
     for i, p in enumerate(preds):
         err = float(np.abs(p - G["flow%d" % i]).max())
+        print(f"flow prediction {i}: max |diff| {err:.2e} (|flow| up to {float(np.abs(G['flow%d' % i]).max()):.2f})")
         assert err <= tol, f"flow prediction {i}: {err:.2e}"
     ref = float(G[prefix + "loss"])
     assert abs(loss - ref) <= 10 * tol * max(1.0, abs(ref)), (loss, ref)

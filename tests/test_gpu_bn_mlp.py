@@ -45,9 +45,13 @@ def _reference(x, convs, bns, use_act):
     return x.max(dim=-1).values
 
 
+@pytest.mark.parametrize("tma", [True, False])
 @pytest.mark.parametrize("B,cin,M,S,widths,use_act", SHAPES)
-def test_fused_bn_mlp_matches_fp64_torch(b200, B, cin, M, S, widths, use_act):
+def test_fused_bn_mlp_matches_fp64_torch(b200, monkeypatch, B, cin, M, S, widths, use_act, tma):
+    """tma: dense inner layers through the TMA-staged tensor-core kernels (3xTF32) where the shape allows (positions a
+    multiple of 128, widths multiples of 32) / everything through the fp32 SIMT kernels."""
     from ogc_b200 import bn_fused
+    monkeypatch.setattr(bn_fused, "USE_TMA", tma)
     assert bn_fused.supported(widths, S)
     g = torch.Generator().manual_seed(B * 1000 + cin)
     x = (torch.randn(B, cin, M, S, generator=g) * 0.7 + 0.1).cuda()
@@ -128,8 +132,10 @@ def test_flownet_fused_blocks_match_composed_blocks(b200):
 
     pf, gf, sf = run(True)
     pc, gc, sc = run(False)
-    for a, b in zip(pf, pc):
-        assert float((a - b).abs().max()) <= 1e-4
+    for a, b in zip(pf, pc):       # untrained network: flows of magnitude ~2; 1e-4 of the range
+        err = float((a - b).abs().max() / b.abs().max())
+        print(f"flow prediction: {err:.2e} of the range")
+        assert err <= 1e-4
     assert set(gf) == set(gc)
     worst = max(float((gf[n] - gc[n]).norm() / gc[n].norm().clamp_min(1e-12)) for n in gc)
     print(f"worst relative gradient difference {worst:.2e}")
