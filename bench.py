@@ -509,7 +509,7 @@ def main():
             del step
             torch.cuda.empty_cache()
             from ogc_b200 import bn_fused
-            bn_fused.USE_TMA = True
+            prev_tma, bn_fused.USE_TMA = bn_fused.USE_TMA, True
             try:
                 step_tc, _ = flow_step_fn(npoint, batch, iters, device)
                 ms_tc, _ = time_cuda(step_tc, args.steps, max(args.warmup, 3))
@@ -518,7 +518,7 @@ def main():
                     "note": "bn_fused.USE_TMA = True (OGC_BN_TMA=1): not the parity configuration (flow golden 1.3e-4 vs the 1e-4 bound)"}
                 del step_tc
             finally:
-                bn_fused.USE_TMA = False
+                bn_fused.USE_TMA = prev_tma
             if not args.no_ref_ext:
                 ref = ref_arm("flow", "--npoint", npoint, "--batch", batch, "--iters", iters, "--steps", 10, "--warmup", 3)
                 if "value" in ref:

@@ -38,17 +38,21 @@ def supported(widths, nsample):
     return nsample < 255 and all(c % 16 == 0 and c <= 256 for c in widths)
 
 
-USE_TMA = os.environ.get("OGC_BN_TMA", "0") == "1"
-# True: dense inner layers (l >= 1) through the TMA-staged tensor-core kernels of the SA block (csrc/sa_*_tma.cu, 3xTF32
-# split; the M*S positions of a sample are (M*S)/64 "centres" of 64 positions to them).  Measured on a B200: the step
-# 27.3 -> 23.8 ms, every block within 5e-7 of fp64 either way -- but the untrained recurrent network amplifies the split's
-# different rounding to 1.3e-4 on the second iteration's flow (fp32 SIMT kernels: 5e-5; parity bound 1e-4), so the
-# parity configuration keeps the fp32 kernels and bench.py reports the tensor-core variant as a labelled extra.
+USE_TMA = {"0": False, "1": True}.get(os.environ.get("OGC_BN_TMA", "bwd"), "bwd")
+# The dense inner layers (l >= 1) can run the TMA-staged tensor-core kernels of the SA block (csrc/sa_*_tma.cu, 3xTF32
+# split; the M*S positions of a sample are (M*S)/64 "centres" of 64 positions to them): False = nowhere, "bwd" = weight /
+# input gradients only, True = forward too.  Measured on a B200 with True: the step 27.3 -> 23.7 ms, every block within
+# 5e-7 of fp64 either way -- but the untrained recurrent network amplifies the split's different rounding in the FORWARD
+# to 1.3e-4 on the second iteration's flow (fp32 SIMT kernels: 5e-5; parity bound 1e-4).  "bwd" (the default) leaves every
+# forward value and decision (ReLU masks, arg-max slots, neighbour sets) untouched -- same golden errors as False, flows and
+# gradients -- and keeps most of the gain: 24.0 ms.
 
 
-def _tma_ok(P, cin, cout):
+def _tma_ok(P, cin, cout, fwd=False):
     from . import sa_fused
-    return (USE_TMA and sa_fused.USE_TC and P % 128 == 0 and cin % 32 == 0 and cin <= 128 and cout % 32 == 0 and cout <= 128)
+    if not (USE_TMA is True or (USE_TMA == "bwd" and not fwd)):
+        return False
+    return sa_fused.USE_TC and P % 128 == 0 and cin % 32 == 0 and cin <= 128 and cout % 32 == 0 and cout <= 128
 
 
 class _FusedBnMlp(Function):
@@ -73,7 +77,7 @@ class _FusedBnMlp(Function):
             W = params[stride * l]
             cout, cin = W.shape[0], W.shape[1]
             y = torch.empty(B, cout, P, **f32)
-            tma = l > 0 and use_act and _tma_ok(P, cin, cout)
+            tma = l > 0 and use_act and _tma_ok(P, cin, cout, fwd=True)
             with TIMER.span("flow_mlp_fwd_tma" if tma else "flow_mlp_fwd", B * 4 * P * (cin + cout), 2 * B * P * cin * cout):
                 if tma:
                     w2d = W.detach().reshape(cout, cin).contiguous()

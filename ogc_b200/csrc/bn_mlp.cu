@@ -62,18 +62,17 @@ bn_stats_kernel(int C, int P, const float *__restrict__ y, double *__restrict__ 
 __global__ void bn_finalize_kernel(int B, int C, double n, const double *__restrict__ sums, const float *__restrict__ gamma,
                                    const float *__restrict__ beta, float *__restrict__ ss, float *__restrict__ mean_rstd,
                                    float *__restrict__ running_mean, float *__restrict__ running_var, float momentum) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;      // thread = (sample, channel): every sample's table entry is
+    if (i >= B * C) return;                                     // computed by its own thread (same inputs, same value)
+    const int b = i / C, c = i - b * C;
     const double mean = sums[c * 2] / n;
     double var = sums[c * 2 + 1] / n - mean * mean;
     var = var > 0 ? var : 0;
     const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(kBnEps)));
     const float sc = gamma[c] * rstd;
-    const float sh = beta[c] - static_cast<float>(mean) * sc;
-    for (int b = 0; b < B; ++b) {
-        ss[(static_cast<size_t>(b) * C + c) * 2] = sc;
-        ss[(static_cast<size_t>(b) * C + c) * 2 + 1] = sh;
-    }
+    ss[static_cast<size_t>(i) * 2] = sc;
+    ss[static_cast<size_t>(i) * 2 + 1] = beta[c] - static_cast<float>(mean) * sc;
+    if (b != 0) return;
     mean_rstd[c * 2] = static_cast<float>(mean);
     mean_rstd[c * 2 + 1] = rstd;
     if (running_mean && running_var) {
@@ -184,14 +183,16 @@ bn_bwd_stats_kernel(int C, int P, const float *__restrict__ dz, const float *__r
 __global__ void bn_bwd_coef_kernel(int B, int C, double n, const double *__restrict__ ab, const float *__restrict__ mean_rstd,
                                    const float *__restrict__ gamma, float *__restrict__ coef, float *__restrict__ dgamma,
                                    float *__restrict__ dbeta) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;      // thread = (sample, channel), as bn_finalize_kernel
+    if (i >= B * C) return;
+    const int b = i / C, c = i - b * C;
     const double A = ab[c * 2], Bx = ab[c * 2 + 1];
     const float mean = mean_rstd[c * 2], rstd = mean_rstd[c * 2 + 1];
     const float k1 = gamma[c] * rstd;
-    const float4 v = make_float4(k1, static_cast<float>(static_cast<double>(k1) * A / n),
-                                 static_cast<float>(static_cast<double>(k1) * rstd * Bx / n), mean);
-    for (int b = 0; b < B; ++b) *reinterpret_cast<float4 *>(coef + (static_cast<size_t>(b) * C + c) * 4) = v;
+    *reinterpret_cast<float4 *>(coef + static_cast<size_t>(i) * 4) =
+        make_float4(k1, static_cast<float>(static_cast<double>(k1) * A / n),
+                    static_cast<float>(static_cast<double>(k1) * rstd * Bx / n), mean);
+    if (b != 0) return;
     atomicAdd(dgamma + c, static_cast<float>(Bx));
     atomicAdd(dbeta + c, static_cast<float>(A));
 }
@@ -214,7 +215,7 @@ extern "C" int ogc_bn_finalize(int b, int c, long long count, const double *sums
     using namespace ogc;
     if (b <= 0 || c <= 0 || count <= 0) return OGC_ERR_INVALID_ARG;
     if (!sums || !gamma || !beta || !scale_shift || !mean_rstd) return OGC_ERR_INVALID_ARG;
-    bn_finalize_kernel<<<(c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+    bn_finalize_kernel<<<(b * c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
         b, c, static_cast<double>(count), sums, gamma, beta, scale_shift, mean_rstd, running_mean, running_var, momentum);
     OGC_RETURN_LAUNCH_STATUS();
 }
@@ -259,7 +260,7 @@ extern "C" int ogc_bn_bwd_coef(int b, int c, long long count, const double *ab, 
     using namespace ogc;
     if (b <= 0 || c <= 0 || count <= 0) return OGC_ERR_INVALID_ARG;
     if (!ab || !mean_rstd || !gamma || !coef || !dgamma || !dbeta) return OGC_ERR_INVALID_ARG;
-    bn_bwd_coef_kernel<<<(c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+    bn_bwd_coef_kernel<<<(b * c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
         b, c, static_cast<double>(count), ab, mean_rstd, gamma, coef, dgamma, dbeta);
     OGC_RETURN_LAUNCH_STATUS();
 }

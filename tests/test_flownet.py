@@ -61,6 +61,7 @@ def test_flownet_state_dict_names_match_reference_layout():
 def test_flownet_composed_cpu_matches_reference(oracle_ops):
     check(*run("cpu", 3), prefix="", tol=1e-5, gtol=1e-4)
     check(*run("cpu", 2), prefix="i2:", tol=1e-5, gtol=1e-4)
+    check(*run("cpu", 2, CASE2048), prefix="i2:", tol=1e-5, gtol=1e-4, G=G2048)      # configs[2]'s own cloud size
 
 
 @pytest.mark.gpu

@@ -45,11 +45,11 @@ def _reference(x, convs, bns, use_act):
     return x.max(dim=-1).values
 
 
-@pytest.mark.parametrize("tma", [True, False])
+@pytest.mark.parametrize("tma", [True, "bwd", False])
 @pytest.mark.parametrize("B,cin,M,S,widths,use_act", SHAPES)
 def test_fused_bn_mlp_matches_fp64_torch(b200, monkeypatch, B, cin, M, S, widths, use_act, tma):
     """tma: dense inner layers through the TMA-staged tensor-core kernels (3xTF32) where the shape allows (positions a
-    multiple of 128, widths multiples of 32) / everything through the fp32 SIMT kernels."""
+    multiple of 128, widths multiples of 32) / their gradients only / everything through the fp32 SIMT kernels."""
     from ogc_b200 import bn_fused
     monkeypatch.setattr(bn_fused, "USE_TMA", tma)
     assert bn_fused.supported(widths, S)
