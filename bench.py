@@ -31,7 +31,8 @@ exchange one NCCL all-reduce (grads + NaN counter).
                                                                                                             } libogc_b200 only
 Other configs (`--config`): train8 = configs[3] (8 pairs/GPU); strong32 = 32 clouds split over the ranks (strong
 scaling); oa_icp = configs[4] (64 clouds, icp_iter 20; the reference runs chunks of 4); ogcdr_flow[4096] = configs[2]
-(FlowStep3D b=16 iters=4 + flow loss + backward + Adam at 2048 / 4096 points); sapien_cpu = configs[0] (CPU plumbing).
+(FlowStep3D b=16 iters=4 + flow loss + backward + Adam at 2048 / 4096 points; `ops` / `roofline` from two eager steps,
+the 3xTF32-forward variant as a labelled extra); sapien_cpu = configs[0] (CPU plumbing).
 stdout carries exactly the JSON line (library banners go to stderr).
 """
 import argparse

@@ -4,7 +4,9 @@ building blocks of utils/flowstep3d_util.py:7-184) on the B200 operator set (BAS
 Spec-driven: every set-abstraction block of the reference is one `FlowSA` instance created from a table, parameter
 names are the reference's (`encoder_loc.sa1.mlp_convs.0.weight`, `...mlp_bns.0.running_mean`, `gru.convz...`,
 `global_corr_layer.epsilon`, `flow_regressor.fc.weight`), so reference checkpoints load with load_state_dict.
-Differences (behaviour-preserving): furthest-point sampling of an unchanged cloud with an unchanged npoint is
+On the GPU the blocks' shared MLPs (conv1x1 -> BatchNorm2d -> ReLU, x L, max over nsample) run fused through
+ogc_b200/bn_fused.py (csrc/bn_mlp.cu + the pointwise contraction kernels); the torch expression below them is the CPU /
+eval-mode path.  Differences (behaviour-preserving): furthest-point sampling of an unchanged cloud with an unchanged npoint is
 memoised inside one forward pass (the reference recomputes the same FPS ~7 times per GRU iteration),
 and the dead `knn=False` branch of FlowEmbedding (Appendix C.2) is not carried over.
 """
