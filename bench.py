@@ -496,8 +496,16 @@ def main():
                 top = max(fam, key=lambda k: op_rows[k]["ms_per_step"])
                 r = op_rows[top]
                 fp32_peak = 2 * 128 * 148 * 1965.0e6 / 1e12      # FFMA: 128 lanes x 2 flops per SM per clock at the 1965 MHz boost clock
+                tr = {}
+                tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+                if os.path.exists(tpath):
+                    tr = json.load(open(tpath)).get(top, {})
                 line["roofline"] = {"kernel": top, "bound": "hbm", "achieved": r["alg_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                    "frac": r["alg_gbs"] / peaks["hbm_gbs"], "peak_how": peak_src, "traffic": None,
+                                    "frac": r["alg_gbs"] / peaks["hbm_gbs"], "peak_how": peak_src,
+                                    "traffic": tr.get("dram_bytes_per_launch"),
+                                    "traffic_note": ("ncu DRAM bytes per launch of this family in ONE representative block (16 x 67>64>64>64 x "
+                                                     f"8192 positions), whose algorithmic bytes per launch are {tr['alg_bytes_same_launches']:.3g}: "
+                                                     + tr.get("note", "")) if tr else None,
                                     "alg_bytes_per_launch": r["alg_bytes_per_launch"], "share_of_step": r["ms_per_step"] / ms,
                                     "fp32_simt_tflops": r.get("useful_tflops"), "fp32_simt_peak_tflops": fp32_peak,
                                     "fp32_simt_frac": (r.get("useful_tflops") or 0.0) / fp32_peak,

@@ -117,8 +117,9 @@ def test_flow_trainer_graph_replay_equals_eager(b200):
           f"graph vs eager: logs {dev(le, lg):.2e} params {float((pe - pg).abs().max()):.2e} "
           f"bn {float((be_ - bg).abs().max()) / float(be_.abs().max()):.2e}")
     # steps 1-2 run on parameters that already differ by such +-lr moves, and the third unrolled iteration amplifies them
-    # (module docstring: 1e-5 -> 1e-2): a floor of 2e-2 on top of the measured eager-vs-eager spread
-    assert dev(le, lg) <= 5 * noise_l + 2e-2
+    # (module docstring: 1e-5 -> 1e-2; eager-vs-eager spreads of 5e-3 ... 4e-2 were measured on a B200): a floor of 5e-2 on
+    # top of the measured eager-vs-eager spread (a replay that does not train, or trains on stale buffers, is off by 0.5)
+    assert dev(le, lg) <= 5 * noise_l + 5e-2
     assert float((pe - pg).abs().max()) <= 5 * noise_p + 1e-4
     assert float((pe - pg).abs().mean()) <= 5 * float((pe - pe2).abs().mean()) + 1e-6
     assert float((be_ - bg).abs().max()) / float(be_.abs().max()) <= 5 * noise_b + 1e-4
