@@ -57,9 +57,10 @@ def _tma_ok(P, cin, cout, fwd=False):
 
 class _FusedBnMlp(Function):
     @staticmethod
-    def forward(ctx, x, use_act, running, *params):
+    def forward(ctx, x, use_act, running, no_grad_rows, *params):
         """x (B,Cin,M,S); params = (W_1, gamma_1, beta_1, ...) with use_act, (W_1, ..., W_L) without;
-        running = [(running_mean, running_var, momentum) or None per layer] (updated in place)."""
+        running = [(running_mean, running_var, momentum) or None per layer] (updated in place); the first no_grad_rows
+        channels of x get a zero gradient (the caller knows nothing upstream of them needs one)."""
         be = get_backend()
         lib = be.lib
         stride = 3 if use_act else 1
@@ -110,7 +111,7 @@ class _FusedBnMlp(Function):
             _lib.check(lib.ogc_bn_pool(B, cL, M, S, _p(ys[-1]), _p(sss[-1]) if use_act else None, _p(out), _p(sel), _st()),
                        "ogc_bn_pool")
         be.launches += 1
-        ctx.dims = (B, M, S, L, use_act)
+        ctx.dims = (B, M, S, L, use_act, no_grad_rows)
         ctx.param_objs = params
         ctx.save_for_backward(x, sel, *ys, *sss, *mrs, *[p.detach() for p in params])
         return out
@@ -119,7 +120,7 @@ class _FusedBnMlp(Function):
     def backward(ctx, go):
         be = get_backend()
         lib = be.lib
-        B, M, S, L, use_act = ctx.dims
+        B, M, S, L, use_act, skip = ctx.dims
         P = M * S
         stride = 3 if use_act else 1
         saved = ctx.saved_tensors
@@ -210,20 +211,25 @@ class _FusedBnMlp(Function):
                     be.launches += 1
                 dz = dz_prev
             elif ctx.needs_input_grad[0]:
+                # rows [skip, cin) of W^T dY; 3 + 64 input channels would otherwise land in a 128-row tile (profiles/README.md)
                 d_x = torch.empty(B, cin, P, **f32)
-                for off in range(0, cin, 128):
+                if skip:
+                    d_x[:, :skip].zero_()
+                for off in range(skip, cin, 128):
                     rows = min(128, cin - off)
                     with TIMER.span("flow_mlp_dx", B * P * 4 * (2 * cout + rows), 2 * B * P * rows * cout):
                         _lib.check(lib.ogc_pw_mlp_input_grad(B, P, cout, cin, off, rows, _p(dz), _p(ys[0]), _p(coef), _p(w2d),
-                                                           _p(d_x), cin, off, _st()), "ogc_pw_mlp_input_grad")
+                                                             _p(d_x), cin, off, _st()), "ogc_pw_mlp_input_grad")
                     be.launches += 1
                 d_x = d_x.view(B, cin, M, S)
-        return (d_x, None, None, *grads)
+        return (d_x, None, None, None, *grads)
 
 
-def fused_bn_mlp(grouped, convs, bns):
+def fused_bn_mlp(grouped, convs, bns, no_grad_rows=0):
     """grouped (B,Cin,M,S); convs = the block's nn.Conv2d 1x1 (bias=False) modules; bns = its nn.BatchNorm2d modules
-    (training mode: batch statistics, running estimates updated) or None for a bare convolution block."""
+    (training mode: batch statistics, running estimates updated) or None for a bare convolution block.
+    no_grad_rows: the leading channels of `grouped` whose gradient nobody needs (the centred coordinates of a cloud that
+    does not require grad): their gradient is returned as zeros instead of being computed."""
     use_act = bns is not None
     params, running = [], []
     for l, conv in enumerate(convs):
@@ -238,4 +244,4 @@ def fused_bn_mlp(grouped, convs, bns):
                 bn.num_batches_tracked.add_(1)
             else:
                 running.append(None)
-    return _FusedBnMlp.apply(grouped.contiguous(), use_act, running, *params)
+    return _FusedBnMlp.apply(grouped.contiguous(), use_act, running, int(no_grad_rows), *params)

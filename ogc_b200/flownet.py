@@ -86,7 +86,8 @@ class FlowSA(nn.Module):
         grouped = torch.cat([ops.grouping_operation(xyz, idx) - new_xyz.unsqueeze(-1),
                              ops.grouping_operation(points.contiguous(), idx)], dim=1)
         if _fused_mlp_ok(grouped, self.mlp_convs, self.mlp_bns, self.use_act):
-            return new_xyz, bn_fused.fused_bn_mlp(grouped, self.mlp_convs, self.mlp_bns if self.use_act else None), fps_idx
+            skip = 0 if xyz.requires_grad else 3        # the centred coordinates of a leaf cloud need no gradient
+            return new_xyz, bn_fused.fused_bn_mlp(grouped, self.mlp_convs, self.mlp_bns if self.use_act else None, skip), fps_idx
         for conv, bn in zip(self.mlp_convs, self.mlp_bns):
             grouped = _conv1x1(conv, grouped)
             if self.use_act:
@@ -115,7 +116,8 @@ class FlowEmbedding(nn.Module):
         feat2 = ops.grouping_operation(feature2.contiguous(), idx)
         x = torch.cat([pos_diff, feat2, feature1.unsqueeze(-1).expand(-1, -1, -1, self.nsample)], dim=1)
         if _fused_mlp_ok(x, self.mlp_convs, self.mlp_bns, True):
-            return bn_fused.fused_bn_mlp(x, self.mlp_convs, self.mlp_bns)
+            skip = 0 if (pos1.requires_grad or pos2.requires_grad) else 3
+            return bn_fused.fused_bn_mlp(x, self.mlp_convs, self.mlp_bns, skip)
         for conv, bn in zip(self.mlp_convs, self.mlp_bns):
             x = F.relu(bn(_conv1x1(conv, x)))
         return x.max(dim=-1).values

@@ -93,6 +93,30 @@ def test_fused_bn_mlp_matches_fp64_torch(b200, monkeypatch, B, cin, M, S, widths
         assert all(b.weight.grad is None for b in bns)
 
 
+def test_fused_bn_mlp_skips_the_gradient_of_leading_rows_on_request(b200):
+    """no_grad_rows = 3 (the centred coordinates of a leaf cloud): rows 3.. of the input gradient and every parameter
+    gradient are what the full computation gives, rows 0..2 are zeros."""
+    from ogc_b200 import bn_fused
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 67, 64, 16, generator=g).cuda()
+    probe = torch.randn(2, 64, 64, generator=g).cuda()
+    convs, bns = _block(67, [64, 64], seed=4)
+    convs, bns = convs.cuda(), bns.cuda()
+    params = list(convs.parameters()) + list(bns.parameters())
+    res = []
+    for skip in (0, 3):
+        xi = x.clone().requires_grad_(True)
+        for p in params:
+            p.grad = None
+        (bn_fused.fused_bn_mlp(xi, convs, bns, skip) * probe).sum().backward()
+        res.append((xi.grad.clone(), [p.grad.clone() for p in params]))
+    (gx0, gp0), (gx3, gp3) = res
+    assert float(gx3[:, :3].abs().max()) == 0.0
+    assert float((gx3[:, 3:] - gx0[:, 3:]).norm() / gx0[:, 3:].norm()) <= 1e-5
+    for a, b in zip(gp0, gp3):
+        assert float((a - b).norm() / a.norm().clamp_min(1e-30)) <= 1e-4
+
+
 def test_fused_bn_mlp_accumulates_into_existing_grads(b200):
     """The trainer's backward: gradients are added straight into the parameters' .grad (sa_fused.grad_targets); a block
     used twice in one forward (the reference re-applies its encoders every GRU iteration) sums both uses."""
