@@ -120,3 +120,24 @@ def test_ball_query_and_fps_through_api(oracle_ops, oracle):
     idx = oracle_ops.ball_query(0.7, 12, xyz, new_xyz)
     assert torch.equal(idx, oracle.ball_query(0.7, 12, xyz, new_xyz))
     assert (idx[:, :, 0] <= sel).all()   # the first hit is the LOWEST index in the ball, at most the centre's own
+
+
+def test_flow_block_fusion_is_gpu_only_host_logic(monkeypatch):
+    """Host logic of the FlowStep3D block fusion (ogc_b200/bn_fused.py, flownet._fused_mlp_ok): CPU tensors, eval-mode
+    BatchNorm and unsupported widths take the torch-composed path (there is no CPU fallback INSIDE the fused path: it
+    would raise on the missing device pointers); the tensor-core switch parses its three settings."""
+    import importlib
+    import torch
+    import torch.nn as nn
+    from ogc_b200 import bn_fused, flownet
+    assert bn_fused.supported([16, 32, 64, 128], 16) and bn_fused.supported([256], 4)
+    assert not bn_fused.supported([24], 16) and not bn_fused.supported([512], 16) and not bn_fused.supported([64], 255)
+    sa = flownet.FlowSA(8, 4, 3, [32, 32])
+    x = torch.zeros(2, 6, 8, 4)
+    assert not flownet._fused_mlp_ok(x, sa.mlp_convs, sa.mlp_bns, True)            # CPU tensor
+    for value, want in (("0", False), ("1", True), ("bwd", "bwd"), ("", "bwd")):
+        monkeypatch.setenv("OGC_BN_TMA", value)
+        assert importlib.reload(bn_fused).USE_TMA == want
+    monkeypatch.delenv("OGC_BN_TMA")
+    assert importlib.reload(bn_fused).USE_TMA == "bwd"
+    assert isinstance(sa.mlp_bns[0], nn.BatchNorm2d)
