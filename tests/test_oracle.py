@@ -234,3 +234,48 @@ def test_three_interpolate_rounding_order(oracle):
     # float(Fraction) rounds to double first; the extra rounding can differ only in astronomically rare
     # half-way cases, not for these constants.
     assert got == t
+
+
+@pytest.mark.parametrize("B,cin,M,S,widths,use_act", [(2, 6, 12, 4, [16, 16], True), (3, 35, 10, 5, [32, 16, 16], True),
+                                                       (2, 22, 9, 4, [16], False)])
+def test_flow_mlp_oracle_matches_torch_autograd(B, cin, M, S, widths, use_act):
+    """oracle/flow_mlp_oracle.py (the BatchNorm shared MLP of the FlowStep3D blocks, utils/flowstep3d_util.py:126-137, in
+    the statistics / coefficient form csrc/bn_mlp.cu evaluates) against torch's own modules and autograd in fp64."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from oracle import flow_mlp_oracle as O
+    g = torch.Generator().manual_seed(B * 100 + cin)
+    x = torch.randn(B, cin, M, S, generator=g, dtype=torch.float64, requires_grad=True)
+    probe = torch.randn(B, widths[-1], M, generator=g, dtype=torch.float64)
+    convs, bns, last = [], [], cin
+    for c in widths:
+        convs.append(nn.Conv2d(last, c, 1, bias=False).double())
+        bn = nn.BatchNorm2d(c).double()
+        with torch.no_grad():
+            bn.weight.add_(0.3 * torch.randn(c, generator=g, dtype=torch.float64))
+            bn.bias.add_(0.2 * torch.randn(c, generator=g, dtype=torch.float64))
+        bns.append(bn)
+        last = c
+    running = [(bn.running_mean.clone().numpy(), bn.running_var.clone().numpy()) for bn in bns]
+    h = x
+    for conv, bn in zip(convs, bns):
+        h = conv(h)
+        if use_act:
+            h = F.relu(bn(h))
+    ref = h.max(dim=-1).values
+    (ref * probe).sum().backward()
+
+    Ws = [c.weight.detach().numpy().reshape(c.weight.shape[0], -1) for c in convs]
+    gam = [b.weight.detach().numpy() for b in bns] if use_act else None
+    bet = [b.bias.detach().numpy() for b in bns] if use_act else None
+    out, cache = O.forward(x.detach().numpy(), Ws, gam, bet, running if use_act else None)
+    dx, dWs, dgs, dbs = O.backward(probe.numpy(), cache)
+    close = lambda a, b: np.allclose(a, b, rtol=1e-9, atol=1e-11)
+    assert close(out, ref.detach().numpy())
+    assert close(dx, x.grad.numpy())
+    for l, c in enumerate(convs):
+        assert close(dWs[l], c.weight.grad.numpy().reshape(dWs[l].shape))
+    if use_act:
+        for l, b in enumerate(bns):
+            assert close(dgs[l], b.weight.grad.numpy()) and close(dbs[l], b.bias.grad.numpy())
+            assert close(running[l][0], b.running_mean.numpy()) and close(running[l][1], b.running_var.numpy())
